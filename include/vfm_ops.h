@@ -1,0 +1,244 @@
+/*
+ * vfm_ops.h -- C ABI of libvfmops.so: the B200 (sm_100a) kernels behind the VFM-VAE pixel-decoder ops.
+ *
+ * This is the drop-in boundary.  Every entry point below is what the reference's pybind plugin function
+ * for the same op would bind if the plugin were a C library; the reference-side bindings a maintainer
+ * would add are shown in INTEGRATION.md.  Reference interfaces replaced (paths relative to the
+ * reference repo tianciB/VFM-VAE):
+ *
+ *   vfm_bias_act               <- bias_act(x,b,xref,yref,dy,grad,dim,act,alpha,gain,clamp)      torch_utils/ops/bias_act.cpp:32-90
+ *   vfm_upfirdn2d              <- upfirdn2d(x,f,upx,upy,downx,downy,padx0..pady1,flip,gain)     torch_utils/ops/upfirdn2d.cpp:16-98
+ *   vfm_filtered_lrelu         <- filtered_lrelu(x,fu,fd,b,si,up,down,px0..py1,sx,sy,gain,...)   torch_utils/ops/filtered_lrelu.cpp:16-208
+ *   vfm_filtered_lrelu_act     <- filtered_lrelu_act_(x,si,sx,sy,gain,slope,clamp,writeSigns)   torch_utils/ops/filtered_lrelu.cpp:213-290
+ *   vfm_modconv_forward/_backward <- modulated_conv2d(...) + its stock-autograd backward        networks/generator.py:46-103
+ *                                    (the reference has no native code for this op: it is Python over a grouped
+ *                                    cuDNN conv, torch_utils/ops/conv2d_resample.py:46-141)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All data pointers are DEVICE pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - the library never allocates device memory and never synchronises; scratch space is passed in by the
+ *     caller (vfm_modconv_workspace_bytes tells how much).  All launches are stream-ordered and there is no
+ *     global mutable device state (unlike the reference's filtered_lrelu __constant__ filter buffer,
+ *     torch_utils/ops/filtered_lrelu.cu:77-78), so concurrent use from several streams is safe.
+ *   - return value: 0 = launched; negative = error, nothing launched (VFM_ERR_*).  VFM_ERR_NO_KERNEL mirrors the
+ *     reference's `return_code = -1` ("no optimised kernel, use the generic composition",
+ *     torch_utils/ops/filtered_lrelu.cpp:52-56).
+ *   - sizes/strides are in ELEMENTS unless a field says bytes.
+ */
+#ifndef VFM_OPS_H
+#define VFM_OPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VFM_API __attribute__((visibility("default")))
+#else
+#define VFM_API
+#endif
+
+enum vfm_dtype { VFM_F16 = 0, VFM_F32 = 1, VFM_F64 = 2 };
+
+enum vfm_status {
+    VFM_OK = 0,
+    VFM_ERR_NO_KERNEL = -1,   /* no specialised kernel for these parameters */
+    VFM_ERR_INVALID = -2,     /* argument check failed (see vfm_last_error) */
+    VFM_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed (see vfm_last_error) */
+    VFM_ERR_WORKSPACE = -4    /* workspace missing or too small */
+};
+
+/* Human-readable description of the last error on the calling thread ("" if none). */
+VFM_API const char* vfm_last_error(void);
+VFM_API int vfm_abi_version(void);
+/* Number of kernels this library has launched in this process (all ops); bench.py reports the delta. */
+VFM_API uint64_t vfm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bias_act: y = clamp(act(x + b) * gain, +-clamp)            (grad = 0)
+ *           dx = dy * act'(.) * gain, 0 where |yref| >= clamp (grad = 1; here `x` is the incoming gradient)
+ *           second-order term                                 (grad = 2; `x` = d_dx, `dy` = first-order dy)
+ * Same argument meaning as the reference kernel parameters (torch_utils/ops/bias_act.h:12-34):
+ * the bias index of flat element i is (i / step_b) % size_b.
+ * Extension: if `db` is non-NULL (fp32[size_b], must be zero-initialised by the caller) the kernel also
+ * accumulates the bias gradient sum_{all but dim} y into it with warp-shuffle + block reductions, which
+ * replaces the separate `dx.sum(...)` reduction at torch_utils/ops/bias_act.py:170.
+ */
+typedef struct {
+    const void* x;      /* [size_x] */
+    const void* b;      /* [size_b] or NULL */
+    const void* xref;   /* [size_x] or NULL */
+    const void* yref;   /* [size_x] or NULL */
+    const void* dy;     /* [size_x] or NULL */
+    void*       y;      /* [size_x] out */
+    float*      db;     /* [size_b] fp32 accumulate, or NULL */
+    int32_t     dtype;  /* vfm_dtype of x/b/xref/yref/dy/y */
+    int32_t     grad;   /* 0, 1, 2 */
+    int32_t     act;    /* 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish */
+    float       alpha;
+    float       gain;
+    float       clamp;  /* < 0 = off */
+    int64_t     size_x;
+    int64_t     size_b;
+    int64_t     step_b;
+} vfm_bias_act_params;
+
+VFM_API int vfm_bias_act(const vfm_bias_act_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * upfirdn2d: zero-insert by (upx,upy) -> pad/crop -> FIR -> decimate by (downx,downy), per (n,c) plane.
+ * out = (in*up + pad0 + pad1 - taps + down) / down   (the caller computes it, torch_utils/ops/upfirdn2d.cpp:35-36).
+ * Any element strides (NCHW or channels_last).  Filter is fp32 [fh,fw] with its own strides.
+ */
+typedef struct {
+    const void*  x;
+    const float* f;
+    void*        y;
+    int32_t      dtype;
+    int32_t      upx, upy, downx, downy;
+    int32_t      padx0, pady0;          /* only the leading pads matter once the output size is fixed */
+    int32_t      flip;                  /* 0 = true convolution, 1 = correlation */
+    float        gain;
+    int32_t      in_w, in_h, channels, batch;
+    int64_t      in_stride_w, in_stride_h, in_stride_c, in_stride_n;
+    int32_t      fw, fh;
+    int64_t      f_stride_w, f_stride_h;
+    int32_t      out_w, out_h;
+    int64_t      out_stride_w, out_stride_h, out_stride_c, out_stride_n;
+    /* Extension (NULL = off): fp32 addend broadcast over c: y += add[n*add_stride_n + oy*add_stride_h + ox]
+     * (add_stride_n = 0 broadcasts over n too).  Used by the up=2 modulated conv to fold the `x.add_(noise)` of
+     * networks/generator.py:101-102 into the blur. */
+    const float* add;
+    int64_t      add_stride_h;
+    int64_t      add_stride_n;
+} vfm_upfirdn2d_params;
+
+VFM_API int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * filtered_lrelu: y = down_fd( clamp( lrelu( up_fu(x + b) * up^2 * gain ), +-clamp ) ), one fused kernel.
+ * Sign tensor: uint8 [N,C,s_h,s_w_bytes], 2 bits per element of the upsampled intermediate, 4 per byte,
+ * bit0 = negative, bit1 = clamped -- the reference format (torch_utils/ops/filtered_lrelu.cpp:87-94,
+ * filtered_lrelu.cu:494-505) so tensors saved by either implementation are interchangeable.
+ * fu/fd: fp32, separable when f*_h == 0 ([taps]) else full 2-D [h,w].
+ * Returns VFM_ERR_NO_KERNEL when the parameters are outside what the fused kernel supports (up/down not in
+ * {1,2,4}, more than 32 taps, fp64): the caller then composes upfirdn2d + vfm_filtered_lrelu_act + upfirdn2d
+ * exactly as the reference does (torch_utils/ops/filtered_lrelu.py:223-229).
+ */
+typedef struct {
+    const void*  x;
+    void*        y;
+    const void*  b;          /* [C] same dtype as x (never NULL; zeros if no bias) */
+    uint8_t*     s;          /* signs in/out or NULL */
+    const float* fu;
+    const float* fd;
+    int32_t      dtype;
+    int32_t      up, down;
+    int32_t      fu_w, fu_h; /* fu_h == 0 -> separable */
+    int32_t      fd_w, fd_h;
+    int64_t      fu_stride_w, fu_stride_h, fd_stride_w, fd_stride_h;
+    int32_t      pad_x0, pad_y0;
+    float        gain, slope, clamp;
+    int32_t      flip;
+    int32_t      write_signs, read_signs;
+    int32_t      x_w, x_h, channels, batch;
+    int64_t      x_stride_w, x_stride_h, x_stride_c, x_stride_n;
+    int32_t      y_w, y_h;
+    int64_t      y_stride_w, y_stride_h, y_stride_c, y_stride_n;
+    int64_t      b_stride;
+    int32_t      s_w_bytes, s_h;   /* sign tensor row length in bytes and height */
+    int32_t      s_ofs_x, s_ofs_y; /* offset between upsampled coordinates and sign coordinates */
+    int32_t      s_w_active;       /* active width in ELEMENTS (write: yw*down-(down-1)+fd_w-1; read: s_w_bytes*4) */
+} vfm_filtered_lrelu_params;
+
+VFM_API int vfm_filtered_lrelu(const vfm_filtered_lrelu_params* p, void* stream);
+
+/* In-place gain * lrelu * clamp with sign write/read, used by the generic composition. */
+typedef struct {
+    void*    x;
+    uint8_t* s;
+    int32_t  dtype;
+    float    gain, slope, clamp;
+    int32_t  write_signs, read_signs;
+    int32_t  x_w, x_h, channels, batch;
+    int64_t  x_stride_w, x_stride_h, x_stride_c, x_stride_n;
+    int32_t  s_w, s_h;             /* sign tensor width in ELEMENTS (multiple of 4) and height */
+    int32_t  s_ofs_x, s_ofs_y;
+} vfm_filtered_lrelu_act_params;
+
+VFM_API int vfm_filtered_lrelu_act(const vfm_filtered_lrelu_act_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * modulated_conv2d (networks/generator.py:46-103), k in {1,3} (any odd k on the generic path), up in {1,2}, down = 1.
+ *
+ *   w'[n,o,i,k] = weight[o,i,k] * styles[n,i];  d[n,o] = rsqrt(sum_{i,k} w'^2 + 1e-8)  (demodulate)
+ *   y[n,o]      = d[n,o] * conv2d_resample(x[n] * styles[n], weight) + noise
+ *
+ * The modulation is applied to the activation operand and the demodulation in the GEMM epilogue, so the
+ * [N,O,I,kh,kw] per-sample weight tensor of the reference is never materialised.
+ * fp16 inputs with demodulate use the reference's overflow pre-normalisation (generator.py:66-68) internally.
+ * x, y: NCHW contiguous, `dtype`.  weight fp32 [O,I,kh,kw] contiguous; styles fp32 [N,I]; noise fp32.
+ * dcoefs: fp32 [N,O] written by forward (ones if !demodulate) and consumed by backward.
+ */
+enum vfm_noise_mode { VFM_NOISE_NONE = 0, VFM_NOISE_HW = 1 /* [Hout,Wout] */, VFM_NOISE_N1HW = 2 /* [N,1,Hout,Wout] */ };
+
+typedef struct {
+    int32_t      dtype;
+    int32_t      batch, in_channels, out_channels, in_h, in_w, kh, kw;
+    int32_t      up;               /* 1 or 2 */
+    int32_t      padding;          /* symmetric, w.r.t. the upsampled image (kh/2 in the decoder) */
+    int32_t      demodulate;
+    int32_t      flip_weight;      /* 1 = correlation (F.conv2d), 0 = true convolution */
+    int32_t      noise_mode;
+    const float* resample_filter;  /* fp32 [fh,fw] contiguous 2-D, required when up == 2 */
+    int32_t      fw, fh;
+    int32_t      out_h, out_w;
+    int32_t      force_generic;    /* 1 = skip the tcgen05 path (used by the parity tests to cross-check both) */
+} vfm_modconv_desc;
+
+typedef struct {
+    vfm_modconv_desc d;
+    const void*  x;        /* [N,I,H,W] */
+    const float* weight;   /* [O,I,kh,kw] */
+    const float* styles;   /* [N,I] */
+    const float* noise;    /* per noise_mode or NULL */
+    void*        y;        /* [N,O,Hout,Wout] out */
+    float*       dcoefs;   /* [N,O] out */
+    void*        workspace;
+    size_t       workspace_bytes;
+} vfm_modconv_fwd_params;
+
+typedef struct {
+    vfm_modconv_desc d;
+    const void*  dy;       /* [N,O,Hout,Wout] */
+    const void*  x;        /* [N,I,H,W] */
+    const void*  y;        /* forward output (needed when demodulate: g[n,o] = sum dy*(y-noise)/d) */
+    const float* weight;
+    const float* styles;
+    const float* noise;
+    const float* dcoefs;   /* from forward */
+    void*        dx;       /* [N,I,H,W] out, or NULL */
+    float*       dweight;  /* [O,I,kh,kw] fp32 out, or NULL */
+    float*       dstyles;  /* [N,I] fp32 out, or NULL */
+    float*       dnoise;   /* fp32, shape per noise_mode, out, or NULL */
+    void*        workspace;
+    size_t       workspace_bytes;
+} vfm_modconv_bwd_params;
+
+/* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
+VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);
+VFM_API int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream);
+VFM_API int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream);
+/* 1 if the tcgen05/TMEM implicit-GEMM path will be used for this descriptor, 0 if the generic SIMT kernel. */
+VFM_API int vfm_modconv_uses_tensor_cores(const vfm_modconv_desc* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFM_OPS_H */

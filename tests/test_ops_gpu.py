@@ -1,0 +1,359 @@
+"""Parity of the sm_100a kernels (called through the C ABI / plugin layer) against
+  (1) the committed golden vectors produced by the unmodified reference, and
+  (2) the CPU oracle on seeded inputs at decoder-like sizes.
+Tolerances are the ones north_star states: max|a-b|/max|b| <= 1e-5 in fp32, <= 2e-3 in fp16, outputs and gradients
+(fp64 is held to 1e-6 for the modulated conv, whose kernel interface takes fp32 weights/styles, and 1e-10 elsewhere)."""
+import math
+
+import pytest
+import torch
+
+from conftest import DT, golden, rel_err
+from oracle import ref_ops as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'float32': 1e-5, 'float64': 1e-10, 'float16': 2e-3}
+DEV = 'cuda'
+
+
+def _ops():
+    import vfm_vae_b200 as V
+    return V
+
+
+def _cases(name):
+    return golden(name).meta['cases']
+
+
+# ----------------------------------------------------------------------------------------------------- bias_act
+
+@pytest.mark.parametrize('case', _cases('bias_act'), ids=lambda c: f"{c['key']}-{c['act']}-{c['dtype']}")
+def test_bias_act_golden(case):
+    V = _ops()
+    G = golden('bias_act')
+    k, tol = case['key'], TOL[case['dtype']]
+    x = G.t(k + '_x', DEV).requires_grad_(True)
+    b = G.t(k + '_b', DEV).requires_grad_(True) if case['use_b'] else None
+    kw = dict(dim=case['dim'], act=case['act'], alpha=case['alpha'], gain=case['gain'], clamp=case['clamp'])
+    y = V.bias_act.bias_act(x, b, **kw)
+    assert y.dtype == DT[case['dtype']] and y.shape == x.shape
+    assert rel_err(y, G.t(k + '_y')) <= tol
+    dy = G.t(k + '_dy', DEV)
+    grads = torch.autograd.grad(y, [x] + ([b] if b is not None else []), dy)
+    assert rel_err(grads[0], G.t(k + '_dx')) <= tol
+    if b is not None:
+        assert rel_err(grads[1], G.t(k + '_db')) <= tol
+    # second order
+    dy_leaf = dy.clone().requires_grad_(True)
+    y2 = V.bias_act.bias_act(x, b, **kw)
+    dx2, = torch.autograd.grad(y2, x, dy_leaf, create_graph=True)
+    g2 = torch.autograd.grad(dx2, [dy_leaf, x], G.t(k + '_ddx', DEV), allow_unused=True)
+    assert rel_err(g2[0], G.t(k + '_g2_dy')) <= tol
+    ref_g2x = G.t(k + '_g2_x')
+    got_g2x = g2[1] if g2[1] is not None else torch.zeros_like(x)
+    assert rel_err(got_g2x, ref_g2x) <= tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('channels_last', [False, True])
+@pytest.mark.parametrize('shape', [(4, 128, 64, 64), (3, 6, 33, 17), (2, 512, 8, 8)])
+def test_bias_act_decoder_shapes(dtype, channels_last, shape):
+    V = _ops()
+    g = torch.Generator().manual_seed(10)
+    x32 = torch.randn(shape, generator=g) * 3
+    b32 = torch.randn(shape[1], generator=g)
+    dy32 = torch.randn(shape, generator=g)
+    # the oracle sees exactly the values the kernel sees (after the cast), computed in fp32
+    xq, bq, dyq = x32.to(dtype).float(), b32.to(dtype).float(), dy32.to(dtype).float()
+    xr = xq.clone().requires_grad_(True)
+    br = bq.clone().requires_grad_(True)
+    yr = O.bias_act(xr, br, act='lrelu', gain=math.sqrt(2), clamp=2.0)
+    dxr, dbr = torch.autograd.grad(yr, [xr, br], dyq)
+    x = xq.to(DEV, dtype)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    b = bq.to(DEV, dtype).requires_grad_(True)
+    y = V.bias_act.bias_act(x, b, act='lrelu', gain=math.sqrt(2), clamp=2.0)
+    assert y.stride() == x.stride()
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert rel_err(y, yr) <= tol
+    dx, db = torch.autograd.grad(y, [x, b], dyq.to(DEV, dtype))
+    assert rel_err(dx, dxr) <= tol
+    assert rel_err(db, dbr) <= (tol if dtype == torch.float32 else 4e-3)
+
+
+def test_bias_act_errors():
+    V = _ops()
+    x = torch.randn(2, 3, 4, 4, device=DEV)
+    with pytest.raises(RuntimeError):
+        V.bias_act.bias_act(x, torch.randn(5, device=DEV))          # wrong bias length
+    with pytest.raises(RuntimeError):
+        V.bias_act.bias_act(x.cpu(), None)                           # no CPU path
+    with pytest.raises(RuntimeError):
+        V.bias_act.bias_act(x, torch.randn(3, device=DEV).double())  # dtype mismatch
+    assert V.bias_act.bias_act(x, None) is not None                  # identity short-circuit
+    e = torch.empty(0, 3, 4, 4, device=DEV)
+    assert V.bias_act.bias_act(e, torch.zeros(3, device=DEV), act='lrelu').shape == e.shape   # empty input
+
+
+# ---------------------------------------------------------------------------------------------------- upfirdn2d
+
+@pytest.mark.parametrize('case', _cases('upfirdn2d'), ids=lambda c: f"{c['key']}-{c['dtype']}")
+def test_upfirdn2d_golden(case):
+    V = _ops()
+    G = golden('upfirdn2d')
+    k, tol = case['key'], TOL[case['dtype']]
+    x = G.t(k + '_x', DEV).requires_grad_(True)
+    f = G.t(k + '_f', DEV) if case['has_f'] else None
+    y = V.upfirdn2d.upfirdn2d(x, f, up=case['up'], down=case['down'], padding=case['padding'], flip_filter=case['flip'], gain=case['gain'])
+    ref = G.t(k + '_y')
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    assert rel_err(y, ref) <= tol
+    dx, = torch.autograd.grad(y, x, G.t(k + '_dy', DEV))
+    assert rel_err(dx, G.t(k + '_dx')) <= tol
+
+
+def test_upfirdn2d_helpers_golden():
+    V = _ops()
+    G = golden('upfirdn2d')
+    x, f = G.t('h_x', DEV), G.t('h_f', DEV)
+    assert rel_err(V.upfirdn2d.filter2d(x, f), G.t('h_filter2d')) <= 1e-5
+    assert rel_err(V.upfirdn2d.upsample2d(x, f), G.t('h_upsample2d')) <= 1e-5
+    assert rel_err(V.upfirdn2d.downsample2d(x, f), G.t('h_downsample2d')) <= 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('cfg', [
+    dict(shape=(1, 64, 65, 65), up=1, down=1, padding=[1, 1, 1, 1], gain=4.0),      # post-convT blur (tiled 1/1)
+    dict(shape=(2, 8, 257, 257), up=1, down=1, padding=[1, 1, 1, 1], gain=4.0),
+    dict(shape=(2, 16, 64, 64), up=2, down=1, padding=[2, 1, 2, 1], gain=4.0),       # upsample2d (tiled 2/1)
+    dict(shape=(2, 16, 128, 128), up=1, down=2, padding=[1, 1, 1, 1], gain=1.0),     # downsample2d (tiled 1/2)
+    dict(shape=(2, 4, 40, 52), up=2, down=1, padding=[3, 2, 1, 4], gain=1.0),        # odd phase alignment
+    dict(shape=(2, 4, 40, 52), up=1, down=1, padding=[-3, 2, 5, -1], gain=1.0),      # crop + pad
+])
+@pytest.mark.parametrize('channels_last', [False, True])
+def test_upfirdn2d_decoder_shapes(dtype, cfg, channels_last):
+    V = _ops()
+    g = torch.Generator().manual_seed(11)
+    xq = torch.randn(cfg['shape'], generator=g).to(dtype).float()
+    f = O.setup_filter([1, 3, 3, 1])
+    kw = dict(up=cfg['up'], down=cfg['down'], padding=cfg['padding'], gain=cfg['gain'])
+    xr = xq.clone().requires_grad_(True)
+    yr = O.upfirdn2d(xr, f, **kw)
+    dyq = torch.randn(yr.shape, generator=g).to(dtype).float()
+    dxr, = torch.autograd.grad(yr, xr, dyq)
+    x = xq.to(DEV, dtype)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = V.upfirdn2d.upfirdn2d(x, f.to(DEV), **kw)
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert y.shape == yr.shape
+    assert rel_err(y, yr) <= tol
+    dx, = torch.autograd.grad(y, x, dyq.to(DEV, dtype))
+    assert rel_err(dx, dxr) <= tol
+
+
+def test_upfirdn2d_errors():
+    V = _ops()
+    x = torch.randn(1, 1, 4, 4, device=DEV)
+    with pytest.raises(RuntimeError):
+        V.upfirdn2d.upfirdn2d(x, torch.ones(8, 8, device=DEV))                    # output smaller than 1x1
+    with pytest.raises(RuntimeError):
+        V.upfirdn2d.upfirdn2d(x, torch.ones(2, 2, device=DEV, dtype=torch.float64))   # f must be fp32
+
+
+# ----------------------------------------------------------------------------------------------- filtered_lrelu
+
+@pytest.mark.parametrize('case', _cases('filtered_lrelu'), ids=lambda c: f"{c['key']}-{c['dtype']}")
+def test_filtered_lrelu_golden(case):
+    V = _ops()
+    G = golden('filtered_lrelu')
+    k = case['key']
+    tol = {'float32': 2e-5, 'float64': 1e-10}[case['dtype']]
+    x = G.t(k + '_x', DEV).requires_grad_(True)
+    b = G.t(k + '_b', DEV).requires_grad_(True) if case['use_b'] else None
+    fu = G.t(k + '_fu', DEV) if case['has_fu'] else None
+    fd = G.t(k + '_fd', DEV) if case['has_fd'] else None
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        y = V.filtered_lrelu.filtered_lrelu(x, fu, fd, b, up=case['up'], down=case['down'], padding=case['padding'],
+                                            gain=case['gain'], slope=case['slope'], clamp=case['clamp'], flip_filter=case['flip'])
+        ref = G.t(k + '_y')
+        assert y.shape == ref.shape
+        assert rel_err(y, ref) <= tol
+        grads = torch.autograd.grad(y, [x] + ([b] if b is not None else []), G.t(k + '_dy', DEV))
+    assert rel_err(grads[0], G.t(k + '_dx')) <= tol
+    if b is not None:
+        assert rel_err(grads[1], G.t(k + '_db')) <= tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('shape', [(2, 16, 64, 64), (1, 8, 37, 50)])
+def test_filtered_lrelu_stylegan3_shape(dtype, shape):
+    """separable 12-tap up2/down2, padding chosen so out == in."""
+    V = _ops()
+    g = torch.Generator().manual_seed(12)
+    xq = torch.randn(shape, generator=g).to(dtype).float()
+    bq = (torch.randn(shape[1], generator=g) * 0.3).to(dtype).float()
+    fu = O.setup_filter([1, 4, 8, 12, 14, 16, 16, 14, 12, 8, 4, 1])
+    fd = O.setup_filter([1, 3, 6, 10, 14, 16, 16, 14, 10, 6, 3, 1])
+    kw = dict(up=2, down=2, padding=[10, 11, 10, 11], gain=math.sqrt(2), slope=0.2, clamp=0.8)
+    xr, br = xq.clone().requires_grad_(True), bq.clone().requires_grad_(True)
+    yr = O.filtered_lrelu(xr, fu, fd, br, **kw)
+    assert yr.shape == xq.shape
+    dyq = torch.randn(yr.shape, generator=g).to(dtype).float()
+    dxr, dbr = torch.autograd.grad(yr, [xr, br], dyq)
+    x = xq.to(DEV, dtype).requires_grad_(True)
+    b = bq.to(DEV, dtype).requires_grad_(True)
+    y = V.filtered_lrelu.filtered_lrelu(x, fu.to(DEV), fd.to(DEV), b, **kw)
+    tol = {torch.float32: 2e-5, torch.float16: 2e-3}[dtype]
+    assert rel_err(y, yr) <= tol
+    dx, db = torch.autograd.grad(y, [x, b], dyq.to(DEV, dtype))
+    assert rel_err(dx, dxr) <= tol
+    assert rel_err(db, dbr) <= (tol if dtype == torch.float32 else 6e-3)
+
+
+def test_filtered_lrelu_sign_tensor_format():
+    """The 2-bit sign tensor written by the fused kernel follows the reference layout and matches the oracle's codes."""
+    from vfm_vae_b200.plugins import filtered_lrelu_plugin as P
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 3, 10, 9, generator=g)
+    b = torch.randn(3, generator=g) * 0.2
+    fu = O.setup_filter(list(range(1, 9)))
+    fd = O.setup_filter([1, 3, 3, 1])
+    up, down, pad, gain, slope, clamp = 2, 2, [5, 5, 4, 6], 1.1, 0.2, 0.6
+    y, so, rc = P.filtered_lrelu(x.to(DEV), fu.to(DEV), fd.to(DEV), b.to(DEV), torch.empty([0]), up, down, *pad, 0, 0, gain, slope, clamp, False, True)
+    assert rc == 0 and so.dtype == torch.uint8
+    codes = O.filtered_lrelu_signs(x, fu, b, up=up, padding=pad, gain=gain, slope=slope, clamp=clamp)
+    yw, yh = y.shape[3], y.shape[2]
+    sw_active = yw * down - (down - 1) + fd.shape[-1] - 1
+    sh = yh * down - (down - 1) + fd.shape[0] - 1
+    assert so.shape == (2, 3, sh, ((sw_active + 15) & ~15) >> 2)
+    so = so.cpu()
+    unpacked = torch.stack([(so >> (2 * k)) & 3 for k in range(4)], dim=-1).reshape(2, 3, sh, -1)
+    assert torch.equal(unpacked[..., :sw_active], codes[:, :, :sh, :sw_active])
+
+
+def test_filtered_lrelu_composed_fallback():
+    """More than 32 taps -> plugin answers return_code -1 -> wrapper composes upfirdn2d + act + upfirdn2d."""
+    V = _ops()
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(1, 2, 40, 40, generator=g)
+    fu = O.setup_filter(list(range(1, 41)), separable=True)
+    xr = x.clone().requires_grad_(True)
+    yr = O.filtered_lrelu(xr, fu, None, None, up=2, padding=[20, 19, 20, 19], clamp=0.5)
+    dy = torch.randn(yr.shape, generator=g)
+    dxr, = torch.autograd.grad(yr, xr, dy)
+    xc = x.to(DEV).requires_grad_(True)
+    with pytest.warns(RuntimeWarning):
+        y = V.filtered_lrelu.filtered_lrelu(xc, fu.to(DEV), None, None, up=2, padding=[20, 19, 20, 19], clamp=0.5)
+    assert rel_err(y, yr) <= 2e-5
+    with pytest.warns(RuntimeWarning):
+        dx, = torch.autograd.grad(y, xc, dy.to(DEV))
+    assert rel_err(dx, dxr) <= 2e-5
+
+
+# --------------------------------------------------------------------------------------------- modulated_conv2d
+
+@pytest.mark.parametrize('case', _cases('modulated_conv2d'), ids=lambda c: f"{c['key']}-{c['dtype']}")
+def test_modulated_conv2d_golden(case):
+    V = _ops()
+    G = golden('modulated_conv2d')
+    k = case['key']
+    tol = {'float32': 1e-5, 'float64': 1e-6}[case['dtype']]
+    x = G.t(k + '_x', DEV).requires_grad_(True)
+    w = G.t(k + '_weight', DEV).requires_grad_(True)
+    s = G.t(k + '_styles', DEV).requires_grad_(True)
+    noise = G.t(k + '_noise', DEV).requires_grad_(True) if case['noise'] else None
+    f = G.t(k + '_f', DEV) if case['use_f'] else None
+    y = V.modulated_conv2d(x, w, s, noise=noise, up=case['up'], padding=case['k'] // 2, resample_filter=f,
+                           demodulate=case['demodulate'], flip_weight=case['flip_weight'])
+    ref = G.t(k + '_y')
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    assert rel_err(y, ref) <= tol
+    leaves = [x, w, s] + ([noise] if noise is not None else [])
+    grads = torch.autograd.grad(y, leaves, G.t(k + '_dy', DEV))
+    for gr, name in zip(grads, ['dx', 'dweight', 'dstyles', 'dnoise']):
+        assert rel_err(gr, G.t(k + '_' + name)) <= tol, name
+
+
+def _modconv_vs_oracle(N, I, O_, H, W, k, up, demod, dtype, noise_kind, generic, seed=20):
+    V = _ops()
+    from vfm_vae_b200.torch_utils.ops import modulated_conv2d as M
+    g = torch.Generator().manual_seed(seed)
+    xq = torch.randn(N, I, H, W, generator=g).to(dtype).float()
+    w = torch.randn(O_, I, k, k, generator=g)
+    s = torch.randn(N, I, generator=g) + 1
+    f = O.setup_filter([1, 3, 3, 1]) if up == 2 else None
+    noise = None
+    if noise_kind == 'const':
+        noise = torch.randn(H * up, W * up, generator=g) * 0.3
+    elif noise_kind == 'random':
+        noise = torch.randn(N, 1, H * up, W * up, generator=g) * 0.3
+    leaves_r = [t.clone().requires_grad_(True) for t in ([xq, w, s] + ([noise] if noise is not None else []))]
+    yr = O.modulated_conv2d(leaves_r[0], leaves_r[1], leaves_r[2], noise=(leaves_r[3] if noise is not None else None), up=up,
+                            padding=k // 2, resample_filter=f, demodulate=demod, flip_weight=(up == 1))
+    dyq = torch.randn(yr.shape, generator=g).to(dtype).float()
+    gr = torch.autograd.grad(yr, leaves_r, dyq)
+    leaves = [xq.to(DEV, dtype).requires_grad_(True), w.to(DEV).requires_grad_(True), s.to(DEV).requires_grad_(True)]
+    if noise is not None:
+        leaves.append(noise.to(DEV).requires_grad_(True))
+    M.force_generic = generic
+    try:
+        y = V.modulated_conv2d(leaves[0], leaves[1], leaves[2], noise=(leaves[3] if noise is not None else None), up=up,
+                               padding=k // 2, resample_filter=(f.to(DEV) if f is not None else None), demodulate=demod,
+                               flip_weight=(up == 1))
+        gg = torch.autograd.grad(y, leaves, dyq.to(DEV, dtype))
+    finally:
+        M.force_generic = False
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert y.dtype == dtype and y.shape == yr.shape
+    assert rel_err(y, yr) <= tol, 'y'
+    for a, b, name in zip(gg, gr, ['dx', 'dweight', 'dstyles', 'dnoise']):
+        assert rel_err(a, b) <= tol, name
+
+
+@pytest.mark.parametrize('generic', [True, False], ids=['generic', 'auto'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [
+    dict(N=2, I=64, O_=64, H=16, W=16, k=3, up=1, demod=True, noise_kind='const'),
+    dict(N=2, I=128, O_=64, H=8, W=8, k=3, up=2, demod=True, noise_kind='const'),
+    dict(N=3, I=64, O_=128, H=24, W=24, k=3, up=1, demod=True, noise_kind='random'),
+    dict(N=2, I=64, O_=3, H=32, W=32, k=1, up=1, demod=False, noise_kind=None),          # ToRGB
+    dict(N=1, I=192, O_=64, H=32, W=32, k=3, up=1, demod=True, noise_kind=None),
+    dict(N=2, I=40, O_=24, H=9, W=13, k=3, up=1, demod=True, noise_kind='const'),         # ragged channels / sizes
+    dict(N=2, I=40, O_=24, H=9, W=13, k=3, up=2, demod=True, noise_kind='const'),
+], ids=lambda c: f"N{c['N']}I{c['I']}O{c['O_']}H{c['H']}k{c['k']}up{c['up']}")
+def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
+    _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)
+
+
+def test_modulated_conv2d_errors():
+    V = _ops()
+    x = torch.randn(2, 4, 8, 8, device=DEV)
+    w = torch.randn(3, 4, 3, 3, device=DEV)
+    s = torch.ones(2, 4, device=DEV)
+    with pytest.raises(NotImplementedError):
+        V.modulated_conv2d(x, w, s, down=2, padding=1)
+    with pytest.raises(AssertionError):
+        V.modulated_conv2d(x, w, torch.ones(2, 5, device=DEV), padding=1)
+    with pytest.raises(RuntimeError):
+        V.modulated_conv2d(x.cpu(), w.cpu(), s.cpu(), padding=1)
+    with pytest.raises(RuntimeError):
+        V.modulated_conv2d(x, w, s, up=2, padding=1)     # up=2 without a resample filter
+
+
+@pytest.mark.parametrize('case', [c for c in _cases('conv2d_resample') if c['down'] == 1 and isinstance(c['padding'], int)], ids=lambda c: c['key'])
+def test_conv2d_resample_golden(case):
+    V = _ops()
+    G = golden('conv2d_resample')
+    k = case['key']
+    y = V.conv2d_resample.conv2d_resample(G.t(k + '_x', DEV), G.t(k + '_w', DEV), f=G.t('f', DEV), up=case['up'],
+                                          padding=case['padding'], flip_weight=case['flip_weight'])
+    ref = G.t(k + '_y')
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) <= 1e-6

@@ -1,0 +1,251 @@
+// extern "C" entry points of the modulated conv: validation, workspace planning, and dispatch between the tcgen05
+// implicit-GEMM path (modconv_tc.cu) and the generic SIMT path (modconv_generic.cu).
+#include "modconv_common.cuh"
+
+namespace vfm {
+namespace modconv {
+
+// ---- generic path (modconv_generic.cu) ----
+int run_conv(int dtype, const ConvArgs& a, cudaStream_t stream);
+int run_wgrad(int dtype, WgradArgs a, cudaStream_t stream);
+int run_gsum(int dtype, const void* dy, const void* y, const float* noise, int64_t noise_sn, const float* dcoefs, int planes, int O, int HW, float* g, cudaStream_t stream);
+int run_dnoise(int dtype, const void* dy, int N, int O, int HW, int per_sample, float* dnoise, cudaStream_t stream);
+int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream);
+int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, const float* dcoefs, const float* iscale, const float* wsq, int N, int O, int I, int demod, cudaStream_t stream);
+
+// ---- tensor-core path (modconv_tc.cu) ----
+bool tc_supported(const vfm_modconv_desc& d);
+size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
+int tc_forward(const vfm_modconv_fwd_params& p, const Coefs& k, void* ws, size_t ws_bytes, cudaStream_t stream);
+int tc_backward(const vfm_modconv_bwd_params& p, const Coefs& k, float* g, float* dsum, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+static size_t esize(int dtype) { return dtype == VFM_F16 ? 2 : (dtype == VFM_F32 ? 4 : 8); }
+
+static int validate(const vfm_modconv_desc& d) {
+    VFM_CHECK_ARG(d.dtype == VFM_F16 || d.dtype == VFM_F32 || d.dtype == VFM_F64, "modulated_conv2d: unsupported dtype %d", d.dtype);
+    VFM_CHECK_ARG(d.batch >= 1 && d.in_channels >= 1 && d.out_channels >= 1 && d.in_h >= 1 && d.in_w >= 1, "modulated_conv2d: empty tensor");
+    VFM_CHECK_ARG(d.kh == d.kw && (d.kh & 1) == 1, "modulated_conv2d: kernel must be square with odd size (got %dx%d)", d.kh, d.kw);
+    VFM_CHECK_ARG(d.up == 1 || d.up == 2, "modulated_conv2d: up must be 1 or 2 (got %d); down > 1 is not on the decoder path", d.up);
+    VFM_CHECK_ARG(d.noise_mode >= 0 && d.noise_mode <= 2, "modulated_conv2d: bad noise_mode");
+    VFM_CHECK_ARG(d.up == 1 || (d.resample_filter && d.fw >= 1 && d.fh >= 1), "modulated_conv2d: up=2 needs a 2-D resample filter");
+    if (d.kh * d.kw > kMaxTaps) { set_error("modulated_conv2d: %dx%d kernels are not supported", d.kh, d.kw); return VFM_ERR_NO_KERNEL; }
+    // expected output size
+    int oh, ow;
+    if (d.up == 1) { oh = d.in_h + 2 * d.padding - d.kh + 1; ow = d.in_w + 2 * d.padding - d.kw + 1; }
+    else {
+        int px0 = d.padding + (d.fw + 1) / 2, px1 = d.padding + (d.fw - 2) / 2;
+        int py0 = d.padding + (d.fh + 1) / 2, py1 = d.padding + (d.fh - 2) / 2;
+        ow = d.in_w * 2 + px0 + px1 - d.fw + 1 - (d.kw - 1);
+        oh = d.in_h * 2 + py0 + py1 - d.fh + 1 - (d.kh - 1);
+    }
+    VFM_CHECK_ARG(oh == d.out_h && ow == d.out_w, "modulated_conv2d: out size %dx%d does not match expected %dx%d", d.out_h, d.out_w, oh, ow);
+    return VFM_OK;
+}
+
+// stage-1 geometry for up == 2
+struct Stage1 {
+    int zh, zw;            // intermediate size
+    int sn, sd;
+    TapTable taps;         // forward taps
+    // stage-2 resampler
+    int r_up, r_px0, r_py0;
+    // backward of the resampler (torch_utils/ops/upfirdn2d.py:251-269)
+    int rb_px0, rb_py0;
+};
+
+static Stage1 make_stage1(const vfm_modconv_desc& d) {
+    Stage1 s;
+    const int kh = d.kh, kw = d.kw;
+    s.taps.ntaps = kh * kw;
+    if (d.up == 1) {
+        s.zh = d.out_h; s.zw = d.out_w; s.sn = 1; s.sd = 1;
+        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
+            int t = ky * kw + kx;
+            s.taps.off_y[t] = ky - d.padding; s.taps.off_x[t] = kx - d.padding;
+            s.taps.widx[t] = d.flip_weight ? t : (kh - 1 - ky) * kw + (kw - 1 - kx);
+        }
+        s.r_up = 1; s.r_px0 = s.r_py0 = s.rb_px0 = s.rb_py0 = 0;
+    } else if (kh == 1) {
+        // conv2d_resample fast path "1x1 + upsampling": convolve first, then upfirdn2d(up=2) (conv2d_resample.py:101-104)
+        s.zh = d.in_h; s.zw = d.in_w; s.sn = 1; s.sd = 1;
+        s.taps.off_y[0] = s.taps.off_x[0] = 0; s.taps.widx[0] = 0;
+        s.r_up = 2;
+        s.r_px0 = d.padding + (d.fw + 1) / 2; s.r_py0 = d.padding + (d.fh + 1) / 2;
+        // backward of upfirdn2d(up=2): down=2 with pad p0 = fw - px0 - 1
+        s.rb_px0 = d.fw - s.r_px0 - 1; s.rb_py0 = d.fh - s.r_py0 - 1;
+    } else {
+        UpGeom g = up_geometry(d);
+        s.zh = g.zh; s.zw = g.zw; s.sn = 1; s.sd = 2;
+        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
+            int t = ky * kw + kx;
+            s.taps.off_y[t] = g.pyt - ky; s.taps.off_x[t] = g.pxt - kx;
+            s.taps.widx[t] = d.flip_weight ? (kh - 1 - ky) * kw + (kw - 1 - kx) : t;
+        }
+        s.r_up = 1; s.r_px0 = g.bpx0; s.r_py0 = g.bpy0;
+        s.rb_px0 = d.fw - g.bpx0 - 1; s.rb_py0 = d.fh - g.bpy0 - 1;
+    }
+    return s;
+}
+
+// taps for the data gradient: input position of dz for output position of dx
+static void dgrad_taps(const vfm_modconv_desc& d, const Stage1& s, TapTable& t, int& sn, int& sd) {
+    t.ntaps = s.taps.ntaps;
+    // forward: xin = (z*s.sn + off)/s.sd  <=>  z = (xin*s.sd - off)/s.sn ; here s.sn == 1 always
+    sn = s.sd; sd = 1;
+    for (int i = 0; i < t.ntaps; i++) { t.off_y[i] = -s.taps.off_y[i]; t.off_x[i] = -s.taps.off_x[i]; t.widx[i] = s.taps.widx[i]; }
+}
+
+static int call_upfirdn(int dtype, const void* in, void* out, const float* f, int fw, int fh, int up, int down, int px0, int py0, int flip, float gain,
+                        int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream) {
+    vfm_upfirdn2d_params u;
+    u.x = in; u.f = f; u.y = out; u.dtype = dtype;
+    u.upx = u.upy = up; u.downx = u.downy = down; u.padx0 = px0; u.pady0 = py0; u.flip = flip; u.gain = gain;
+    u.in_w = iw; u.in_h = ih; u.channels = C; u.batch = N;
+    u.in_stride_w = 1; u.in_stride_h = iw; u.in_stride_c = (int64_t)ih * iw; u.in_stride_n = (int64_t)C * ih * iw;
+    u.fw = fw; u.fh = fh; u.f_stride_w = 1; u.f_stride_h = fw;
+    u.out_w = ow; u.out_h = oh;
+    u.out_stride_w = 1; u.out_stride_h = ow; u.out_stride_c = (int64_t)oh * ow; u.out_stride_n = (int64_t)C * oh * ow;
+    u.add = add; u.add_stride_h = ow; u.add_stride_n = add_sn;
+    return vfm_upfirdn2d(&u, stream);
+}
+
+static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
+    Carver cv(nullptr, ~(size_t)0);
+    Coefs k; carve_coefs(cv, d, k);
+    Stage1 s = make_stage1(d);
+    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * s.zw * esize(d.dtype));
+    if (direction == 1) { cv.take<float>((size_t)d.batch * d.out_channels); cv.take<float>((size_t)d.batch * d.in_channels); }
+    return cv.off + 256;
+}
+
+}  // namespace modconv
+}  // namespace vfm
+
+using namespace vfm;
+using namespace vfm::modconv;
+
+extern "C" int vfm_modconv_uses_tensor_cores(const vfm_modconv_desc* d) {
+    if (!d || d->force_generic) return 0;
+    return tc_supported(*d) ? 1 : 0;
+}
+
+extern "C" size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction) {
+    if (!d) return 0;
+    size_t g = generic_workspace(*d, direction);
+    if (!d->force_generic && tc_supported(*d)) g += tc_workspace_bytes(*d, direction);
+    return g;
+}
+
+extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p != nullptr, "modulated_conv2d: params is NULL");
+    const vfm_modconv_desc& d = p->d;
+    int st = validate(d); if (st) return st;
+    VFM_CHECK_ARG(p->x && p->weight && p->styles && p->y && p->dcoefs, "modulated_conv2d: x, weight, styles, y, dcoefs must be non-NULL");
+    VFM_CHECK_ARG((d.noise_mode == VFM_NOISE_NONE) == (p->noise == nullptr), "modulated_conv2d: noise pointer does not match noise_mode");
+    size_t need = vfm_modconv_workspace_bytes(&d, 0);
+    if (!p->workspace || p->workspace_bytes < need) { set_error("modulated_conv2d: workspace too small (%zu < %zu)", p->workspace_bytes, need); return VFM_ERR_WORKSPACE; }
+
+    Carver cv(p->workspace, p->workspace_bytes);
+    Coefs k; carve_coefs(cv, d, k);
+    Stage1 s = make_stage1(d);
+    void* z = nullptr;
+    if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * s.zw * esize(d.dtype));
+    st = compute_coefs(d, p->weight, p->styles, k, p->dcoefs, nullptr, stream); if (st) return st;
+
+    if (!d.force_generic && tc_supported(d)) {
+        cv.off = (cv.off + 255) & ~(size_t)255;
+        return tc_forward(*p, k, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+    }
+
+    const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
+    ConvArgs a;
+    a.in = p->x; a.w = p->weight;
+    a.w_s_co = (int64_t)d.in_channels * d.kh * d.kw; a.w_s_ci = (int64_t)d.kh * d.kw;
+    a.in_scale = k.iscale; a.out_scale = k.oscale;
+    a.aux = nullptr; a.aux_sum = nullptr;
+    a.N = d.batch; a.Cin = d.in_channels; a.Cout = d.out_channels; a.Hin = d.in_h; a.Win = d.in_w;
+    a.sn = s.sn; a.sd = s.sd; a.taps = s.taps;
+    if (d.up == 1) {
+        a.out = p->y; a.Hout = d.out_h; a.Wout = d.out_w;
+        a.add = p->noise; a.add_sn = noise_sn; a.add_sh = d.out_w;
+        return run_conv(d.dtype, a, stream);
+    }
+    a.out = z; a.Hout = s.zh; a.Wout = s.zw; a.add = nullptr; a.add_sn = a.add_sh = 0;
+    st = run_conv(d.dtype, a, stream); if (st) return st;
+    return call_upfirdn(d.dtype, z, p->y, d.resample_filter, d.fw, d.fh, s.r_up, 1, s.r_px0, s.r_py0, 0, (float)(d.up * d.up),
+                        d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream);
+}
+
+extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p != nullptr, "modulated_conv2d backward: params is NULL");
+    const vfm_modconv_desc& d = p->d;
+    int st = validate(d); if (st) return st;
+    VFM_CHECK_ARG(p->dy && p->x && p->weight && p->styles && p->dcoefs, "modulated_conv2d backward: dy, x, weight, styles, dcoefs must be non-NULL");
+    VFM_CHECK_ARG(!d.demodulate || p->y, "modulated_conv2d backward: y (forward output) is required when demodulate is on");
+    VFM_CHECK_ARG(!p->dstyles || p->dx, "modulated_conv2d backward: dstyles needs dx to be computed as well");
+    VFM_CHECK_ARG(!p->dnoise || d.noise_mode != VFM_NOISE_NONE, "modulated_conv2d backward: dnoise requested without noise");
+    size_t need = vfm_modconv_workspace_bytes(&d, 1);
+    if (!p->workspace || p->workspace_bytes < need) { set_error("modulated_conv2d backward: workspace too small (%zu < %zu)", p->workspace_bytes, need); return VFM_ERR_WORKSPACE; }
+
+    const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
+    Carver cv(p->workspace, p->workspace_bytes);
+    Coefs k; carve_coefs(cv, d, k);
+    Stage1 s = make_stage1(d);
+    void* dz = nullptr;
+    if (d.up == 2) dz = cv.take<char>((size_t)N * O * s.zh * s.zw * esize(d.dtype));
+    float* g = cv.take<float>((size_t)N * O);
+    float* dsum = cv.take<float>((size_t)N * I);
+    st = compute_coefs(d, p->weight, p->styles, k, nullptr, p->dcoefs, stream); if (st) return st;
+
+    const int HWo = d.out_h * d.out_w;
+    const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)HWo : 0;
+    if (d.demodulate && (p->dweight || p->dstyles)) {
+        st = run_gsum(d.dtype, p->dy, p->y, p->noise, noise_sn, p->dcoefs, N * O, O, HWo, g, stream); if (st) return st;
+    }
+    if (p->dnoise) {
+        int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
+        VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
+        st = run_dnoise(d.dtype, p->dy, N, O, HWo, per_sample, p->dnoise, stream); if (st) return st;
+    }
+
+    if (!d.force_generic && tc_supported(d)) {
+        cv.off = (cv.off + 255) & ~(size_t)255;
+        st = tc_backward(*p, k, g, dsum, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        if (st) return st;
+    } else {
+        // gradient w.r.t. the stage-1 output
+        const void* dzp = p->dy;
+        if (d.up == 2) {
+            // backward of upfirdn2d (torch_utils/ops/upfirdn2d.py:251-269): swap up/down, flip the filter, same gain
+            st = call_upfirdn(d.dtype, p->dy, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
+                              N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream);
+            if (st) return st;
+            dzp = dz;
+        }
+        if (p->dx) {
+            ConvArgs a;
+            a.in = dzp; a.out = p->dx; a.w = p->weight;
+            a.w_s_co = KK; a.w_s_ci = (int64_t)I * KK;          // roles of the channel axes are swapped
+            a.in_scale = k.oscale; a.out_scale = k.iscale; a.add = nullptr; a.add_sn = a.add_sh = 0;
+            a.aux = p->dstyles ? p->x : nullptr; a.aux_sum = p->dstyles ? dsum : nullptr;
+            a.N = N; a.Cin = O; a.Cout = I; a.Hin = s.zh; a.Win = s.zw; a.Hout = d.in_h; a.Wout = d.in_w;
+            dgrad_taps(d, s, a.taps, a.sn, a.sd);
+            if (p->dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
+            st = run_conv(d.dtype, a, stream); if (st) return st;
+        }
+        if (p->dweight) {
+            VFM_CUDA_OK(cudaMemsetAsync(p->dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
+            WgradArgs w;
+            w.dy = dzp; w.x = p->x; w.oscale = k.oscale; w.iscale = k.iscale; w.dw = p->dweight;
+            w.s_co = (int64_t)I * KK; w.s_ci = KK;
+            w.N = N; w.Co = O; w.Ci = I; w.Hd = s.zh; w.Wd = s.zw; w.Hx = d.in_h; w.Wx = d.in_w;
+            w.sn = s.sn; w.sd = s.sd; w.taps = s.taps; w.chunks = 0; w.chunk_pix = 0;
+            st = run_wgrad(d.dtype, w, stream); if (st) return st;
+        }
+    }
+    if (p->dweight && d.demodulate) { st = run_dw_fix(p->dweight, p->weight, k.a, g, p->dcoefs, k.iscale, N, O, I, KK, stream); if (st) return st; }
+    if (p->dstyles) { st = run_ds_fix(p->dstyles, dsum, k.c, g, p->dcoefs, k.iscale, k.wsq, N, O, I, d.demodulate, stream); if (st) return st; }
+    return VFM_OK;
+}

@@ -1,0 +1,111 @@
+"""Style-modulated / demodulated conv2d on sm_100a.  Drop-in for the reference helper networks/generator.py:46-103
+(same signature and argument meaning), implemented as ONE custom autograd Function over the native
+``modconv_plugin.forward/backward`` entry points instead of stock autograd through a grouped cuDNN conv:
+
+* the per-sample weight tensor [N,O,I,kh,kw] is never built: styles scale the activation operand, the demodulation
+  coefficients d[n,o] scale the accumulator in the GEMM epilogue, noise is added there too;
+* backward = one data-gradient conv (with the dstyles reduction in its epilogue) + one batched weight-gradient GEMM
+  + two tiny fix-up kernels for the gradient through d[n,o] (formulas: SURVEY.md section 8a).
+
+``fused_modconv`` is accepted and ignored: both reference branches compute the same function and there is only one
+kernel here.  ``down`` must be 1 (the decoder never uses anything else).  weight/styles/noise are consumed in fp32
+(they are fp32 parameters in the decoder); second-order gradients are not implemented."""
+import torch
+
+from ... import custom_ops
+
+_plugin = None
+
+#: set True (tests only) to run every call through the generic SIMT kernel instead of the tcgen05 path
+force_generic = False
+
+
+def _init():
+    global _plugin
+    if _plugin is None:
+        _plugin = custom_ops.get_plugin(module_name='modconv_plugin')
+    return True
+
+
+def _noise_canon(noise, n, oh, ow):
+    """-> fp32 contiguous [oh,ow] or [n,1,oh,ow] view of whatever broadcastable noise the caller passed."""
+    if noise is None:
+        return None
+    t = noise.to(torch.float32)
+    if t.dim() <= 2:
+        return t.expand(oh, ow).contiguous()
+    t = t.expand(n, 1, oh, ow) if t.dim() == 4 else t.reshape(-1, 1, oh, ow).expand(n, 1, oh, ow)
+    if t.stride(0) == 0:     # broadcast over the batch -> the cheaper [H,W] mode
+        return t[0, 0].contiguous()
+    return t.contiguous()
+
+
+class _ModulatedConv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight):
+        n = x.shape[0]
+        xc = x.contiguous()
+        w32 = weight.detach().to(torch.float32).contiguous()
+        s32 = styles.detach().to(torch.float32).contiguous()
+        f32 = resample_filter.to(device=x.device, dtype=torch.float32).contiguous() if (up > 1 and resample_filter is not None) else None
+        kh = weight.shape[2]
+        oh = x.shape[2] * up + (2 * padding - kh + 1 if up == 1 else 0)
+        ow = x.shape[3] * up + (2 * padding - weight.shape[3] + 1 if up == 1 else 0)
+        if up > 1:
+            oh = x.shape[2] * up + 2 * padding - (kh - 1)
+            ow = x.shape[3] * up + 2 * padding - (weight.shape[3] - 1)
+        n32 = _noise_canon(noise.detach() if noise is not None else None, n, oh, ow)
+        y, dcoefs = _plugin.forward(xc, w32, s32, n32, up, padding, f32, demodulate, flip_weight, force_generic)
+        ctx.save_for_backward(xc, w32, s32, n32 if n32 is not None else torch.empty([0]), dcoefs,
+                              y if demodulate else torch.empty([0]), f32 if f32 is not None else torch.empty([0]))
+        ctx.cfg = (up, padding, demodulate, flip_weight)
+        ctx.in_dtypes = (x.dtype, weight.dtype, styles.dtype, noise.dtype if noise is not None else None)
+        ctx.noise_shape = tuple(noise.shape) if noise is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w32, s32, n32, dcoefs, y, f32 = ctx.saved_tensors
+        up, padding, demodulate, flip_weight = ctx.cfg
+        n32 = n32 if n32.numel() else None
+        f32 = f32 if f32.numel() else None
+        y = y if y.numel() else None
+        need = ctx.needs_input_grad
+        dx, dw, ds, dn = _plugin.backward(dy.contiguous(), xc, y, w32, s32, n32, dcoefs, up, padding, f32, demodulate, flip_weight,
+                                          need_dx=need[0], need_dweight=need[1], need_dstyles=need[2],
+                                          need_dnoise=(need[3] and n32 is not None), force_generic=force_generic)
+        xd, wd, sd, nd = ctx.in_dtypes
+        if dx is not None and not need[0]:
+            dx = None
+        if dw is not None:
+            dw = dw.to(wd)
+        if ds is not None:
+            ds = ds.to(sd)
+        if dn is not None:
+            # undo the broadcast of _noise_canon
+            shape = ctx.noise_shape
+            full = dn if dn.dim() == 4 else dn[None, None]
+            while full.dim() > len(shape):
+                full = full.sum(0)
+            for i, sz in enumerate(shape):
+                if sz == 1 and full.shape[i] != 1:
+                    full = full.sum(i, keepdim=True)
+            dn = full.reshape(shape).to(nd)
+        return dx, dw, ds, dn, None, None, None, None, None
+
+
+def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
+                     flip_weight=True, fused_modconv=True):
+    """Arguments as in the reference (networks/generator.py:46-58)."""
+    assert isinstance(x, torch.Tensor) and x.ndim == 4
+    batch_size = x.shape[0]
+    out_channels, in_channels, kh, kw = weight.shape
+    assert x.shape[1] == in_channels, f'x has {x.shape[1]} channels, weight expects {in_channels}'
+    assert tuple(styles.shape) == (batch_size, in_channels), f'styles must be [{batch_size}, {in_channels}]'
+    if down != 1:
+        raise NotImplementedError('vfm_vae_b200.modulated_conv2d: down > 1 is not on the decoder path and is not implemented')
+    if x.device.type != 'cuda':
+        raise RuntimeError('vfm_vae_b200.modulated_conv2d has no reference/CPU implementation: CUDA tensors only '
+                           '(the CPU oracle is oracle/ref_ops.py, for tests).')
+    _init()
+    return _ModulatedConv2d.apply(x, weight, styles, noise, int(up), int(padding), resample_filter, bool(demodulate), bool(flip_weight))

@@ -60,6 +60,20 @@ VFM_API int vfm_abi_version(void);
 /* Number of kernels this library has launched in this process (all ops); bench.py reports the delta. */
 VFM_API uint64_t vfm_launch_count(void);
 
+/* Optional per-kernel timing (measurement aid for bench.py; off by default and free when off).
+ * vfm_timing_enable(1) clears old records and makes every hot kernel launch record a CUDA event before and after it on
+ * the launching stream, tagged with the launch's ALGORITHMIC flops and bytes.  vfm_timing_report() waits for the
+ * recorded events and returns one aggregated entry per kernel name (returns the number of distinct names). */
+typedef struct {
+    char     name[64];
+    int64_t  launches;
+    double   total_ms;   /* sum of event-measured durations */
+    double   flops;      /* sum of algorithmic FLOPs */
+    double   bytes;      /* sum of algorithmic HBM bytes */
+} vfm_kernel_stat;
+VFM_API void vfm_timing_enable(int on);
+VFM_API int vfm_timing_report(vfm_kernel_stat* out, int max_entries);
+
 /* ------------------------------------------------------------------------------------------------------------
  * bias_act: y = clamp(act(x + b) * gain, +-clamp)            (grad = 0)
  *           dx = dy * act'(.) * gain, 0 where |yref| >= clamp (grad = 1; here `x` is the incoming gradient)
@@ -81,9 +95,9 @@ typedef struct {
     int32_t     dtype;  /* vfm_dtype of x/b/xref/yref/dy/y */
     int32_t     grad;   /* 0, 1, 2 */
     int32_t     act;    /* 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu 7 selu 8 softplus 9 swish */
-    float       alpha;
-    float       gain;
-    float       clamp;  /* < 0 = off */
+    double      alpha;  /* scalars travel as fp64 so that the fp64 kernels are exact (the reference passes floats) */
+    double      gain;
+    double      clamp;  /* < 0 = off */
     int64_t     size_x;
     int64_t     size_b;
     int64_t     step_b;
@@ -104,7 +118,7 @@ typedef struct {
     int32_t      upx, upy, downx, downy;
     int32_t      padx0, pady0;          /* only the leading pads matter once the output size is fixed */
     int32_t      flip;                  /* 0 = true convolution, 1 = correlation */
-    float        gain;
+    double       gain;
     int32_t      in_w, in_h, channels, batch;
     int64_t      in_stride_w, in_stride_h, in_stride_c, in_stride_n;
     int32_t      fw, fh;
@@ -164,7 +178,7 @@ typedef struct {
     void*    x;
     uint8_t* s;
     int32_t  dtype;
-    float    gain, slope, clamp;
+    double   gain, slope, clamp;
     int32_t  write_signs, read_signs;
     int32_t  x_w, x_h, channels, batch;
     int64_t  x_stride_w, x_stride_h, x_stride_c, x_stride_n;

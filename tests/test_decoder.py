@@ -1,0 +1,97 @@
+"""The decoder mirror (vfm_vae_b200/decoder.py) against a golden checkpoint + outputs of the reference's own
+SynthesisNetwork(use_convnext=False) (tests/golden/decoder_legacy.npz, made by tools/make_golden.py).
+
+CPU: host logic only, with the oracle ops injected (test-only).  GPU: the real thing -- every modulated conv,
+bias_act and upfirdn2d on the sm_100a kernels -- forward and parameter gradients."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import golden, rel_err
+from oracle import ref_ops as O
+
+
+def oracle_ops():
+    def modconv(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True, flip_weight=True, fused_modconv=True):
+        return O.modulated_conv2d(x, weight, styles, noise=noise, up=up, down=down, padding=padding, resample_filter=resample_filter,
+                                  demodulate=demodulate, flip_weight=flip_weight)
+    return SimpleNamespace(bias_act=O.bias_act, def_gain=lambda a: O.ACTIVATIONS[a][1], setup_filter=O.setup_filter,
+                           upsample2d=O.upsample2d, modulated_conv2d=modconv)
+
+
+def build(ops, device='cpu'):
+    from vfm_vae_b200.decoder import SynthesisNetwork
+    # the reference trains and evaluates with TF32 off (training/training_loop.py:504-505); the out-of-scope glue layers
+    # (z-convs, attention) run on cuDNN/cuBLAS and would otherwise lose 1e-3 of precision
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    G = golden('decoder_legacy')
+    kw = dict(G.meta['kwargs'])
+    net = SynthesisNetwork(ops=ops, **kw)
+    sd = {k[4:]: G.t(k) for k in G.keys() if k.startswith('sd::')}
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert net.num_ws == G.meta['num_ws']
+    return net.to(device), G
+
+
+def check(net, G, device, tol):
+    z, ws = G.t('z', device), G.t('ws', device)
+    img, multi = net(z, ws, None, None)
+    assert img.dtype == torch.float32
+    assert rel_err(img, G.t('img')) <= tol
+    assert len(multi) == 3
+    for i, m in enumerate(multi):
+        assert rel_err(m, G.t(f'multi{i}')) <= tol, f'multi{i}'
+    loss = img.square().mean() + sum(m.square().mean() for m in multi)
+    assert abs(loss.item() - G.meta['loss']) <= tol * abs(G.meta['loss']) * 10
+    params = dict(net.named_parameters())
+    names = G.meta['grad_names']
+    grads = torch.autograd.grad(loss, [params[n] for n in names])
+    for n, g in zip(names, grads):
+        assert rel_err(g, G.t('grad::' + n)) <= 20 * tol, n
+
+
+def test_decoder_host_logic_cpu():
+    net, G = build(oracle_ops())
+    check(net, G, 'cpu', 2e-5)
+
+
+def test_state_dict_names_match_reference():
+    from vfm_vae_b200.decoder import SynthesisNetwork
+    G = golden('decoder_legacy')
+    net = SynthesisNetwork(ops=oracle_ops(), **G.meta['kwargs'])
+    ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k[4:]: tuple(G.z[k].shape) for k in G.keys() if k.startswith('sd::')}
+    assert ours == ref
+
+
+@pytest.mark.gpu
+def test_decoder_cuda_fp32():
+    from vfm_vae_b200.decoder import default_ops
+    net, G = build(default_ops(), 'cuda')
+    z, ws = G.t('z', 'cuda'), G.t('ws', 'cuda')
+    # the golden was produced on CPU where every block runs fp32: force the same here
+    img, multi = net(z, ws, None, None, force_fp32=True)
+    assert rel_err(img, G.t('img')) <= 2e-5
+    for i, m in enumerate(multi):
+        assert rel_err(m, G.t(f'multi{i}')) <= 2e-5
+    loss = img.square().mean() + sum(m.square().mean() for m in multi)
+    params = dict(net.named_parameters())
+    names = G.meta['grad_names']
+    grads = torch.autograd.grad(loss, [params[n] for n in names])
+    for n, g in zip(names, grads):
+        assert rel_err(g, G.t('grad::' + n)) <= 2e-4, n
+
+
+@pytest.mark.gpu
+def test_decoder_cuda_fp16_blocks():
+    """num_fp16_res=2 of the golden config: the two highest-resolution blocks run in fp16 like the reference does on CUDA."""
+    from vfm_vae_b200.decoder import default_ops
+    net, G = build(default_ops(), 'cuda')
+    img, multi = net(G.t('z', 'cuda'), G.t('ws', 'cuda'), None, None)
+    assert img.dtype == torch.float32
+    assert rel_err(img, G.t('img')) <= 4e-3
+    for i, m in enumerate(multi):
+        assert rel_err(m, G.t(f'multi{i}')) <= 4e-3

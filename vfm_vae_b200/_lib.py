@@ -13,19 +13,19 @@ VFM_F16, VFM_F32, VFM_F64 = 0, 1, 2
 VFM_OK, VFM_ERR_NO_KERNEL, VFM_ERR_INVALID, VFM_ERR_CUDA, VFM_ERR_WORKSPACE = 0, -1, -2, -3, -4
 NOISE_NONE, NOISE_HW, NOISE_N1HW = 0, 1, 2
 
-_i32, _i64, _f32, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+_i32, _i64, _f32, _f64, _vp, _sz = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p, C.c_size_t
 
 
 class BiasActParams(C.Structure):
     _fields_ = [('x', _vp), ('b', _vp), ('xref', _vp), ('yref', _vp), ('dy', _vp), ('y', _vp), ('db', _vp),
-                ('dtype', _i32), ('grad', _i32), ('act', _i32), ('alpha', _f32), ('gain', _f32), ('clamp', _f32),
+                ('dtype', _i32), ('grad', _i32), ('act', _i32), ('alpha', _f64), ('gain', _f64), ('clamp', _f64),
                 ('size_x', _i64), ('size_b', _i64), ('step_b', _i64)]
 
 
 class Upfirdn2dParams(C.Structure):
     _fields_ = [('x', _vp), ('f', _vp), ('y', _vp), ('dtype', _i32),
                 ('upx', _i32), ('upy', _i32), ('downx', _i32), ('downy', _i32),
-                ('padx0', _i32), ('pady0', _i32), ('flip', _i32), ('gain', _f32),
+                ('padx0', _i32), ('pady0', _i32), ('flip', _i32), ('gain', _f64),
                 ('in_w', _i32), ('in_h', _i32), ('channels', _i32), ('batch', _i32),
                 ('in_stride_w', _i64), ('in_stride_h', _i64), ('in_stride_c', _i64), ('in_stride_n', _i64),
                 ('fw', _i32), ('fh', _i32), ('f_stride_w', _i64), ('f_stride_h', _i64),
@@ -49,7 +49,7 @@ class FilteredLreluParams(C.Structure):
 
 
 class FilteredLreluActParams(C.Structure):
-    _fields_ = [('x', _vp), ('s', _vp), ('dtype', _i32), ('gain', _f32), ('slope', _f32), ('clamp', _f32),
+    _fields_ = [('x', _vp), ('s', _vp), ('dtype', _i32), ('gain', _f64), ('slope', _f64), ('clamp', _f64),
                 ('write_signs', _i32), ('read_signs', _i32),
                 ('x_w', _i32), ('x_h', _i32), ('channels', _i32), ('batch', _i32),
                 ('x_stride_w', _i64), ('x_stride_h', _i64), ('x_stride_c', _i64), ('x_stride_n', _i64),

@@ -13,7 +13,7 @@ namespace {
 
 struct BiasActArgs {
     const void* x; const void* b; const void* xref; const void* yref; const void* dy; void* y; float* db;
-    int grad; float alpha, gain, clamp;
+    int grad; double alpha, gain, clamp;
     int64_t size_x, size_b, step_b;
     int64_t vec_per_block;  // contiguous span of vectors handled by one block
 };
@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
     const bool small = p.size_x < (int64_t)0x7fffffff;
 
     for (int64_t v0 = v_begin + threadIdx.x; v0 < v_end; v0 += (int64_t)blockDim.x * UNROLL) {
-        T xv[UNROLL][VEC], rv[UNROLL][VEC], yv[UNROLL][VEC], dv[UNROLL][VEC];
+        struct alignas(MODE == 2 ? sizeof(T) : 16) Vec { T e[VEC]; };
+        Vec xv[UNROLL], rv[UNROLL], yv[UNROLL], dv[UNROLL];
         bool act[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
@@ -118,15 +119,15 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
             act[u] = v < v_end;
             if (!act[u]) continue;
             if (MODE == 2) {
-                xv[u][0] = ((const T*)p.x)[v];
-                if (p.xref) rv[u][0] = ((const T*)p.xref)[v];
-                if (p.yref) yv[u][0] = ((const T*)p.yref)[v];
-                if (p.dy) dv[u][0] = ((const T*)p.dy)[v];
+                xv[u].e[0] = ((const T*)p.x)[v];
+                if (p.xref) rv[u].e[0] = ((const T*)p.xref)[v];
+                if (p.yref) yv[u].e[0] = ((const T*)p.yref)[v];
+                if (p.dy) dv[u].e[0] = ((const T*)p.dy)[v];
             } else {
-                *(uint4*)xv[u] = ldg_stream((const uint4*)p.x + v);
-                if (p.xref) *(uint4*)rv[u] = ldg_stream((const uint4*)p.xref + v);
-                if (p.yref) *(uint4*)yv[u] = ldg_stream((const uint4*)p.yref + v);
-                if (p.dy) *(uint4*)dv[u] = ldg_stream((const uint4*)p.dy + v);
+                *(uint4*)&xv[u] = ldg_stream((const uint4*)p.x + v);
+                if (p.xref) *(uint4*)&rv[u] = ldg_stream((const uint4*)p.xref + v);
+                if (p.yref) *(uint4*)&yv[u] = ldg_stream((const uint4*)p.yref + v);
+                if (p.dy) *(uint4*)&dv[u] = ldg_stream((const uint4*)p.dy + v);
             }
         }
 #pragma unroll
@@ -139,14 +140,15 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
                 if (small) c0 = (int64_t)(((uint32_t)e0 / (uint32_t)p.step_b) % (uint32_t)p.size_b);
                 else c0 = (e0 / p.step_b) % p.size_b;
             }
-            T out[VEC];
+            Vec outv;
+            T* out = outv.e;
             S sum = (S)0;
 #pragma unroll
             for (int k = 0; k < VEC; k++) {
                 int64_t c = (MODE == 1) ? c0 + k : c0;
                 S b = p.b ? to_acc(((const T*)p.b)[c]) : (S)0;
-                S r = bias_act_elem<A, S>(to_acc(xv[u][k]), b, p.xref ? to_acc(rv[u][k]) : (S)0,
-                                          p.yref ? to_acc(yv[u][k]) : (S)0, p.dy ? to_acc(dv[u][k]) : (S)1,
+                S r = bias_act_elem<A, S>(to_acc(xv[u].e[k]), b, p.xref ? to_acc(rv[u].e[k]) : (S)0,
+                                          p.yref ? to_acc(yv[u].e[k]) : (S)0, p.dy ? to_acc(dv[u].e[k]) : (S)1,
                                           G, alpha, gain, clamp);
                 out[k] = from_acc<T, S>(r);
                 if (want_db) {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
                 }
             }
             if (MODE == 2) ((T*)p.y)[v] = out[0];
-            else stg_stream((uint4*)p.y + v, *(const uint4*)out);
+            else stg_stream((uint4*)p.y + v, *(const uint4*)&outv);
             if (want_db && MODE != 1) {
                 // lanes of a warp usually sit in the same (n,c) row: one shuffle reduction, one shared atomic
                 unsigned mask = __activemask();
@@ -199,6 +201,9 @@ int launch_mode(const BiasActArgs& a0, int mode, cudaStream_t stream) {
     else if (mode == 1) kern = bias_act_kernel<T, A, 1>;
     else kern = bias_act_kernel<T, A, 2>;
     if (smem > 48 * 1024) VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ntens = 2 + (a.xref ? 1 : 0) + (a.yref ? 1 : 0) + (a.dy ? 1 : 0);
+    KernelTimer timer(a.grad == 0 ? "bias_act_fwd" : (a.grad == 1 ? "bias_act_grad" : "bias_act_grad2"), stream, 0.0,
+                      (double)ntens * (double)a.size_x * sizeof(T) + (double)a.size_b * sizeof(T));
     kern<<<(unsigned)blocks, threads, smem, stream>>>(a);
     return launch_status("bias_act_kernel");
 }

@@ -17,7 +17,19 @@ constexpr int kNumSMs = 148;  // B200
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
-#define VFM_CHECK_ARG(cond, ...)                 \
+// Scope guard around one kernel launch (or a short launch sequence): when vfm_timing_enable(1) is active it records a
+// CUDA event before and after on the launching stream, tagged with the algorithmic FLOPs / bytes of the launch, so that
+// bench.py can report achieved TFLOP/s or GB/s per kernel from inside the timed region.  Free when timing is off.
+bool timing_enabled();
+class KernelTimer {
+public:
+    KernelTimer(const char* name, cudaStream_t stream, double flops, double bytes);
+    ~KernelTimer();
+private:
+    const char* name_; cudaStream_t stream_; double flops_, bytes_; cudaEvent_t e0_; bool on_;
+};
+
+#define VFM_CHECK_ARG(cond, ...)             \
     do {                                         \
         if (!(cond)) {                           \
             vfm::set_error(__VA_ARGS__);         \

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) filtered_lrelu_kernel(FlrArgs p) {
 // ------------------------------------------------------------------------------------------------------------
 struct FlrActArgs {
     void* x; uint8_t* s;
-    float gain, slope, clamp;
+    double gain, slope, clamp;
     int x_w, x_h, channels, batch;
     int64_t xsw, xsh, xsc, xsn;
     int s_w, s_h, s_ofs_x, s_ofs_y;
@@ -262,6 +262,10 @@ int launch_fused(FlrArgs a, int sign, size_t smem, cudaStream_t stream) {
     if (smem > 48 * 1024) VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (int64_t)a.tiles_x * a.tiles_y * a.channels * a.batch;
     if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu: grid too large"); return VFM_ERR_INVALID; }
+    double planes = (double)a.channels * a.batch;
+    KernelTimer timer("filtered_lrelu_fused", stream, 0.0,
+                      ((double)a.x_w * a.x_h + (double)a.y_w * a.y_h) * planes * sizeof(T) + (double)a.channels * sizeof(T) +
+                      (sign ? planes * a.s_h * a.s_w_bytes : 0.0));
     kern<<<(unsigned)blocks, 256, smem, stream>>>(a);
     return launch_status("filtered_lrelu_kernel");
 }

@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(ConvArgs p) {
 template <class T>
 int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     dim3 grid(ceil_div(a.Hout * a.Wout, CBM), ceil_div(a.Cout, CBN), a.N);
+    KernelTimer timer(a.aux_sum ? "modconv_generic_dgrad" : "modconv_generic_conv", stream,
+                      2.0 * a.N * a.Hout * a.Wout * a.Cout * (double)a.Cin * a.taps.ntaps / (a.sd * a.sd),
+                      ((double)a.N * a.Cin * a.Hin * a.Win + (double)a.N * a.Cout * a.Hout * a.Wout) * sizeof(T));
     conv_generic_kernel<T><<<grid, 256, 0, stream>>>(a);
     return launch_status("modconv conv_generic_kernel");
 }
@@ -307,6 +310,7 @@ int run_wgrad(int dtype, WgradArgs a, cudaStream_t stream) {
     a.chunks = (int)ceil_div64(total, a.chunk_pix);
     dim3 grid(ceil_div(a.Co, WBM), ceil_div(a.Ci, WBN), a.taps.ntaps * a.chunks);
     if (grid.z > 65535 || grid.y > 65535) { set_error("modulated_conv2d: wgrad grid too large"); return VFM_ERR_INVALID; }
+    KernelTimer timer("modconv_generic_wgrad", stream, 2.0 * a.N * a.Hd * a.Wd * a.Co * (double)a.Ci * a.taps.ntaps / (a.sd * a.sd), 0.0);
     switch (dtype) {
         case VFM_F16: wgrad_generic_kernel<__half><<<grid, 256, 0, stream>>>(a); break;
         case VFM_F32: wgrad_generic_kernel<float><<<grid, 256, 0, stream>>>(a); break;

@@ -21,7 +21,7 @@ namespace {
 struct UpfirdnArgs {
     const void* x; const float* f; void* y; const float* add;
     int upx, upy, downx, downy, padx0, pady0, flip;
-    float gain;
+    double gain;
     int in_w, in_h, channels, batch;
     int64_t isw, ish, isc, isn;
     int fw, fh; int64_t fsw, fsh;
@@ -36,6 +36,7 @@ struct UpfirdnArgs {
 template <class T>
 __global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnArgs p, int64_t total, int c_fastest) {
     typedef typename Acc<T>::type S;
+    const float gain32 = (float)p.gain;   // taps are scaled in fp32, as the reference scales its fp32 filter tensor
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         int ox, oy, c, n;
         int64_t r = idx;
@@ -61,10 +62,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnArgs p, int64_t 
                 int ix = (ux + tx) / p.upx;
                 if (ix < 0 || ix >= p.in_w) continue;
                 int fx = p.flip ? tx : p.fw - 1 - tx;
-                acc += to_acc(xp[(int64_t)iy * p.ish + (int64_t)ix * p.isw]) * (S)__ldg(&p.f[fy * p.fsh + fx * p.fsw]);
+                acc += to_acc(xp[(int64_t)iy * p.ish + (int64_t)ix * p.isw]) * (S)(__ldg(&p.f[fy * p.fsh + fx * p.fsw]) * gain32);
             }
         }
-        acc *= (S)p.gain;
         if (p.add) acc += (S)p.add[(int64_t)n * p.add_sn + (int64_t)oy * p.add_sh + ox];
         ((T*)p.y)[(int64_t)n * p.osn + (int64_t)c * p.osc + (int64_t)oy * p.osh + (int64_t)ox * p.osw] = from_acc<T, S>(acc);
     }
@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
     // taps: store as correlation taps with the gain folded in
     for (int i = threadIdx.x; i < FW * FH; i += blockDim.x) {
         int ty = i / FW, tx = i - ty * FW;
-        float v = 0.f;
+        S v = (S)0;
         if (tx < p.fw && ty < p.fh) {
             int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
-            v = p.f[fy * p.fsh + fx * p.fsw] * p.gain;
+            v = (S)(p.f[fy * p.fsh + fx * p.fsw] * (float)p.gain);   // product in fp32: the reference scales its fp32 filter tensor
         }
-        s_f[i] = (S)v;
+        s_f[i] = v;
     }
 
     // tile origin in output coordinates; (ox0*DOWN - pad0) is a multiple of UP by construction of xstart/ystart
@@ -221,6 +221,8 @@ int launch_tiled(UpfirdnArgs a, cudaStream_t stream) {
     a.tiles_y = ceil_div(a.out_h - a.ystart, C::TH);
     int64_t blocks = (int64_t)a.tiles_x * a.tiles_y * a.channels * a.batch;
     if (blocks > 0x7fffffffLL) { set_error("upfirdn2d: grid too large"); return VFM_ERR_INVALID; }
+    KernelTimer timer("upfirdn2d_tiled", stream, 0.0,
+                      ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T) + (double)a.fw * a.fh * 4);
     upfirdn2d_tiled<T, UP, DOWN, FW, FH><<<(unsigned)blocks, 256, 0, stream>>>(a);
     return launch_status("upfirdn2d_tiled");
 }
@@ -242,6 +244,8 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
     int64_t blocks = ceil_div64(total, 256);
     int64_t cap = (int64_t)kNumSMs * 32;
     if (blocks > cap) blocks = cap;
+    KernelTimer timer("upfirdn2d_generic", stream, 0.0,
+                      ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T) + (double)a.fw * a.fh * 4);
     upfirdn2d_generic<T><<<(unsigned)blocks, 256, 0, stream>>>(a, total, c_fastest);
     return launch_status("upfirdn2d_generic");
 }

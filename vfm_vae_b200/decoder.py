@@ -1,0 +1,401 @@
+"""Host-side mirror of the reference's legacy pixel decoder (``use_convnext=False``): the caller of the hot-path ops.
+
+This is the path BASELINE.json's north_star describes: networks/generator.py ``SynthesisNetwork`` built from
+``SynthesisLayer`` / ``ToRGBLayer`` (generator.py:188-310), ``SynthesisBlock`` (generator.py:320-576) and the z-concat /
+self-attention / multi-scale-output plumbing around them (generator.py:655-912, networks/utils/gigagan_utils.py,
+networks/utils/convnext_utils.py:197-257, networks/utils/shared.py).  Every modulated conv, bias_act and upfirdn2d goes
+through the sm_100a kernels; the rest (1x1/depthwise z-convs, GroupNorm, self-attention at <= 32x32 tokens, pixel
+shuffle) is out-of-scope glue and uses stock torch modules, exactly as the reference does.
+
+Module and parameter names equal the reference's, so a reference ``state_dict`` loads with ``strict=True`` (tested
+against a golden checkpoint in tests/test_decoder.py).  The reference decoder itself also runs unchanged on these
+kernels via ``vfm_vae_b200.integration.install()``; this mirror exists because the reference cannot travel to the
+benchmark box.
+
+``ops`` injection: the constructor takes an ``ops`` namespace (default: the CUDA ops).  Tests pass the CPU oracle there
+to check this file's host logic against the golden vectors without a GPU; the product default never touches the oracle.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def default_ops():
+    from .torch_utils.ops import bias_act, upfirdn2d
+    from .torch_utils.ops.modulated_conv2d import modulated_conv2d
+    return SimpleNamespace(bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
+                           setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d,
+                           modulated_conv2d=modulated_conv2d)
+
+
+# ------------------------------------------------------------------------------------------- small shared layers
+
+class FullyConnectedLayer(nn.Module):
+    """Equalised-lr linear layer (networks/utils/shared.py:24-106)."""
+
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1.0, weight_init=1.0, bias_init=0.0):
+        super().__init__()
+        self.in_features, self.out_features, self.activation = in_features, out_features, activation
+        self.weight = nn.Parameter(torch.randn(out_features, in_features) * (weight_init / lr_multiplier))
+        self.bias = nn.Parameter(torch.full((out_features,), bias_init / lr_multiplier)) if bias else None
+        self.weight_gain = lr_multiplier / math.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        w = self.weight.to(x.dtype) * self.weight_gain
+        b = self.bias.to(x.dtype) * self.bias_gain if self.bias is not None else None
+        if self.activation == 'linear':
+            return torch.addmm(b.unsqueeze(0), x, w.t()) if b is not None else x.matmul(w.t())
+        y = x.matmul(w.t())
+        if b is not None:
+            y = y + b
+        return {'relu': F.relu, 'lrelu': lambda t: F.leaky_relu(t, 0.2), 'gelu': F.gelu}[self.activation](y)
+
+
+class StyleSplit(nn.Module):
+    """w -> 3C -> m1*m2+m3 (networks/utils/shared.py:166-175)."""
+
+    def __init__(self, in_channels, out_channels, **kwargs):
+        super().__init__()
+        self.proj = FullyConnectedLayer(in_channels, 3 * out_channels, **kwargs)
+
+    def forward(self, x):
+        m1, m2, m3 = self.proj(x).chunk(3, 1)
+        return m1 * m2 + m3
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+class ChannelRMSNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(dim, 1, 1))
+
+    def forward(self, x):
+        return F.normalize(x, dim=1) * self.scale * self.gamma
+
+
+class SelfAttention(nn.Module):
+    """networks/utils/gigagan_utils.py:46-91 (null key/value, SDPA)."""
+
+    def __init__(self, dim, dim_head=64, heads=8):
+        super().__init__()
+        self.heads = heads
+        inner = dim_head * heads
+        self.norm = ChannelRMSNorm(dim)
+        self.to_q = nn.Conv2d(dim, inner, 1, bias=False)
+        self.to_k = nn.Conv2d(dim, inner, 1, bias=False)
+        self.to_v = nn.Conv2d(dim, inner, 1, bias=False)
+        self.null_kv = nn.Parameter(torch.randn(2, heads, dim_head) * 0.02)
+        self.to_out = nn.Conv2d(inner, dim, 1, bias=False)
+        nn.init.zeros_(self.to_out.weight)
+
+    def forward(self, fmap):
+        B, _, H, W = fmap.shape
+        h = self.heads
+        fmap = self.norm(fmap)
+
+        def split(t):   # b (h d) x y -> b h (x y) d
+            return t.reshape(B, h, -1, H * W).transpose(2, 3)
+
+        q, k, v = split(self.to_q(fmap)), split(self.to_k(fmap)), split(self.to_v(fmap))
+        nk, nv = (t[None, :, None, :].expand(B, -1, -1, -1).to(k.dtype) for t in self.null_kv)
+        k = torch.cat((nk, k), dim=-2)
+        v = torch.cat((nv, v), dim=-2)
+        out = F.scaled_dot_product_attention(q, k, v)
+        out = out.transpose(2, 3).reshape(B, -1, H, W)
+        return self.to_out(out)
+
+
+class SelfAttentionBlock(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, ff_mult=4):
+        super().__init__()
+        self.attn = SelfAttention(dim=dim, dim_head=dim_head, heads=heads)
+        hidden = int(dim * ff_mult)
+        proj2 = nn.Conv2d(hidden, dim, 1)
+        nn.init.zeros_(proj2.weight)
+        self.ff = nn.Sequential(ChannelRMSNorm(dim), nn.Conv2d(dim, hidden, 1), nn.GELU(), proj2)
+
+    def forward(self, x):
+        x = self.attn(x) + x
+        return self.ff(x) + x
+
+
+_BLUR_TAPS = {'3x3': [1, 2, 1], '4x4': [1, 3, 3, 1], '5x5': [1, 4, 6, 4, 1]}
+
+
+class SeparableUpsampleWithFixedBlur(nn.Module):
+    """GN -> dw3x3 -> 1x1 -> PixelShuffle(2) -> replicate-pad -> fixed binomial blur
+    (networks/utils/convnext_utils.py:197-257).  Used by the legacy path only for ``last_upsample_conv``."""
+
+    def __init__(self, in_channels, out_channels, upscale_factor=2, blur_kernel='3x3', pre_normalize=True, use_gaussian_blur=True):
+        super().__init__()
+        self.out_channels, self.pre_normalize, self.use_gaussian_blur = out_channels, pre_normalize, use_gaussian_blur
+        nc = in_channels if pre_normalize else out_channels
+        self.norm = nn.GroupNorm(min(32, nc // 4), nc)
+        self.depthwise = nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False)
+        self.pointwise = nn.Conv2d(in_channels, out_channels * upscale_factor ** 2, 1, bias=False)
+        self.shuffle = nn.PixelShuffle(upscale_factor)
+        if use_gaussian_blur:
+            k = torch.tensor(_BLUR_TAPS[blur_kernel] if isinstance(blur_kernel, str) else blur_kernel, dtype=torch.float32)
+            k2 = torch.outer(k, k)
+            k2 = k2 / k2.sum()
+            kh, kw = k2.shape
+            ph, pw = (kh - 1) // 2, (kw - 1) // 2
+            self.pad = (pw, pw + int(kw % 2 == 0), ph, ph + int(kh % 2 == 0))
+            self.register_buffer('blur_weight', k2[None, None].repeat(out_channels, 1, 1, 1))
+
+    def forward(self, x):
+        if self.pre_normalize:
+            x = self.shuffle(self.pointwise(self.depthwise(self.norm(x))))
+        else:
+            x = self.norm(self.shuffle(self.pointwise(self.depthwise(x))))
+        if self.use_gaussian_blur:
+            x = F.conv2d(F.pad(x, self.pad, mode='replicate'), self.blur_weight.to(x.dtype) if not torch.is_autocast_enabled() else self.blur_weight,
+                         groups=self.out_channels)
+        return x
+
+
+# ------------------------------------------------------------------------------------------- hot-path layers
+
+class SynthesisLayer(nn.Module):
+    """modulated 3x3 conv (+2x up) -> noise -> bias + lrelu + clamp [-> layer-scaled residual]   (generator.py:188-281)"""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, use_noise=True, activation='lrelu',
+                 resample_filter=(1, 3, 3, 1), conv_clamp=None, channels_last=False, layer_scale_init=1e-5, residual=False,
+                 gn_groups=32, ops=None):
+        super().__init__()
+        if residual:
+            assert in_channels == out_channels and up == 1
+        self.ops = ops
+        self.in_channels, self.out_channels, self.w_dim, self.resolution, self.up = in_channels, out_channels, w_dim, resolution, up
+        self.use_noise, self.activation, self.conv_clamp, self.residual = use_noise, activation, conv_clamp, residual
+        self.register_buffer('resample_filter', ops.setup_filter(list(resample_filter)))
+        self.padding = kernel_size // 2
+        self.act_gain = ops.def_gain(activation)
+        if use_noise:
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = nn.Parameter(torch.zeros([]))
+        self.affine = StyleSplit(w_dim, in_channels, bias_init=1)
+        self.weight = nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = nn.Parameter(torch.zeros([out_channels]))
+        if residual:
+            self.norm = GroupNorm32(gn_groups, out_channels)
+            self.gamma = nn.Parameter(layer_scale_init * torch.ones([1, out_channels, 1, 1]))
+
+    def forward(self, x, w, noise_mode='const', fused_modconv=True, gain=1):
+        assert noise_mode in ('const', 'random', 'none')
+        dtype = x.dtype
+        r_in = self.resolution // self.up
+        assert x.shape[1] == self.in_channels and x.shape[2] == r_in and x.shape[3] == r_in, f'bad input shape {tuple(x.shape)}'
+        noise = None
+        if self.use_noise and noise_mode == 'random':
+            noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
+        if self.use_noise and noise_mode == 'const':
+            noise = self.noise_const * self.noise_strength
+        styles = self.affine(w)
+        if self.residual:
+            x = self.norm(x)
+        y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                      resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+        y = y.to(dtype)
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        y = self.ops.bias_act(y, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+        if self.residual:
+            y = (self.gamma * y).to(dtype).add_(x).mul(np.sqrt(2))
+        return y
+
+
+class ToRGBLayer(nn.Module):
+    """1x1 modulated conv without demodulation -> bias + clamp   (generator.py:284-312)"""
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False, ops=None):
+        super().__init__()
+        self.ops = ops
+        self.in_channels, self.out_channels, self.w_dim, self.conv_clamp = in_channels, out_channels, w_dim, conv_clamp
+        self.affine = StyleSplit(w_dim, in_channels, bias_init=1)
+        self.weight = nn.Parameter(0.1 * torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
+        self.bias = nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+
+    def forward(self, x, w):
+        styles = self.affine(w) * self.weight_gain
+        x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False)
+        return self.ops.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+
+
+class SynthesisBlock(nn.Module):
+    """conv0 (up 2) + 2*num_res_blocks convs (plain, residual alternating, gain sqrt(1/2)) + optional self-attention +
+    multi-scale ToRGB on the running feature sum   (generator.py:320-576, legacy branch)"""
+
+    def __init__(self, block_index, in_channels, out_channels, last_out_channels, w_dim, resolution, img_channels, is_last,
+                 num_res_blocks=1, use_multiscale_output=False, architecture='skip', resample_filter=(1, 3, 3, 1), conv_clamp=None,
+                 use_fp16=False, attn_depth=0, attn_heads=8, attn_ff_mult=4, use_gaussian_blur=True, ops=None, **layer_kwargs):
+        super().__init__()
+        assert architecture in ('orig', 'skip')
+        assert architecture == 'skip' or not use_multiscale_output
+        if in_channels == 0:
+            raise NotImplementedError('SynthesisInput blocks (in_channels == 0) are not used by the f16d32 configs')
+        self.ops = ops
+        self.in_channels, self.out_channels, self.last_out_channels = in_channels, out_channels, last_out_channels
+        self.w_dim, self.resolution, self.img_channels, self.is_last = w_dim, resolution, img_channels, is_last
+        self.architecture, self.use_fp16, self.use_multiscale_output = architecture, use_fp16, use_multiscale_output
+        self.register_buffer('resample_filter', ops.setup_filter(list(resample_filter)))
+        blur_kernel = '3x3' if block_index <= 2 else '5x5'
+        self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2, resample_filter=resample_filter,
+                                    conv_clamp=conv_clamp, ops=ops, **layer_kwargs)
+        convs = []
+        for _ in range(num_res_blocks):
+            convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, ops=ops, **layer_kwargs))
+            convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, residual=True, ops=ops, **layer_kwargs))
+        self.convs1 = nn.ModuleList(convs)
+        self.num_conv = 1 + len(convs)
+        self.num_torgb = 0
+        if is_last or architecture == 'skip':
+            self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, ops=ops)
+            self.num_torgb = 1
+        if use_multiscale_output and last_out_channels is not None:
+            self.last_upsample_conv = SeparableUpsampleWithFixedBlur(last_out_channels, out_channels, upscale_factor=2,
+                                                                     use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel)
+        self.self_attns = nn.ModuleList([SelfAttentionBlock(out_channels, dim_head=out_channels // attn_heads, heads=attn_heads, ff_mult=attn_ff_mult)
+                                         for _ in range(attn_depth)]) if attn_depth > 0 else None
+
+    def forward(self, x, x_sum, img, ws, force_fp32=False, fused_modconv=True, **layer_kwargs):
+        w_iter = iter(ws.unbind(dim=1))
+        on_cuda = ws.device.type == 'cuda'
+        fp16 = on_cuda and self.use_fp16 and not force_fp32
+        dtype = torch.float16 if fp16 else torch.float32
+        amp = dict(device_type='cuda', enabled=fp16, dtype=torch.float16)
+        x = x.to(dtype=dtype)
+        x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+        for conv in self.convs1:
+            x = conv(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
+        if self.self_attns is not None:
+            with torch.amp.autocast(**amp):
+                for attn in self.self_attns:
+                    x = attn(x)
+        x = x.to(dtype=dtype)
+        if self.use_multiscale_output:
+            with torch.amp.autocast(**amp):
+                x_sum = self.last_upsample_conv(x_sum) + x if self.last_out_channels is not None else x
+                img = self.torgb(x_sum, next(w_iter))
+            img = img.to(dtype=torch.float32)
+        else:
+            if img is not None:
+                img = self.ops.upsample2d(img, self.resample_filter)
+            if self.is_last or self.architecture == 'skip':
+                y = self.torgb(x, next(w_iter)).to(dtype=torch.float32)
+                img = img.add_(y) if img is not None else y
+        assert x.dtype == dtype
+        return x, x_sum, img
+
+
+class SynthesisNetwork(nn.Module):
+    """Legacy (use_convnext=False) pixel decoder: z [N,z_dim,zr,zr] + ws [N,num_ws,w_dim] -> img [N,3,R,R] fp32 and the
+    lower-resolution multi-scale images   (generator.py:655-912)."""
+
+    def __init__(self, w_dim, img_resolution, img_channels=3, channel_base=32768, channel_max=512, num_fp16_res=3, conv_clamp=None,
+                 num_blocks=6, num_res_blocks=3, z_resolution=16, z_dim=8, concat_z_block_indices=(), concat_z_mapped_dims=(),
+                 how_to_process_concat_z='unshuffle', activation_for_concat_z='gelu', use_multiscale_output=False,
+                 attn_block_indices=(), attn_depths=(), use_self_attn=False, use_cross_attn=False, use_convnext=False,
+                 use_gaussian_blur=True, c_dim=0, ops=None, **block_kwargs):
+        super().__init__()
+        if use_convnext:
+            raise NotImplementedError('the ConvNeXt decoder variant calls none of the hot-path ops (SURVEY.md 0.2); it is a "next" row')
+        if use_cross_attn:
+            raise NotImplementedError('cross-attention is unused by the f16d32 configs (conditional: False)')
+        assert how_to_process_concat_z == 'unshuffle', 'only the unshuffle z-processing of the shipped configs is mirrored'
+        ops = ops if ops is not None else default_ops()
+        self.ops = ops
+        self.c_dim, self.w_dim, self.img_resolution, self.img_channels = c_dim, w_dim, img_resolution, img_channels
+        self.num_blocks, self.num_fp16_res = num_blocks, num_fp16_res
+        self.z_resolution, self.z_dim = z_resolution, z_dim
+        self.concat_z_block_indices = list(concat_z_block_indices)
+        self.use_multiscale_output = use_multiscale_output
+        res0 = img_resolution // (2 ** (num_blocks - 1))
+        self.block_resolutions = [res0 * 2 ** i for i in range(num_blocks)]
+        scale = img_resolution / 256
+        channels = {i: min(channel_base // int(r / scale), channel_max) for i, r in enumerate(self.block_resolutions)}
+        fp16_idx = num_blocks - num_fp16_res
+
+        self.z_convs = nn.ModuleDict()
+        z_dims = {}
+        for idx in self.concat_z_block_indices:
+            res = self.block_resolutions[idx]
+            mapped = concat_z_mapped_dims[idx] if len(concat_z_mapped_dims) > 0 else None
+            layers = []
+            if res < z_resolution * 2:
+                f = int(z_resolution / res * 2)
+                cin = int(z_dim * f ** 2)
+                out = mapped if mapped is not None else cin
+                layers += [nn.PixelUnshuffle(f), self._conv3x3(cin, out, activation_for_concat_z), self._conv1x1(out, out)]
+            elif res == z_resolution * 2:
+                out = mapped if mapped is not None else z_dim
+                layers += [self._conv3x3(z_dim, out, activation_for_concat_z), self._conv1x1(out, out)]
+            else:
+                f = int(res / z_resolution / 2)
+                out = mapped if mapped is not None else z_dim
+                layers += [self._conv3x3(z_dim, int(out * f ** 2), activation_for_concat_z), nn.PixelShuffle(f), self._conv1x1(out, out)]
+            self.z_convs[str(idx)] = nn.Sequential(*layers)
+            z_dims[idx] = out
+
+        self.blocks = nn.ModuleDict()
+        self.num_ws = 0
+        for idx in range(num_blocks):
+            cin = (channels[idx - 1] if idx > 0 else 0) + z_dims.get(idx, 0)
+            depth = attn_depths[list(attn_block_indices).index(idx)] if (use_self_attn and idx in attn_block_indices) else 0
+            block = SynthesisBlock(block_index=idx, in_channels=cin, out_channels=channels[idx],
+                                   last_out_channels=channels[idx - 1] if idx > 0 else None, w_dim=w_dim,
+                                   resolution=self.block_resolutions[idx], img_channels=img_channels, is_last=(idx == num_blocks - 1),
+                                   use_fp16=(idx >= fp16_idx), conv_clamp=conv_clamp, num_res_blocks=num_res_blocks,
+                                   use_multiscale_output=use_multiscale_output, use_gaussian_blur=use_gaussian_blur,
+                                   attn_depth=depth, ops=ops, **block_kwargs)
+            self.num_ws += block.num_conv + block.num_torgb
+            self.blocks[str(idx)] = block
+
+    @staticmethod
+    def _act(name):
+        return {'lrelu': lambda: nn.LeakyReLU(negative_slope=0.2), 'silu': nn.SiLU, 'gelu': nn.GELU}[name]()
+
+    def _conv3x3(self, cin, cout, activation):
+        return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), nn.Conv2d(cin, cout, 1, bias=False),
+                             GroupNorm32(min(32, cout), cout), self._act(activation))
+
+    def _conv1x1(self, cin, cout):
+        return nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), GroupNorm32(min(32, cout), cout))
+
+    def forward(self, z, ws, text=None, text_mask=None, **block_kwargs):
+        ws = ws.to(torch.float32)
+        x = x_sum = img = None
+        multiscale = []
+        w_idx = 0
+        for idx in range(self.num_blocks):
+            block = self.blocks[str(idx)]
+            n_w = block.num_conv + block.num_torgb
+            cur_ws = ws.narrow(1, w_idx, n_w)
+            w_idx += n_w
+            if idx in self.concat_z_block_indices:
+                with torch.amp.autocast('cuda', enabled=bool(block.use_fp16 and z.device.type == 'cuda'), dtype=torch.float16):
+                    zc = self.z_convs[str(idx)](z)
+                    x = torch.cat([x, zc], dim=1) if x is not None else zc
+            x, x_sum, img = block(x, x_sum, img, cur_ws, **block_kwargs)
+            if not block.is_last:
+                multiscale.append(img)
+        return img, multiscale[::-1]
+
+
+#: SynthesisNetwork kwargs of the shipped f16d32 configs with use_convnext=False (configs/vfm_vae_f16d32_siglip2_stage_1_*.yaml:32-99)
+F16D32_LEGACY_KWARGS = dict(
+    w_dim=512, img_resolution=256, img_channels=3, z_resolution=16, z_dim=512,
+    concat_z_block_indices=[0, 1, 2, 3], concat_z_mapped_dims=[512, 256, 128, 128], how_to_process_concat_z='unshuffle',
+    activation_for_concat_z='lrelu', attn_block_indices=[0, 1, 2], attn_depths=[2, 2, 2], use_self_attn=True, use_cross_attn=False,
+    use_convnext=False, use_multiscale_output=True, num_blocks=6, num_fp16_res=3, conv_clamp=256, channel_base=32768,
+    channel_max=512, num_res_blocks=2, architecture='skip')

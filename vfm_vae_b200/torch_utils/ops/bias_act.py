@@ -64,6 +64,10 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
 
     trivial = (act == 'linear' and gain == 1 and clamp < 0)
     needs_x = ('x' in spec.ref) or spec.has_2nd_grad
+    # The clamp mask of the gradient needs y.  The reference only keeps y for activations whose derivative is written in
+    # terms of y, so its CUDA path lets gradients through a clamped *linear* bias_act (ToRGB) while its impl='ref' path
+    # does not; parity is defined against impl='ref', hence y is also kept for linear + clamp.
+    needs_y = ('y' in spec.ref) or (clamp >= 0 and 'x' not in spec.ref)
 
     def _mem_format(t):
         return torch.channels_last if t.ndim > 2 and t.stride(1) == 1 else torch.contiguous_format
@@ -78,7 +82,7 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if not trivial or b is not _null_tensor:
                 y = _plugin.bias_act(x, b, _null_tensor, _null_tensor, _null_tensor, 0, dim, spec.cuda_idx, alpha, gain, clamp)
             ctx.save_for_backward(x if needs_x else _null_tensor, b if needs_x else _null_tensor,
-                                  y if 'y' in spec.ref else _null_tensor)
+                                  y if needs_y else _null_tensor)
             ctx.b_numel = b.numel()
             return y
 
@@ -93,9 +97,13 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
                     if ctx.needs_input_grad[1]:
                         db = dx.sum([i for i in range(dx.ndim) if i != dim])
                 else:
-                    dx, db = BiasActCudaGrad.apply(dy, x, b, y, bool(ctx.needs_input_grad[1]))
+                    # fused fp32-accumulated db for fp16/fp32; fp64 (test-only dtype) keeps full precision via a plain sum
+                    fuse_db = bool(ctx.needs_input_grad[1]) and dy.dtype != torch.float64
+                    dx, db = BiasActCudaGrad.apply(dy, x, b, y, fuse_db)
                     if not ctx.needs_input_grad[1]:
                         db = None
+                    elif not fuse_db:
+                        db = dx.sum([i for i in range(dx.ndim) if i != dim])
             return dx, db
 
     class BiasActCudaGrad(torch.autograd.Function):
@@ -123,10 +131,11 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if ctx.needs_input_grad[0]:
                 d_dy, _ = BiasActCudaGrad.apply(d_dx, x, b, y, False)
             if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
-                db32 = torch.zeros([d_dx.shape[dim]], dtype=torch.float32, device=d_dx.device) if ctx.needs_input_grad[2] else None
+                fuse_db = bool(ctx.needs_input_grad[2]) and d_dx.dtype != torch.float64
+                db32 = torch.zeros([d_dx.shape[dim]], dtype=torch.float32, device=d_dx.device) if fuse_db else None
                 d_x = _plugin.bias_act(d_dx, b, x, y, dy, 2, dim, spec.cuda_idx, alpha, gain, clamp, db=db32)
                 if ctx.needs_input_grad[2]:
-                    d_b = db32.to(d_dx.dtype)
+                    d_b = db32.to(d_dx.dtype) if fuse_db else d_x.sum([i for i in range(d_x.ndim) if i != dim])
             return d_dy, d_x, d_b, None, None
 
     _bias_act_cuda_cache[key] = BiasActCuda

@@ -346,6 +346,10 @@ def _modconv_vs_oracle(N, I, O_, H, W, k, up, demod, dtype, noise_kind, generic,
     dict(N=4, I=128, O_=256, H=8, W=8, k=3, up=1, demod=True, noise_kind='const'),
     dict(N=1, I=128, O_=128, H=64, W=64, k=3, up=1, demod=True, noise_kind=None),
     dict(N=2, I=128, O_=128, H=16, W=16, k=1, up=1, demod=False, noise_kind=None),
+    dict(N=2, I=128, O_=128, H=16, W=16, k=3, up=2, demod=True, noise_kind='const'),     # 4-phase transposed conv + strided dgrad
+    dict(N=3, I=256, O_=128, H=8, W=8, k=3, up=2, demod=True, noise_kind='random'),
+    dict(N=2, I=128, O_=128, H=4, W=4, k=3, up=2, demod=True, noise_kind='const'),       # block-0 sized: multi-sample tiles
+    dict(N=1, I=128, O_=256, H=33, W=20, k=3, up=1, demod=True, noise_kind='const'),      # ragged image, partial tiles
 ], ids=lambda c: f"N{c['N']}I{c['I']}O{c['O_']}H{c['H']}k{c['k']}up{c['up']}")
 def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
     _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)

@@ -1,5 +1,9 @@
 // extern "C" entry points of the modulated conv: validation, workspace planning, and dispatch between the tcgen05
 // implicit-GEMM path (modconv_tc.cu) and the generic SIMT path (modconv_generic.cu).
+//
+// forward : coefficients -> stage-1 contraction (x*s' (*) W, scaled by d[n,o])  [-> blur for up=2]  (+ noise)
+// backward: coefficients -> g[n,o], dnoise -> [blur backward] -> data gradient (+ dstyles reduction) -> weight gradient
+//           -> fix-ups for the gradient through d[n,o]
 #include "modconv_common.cuh"
 
 namespace vfm {
@@ -16,10 +20,12 @@ int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, con
 // ---- tensor-core path (modconv_tc.cu) ----
 bool tc_supported(const vfm_modconv_desc& d);
 size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
-int tc_forward(const vfm_modconv_fwd_params& p, const Coefs& k, void* ws, size_t ws_bytes, cudaStream_t stream);
-int tc_backward(const vfm_modconv_bwd_params& p, const Coefs& k, float* g, float* dsum, void* ws, size_t ws_bytes, cudaStream_t stream);
-
-static size_t esize(int dtype) { return dtype == VFM_F16 ? 2 : (dtype == VFM_F32 ? 4 : 8); }
+// stage-1 contraction: x -> z (== y for up=1; noise only added when up == 1)
+int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z,
+                      const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream);
+// gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
+int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 static int validate(const vfm_modconv_desc& d) {
     VFM_CHECK_ARG(d.dtype == VFM_F16 || d.dtype == VFM_F32 || d.dtype == VFM_F64, "modulated_conv2d: unsupported dtype %d", d.dtype);
@@ -29,7 +35,6 @@ static int validate(const vfm_modconv_desc& d) {
     VFM_CHECK_ARG(d.noise_mode >= 0 && d.noise_mode <= 2, "modulated_conv2d: bad noise_mode");
     VFM_CHECK_ARG(d.up == 1 || (d.resample_filter && d.fw >= 1 && d.fh >= 1), "modulated_conv2d: up=2 needs a 2-D resample filter");
     if (d.kh * d.kw > kMaxTaps) { set_error("modulated_conv2d: %dx%d kernels are not supported", d.kh, d.kw); return VFM_ERR_NO_KERNEL; }
-    // expected output size
     int oh, ow;
     if (d.up == 1) { oh = d.in_h + 2 * d.padding - d.kh + 1; ow = d.in_w + 2 * d.padding - d.kw + 1; }
     else {
@@ -40,59 +45,6 @@ static int validate(const vfm_modconv_desc& d) {
     }
     VFM_CHECK_ARG(oh == d.out_h && ow == d.out_w, "modulated_conv2d: out size %dx%d does not match expected %dx%d", d.out_h, d.out_w, oh, ow);
     return VFM_OK;
-}
-
-// stage-1 geometry for up == 2
-struct Stage1 {
-    int zh, zw;            // intermediate size
-    int sn, sd;
-    TapTable taps;         // forward taps
-    // stage-2 resampler
-    int r_up, r_px0, r_py0;
-    // backward of the resampler (torch_utils/ops/upfirdn2d.py:251-269)
-    int rb_px0, rb_py0;
-};
-
-static Stage1 make_stage1(const vfm_modconv_desc& d) {
-    Stage1 s;
-    const int kh = d.kh, kw = d.kw;
-    s.taps.ntaps = kh * kw;
-    if (d.up == 1) {
-        s.zh = d.out_h; s.zw = d.out_w; s.sn = 1; s.sd = 1;
-        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
-            int t = ky * kw + kx;
-            s.taps.off_y[t] = ky - d.padding; s.taps.off_x[t] = kx - d.padding;
-            s.taps.widx[t] = d.flip_weight ? t : (kh - 1 - ky) * kw + (kw - 1 - kx);
-        }
-        s.r_up = 1; s.r_px0 = s.r_py0 = s.rb_px0 = s.rb_py0 = 0;
-    } else if (kh == 1) {
-        // conv2d_resample fast path "1x1 + upsampling": convolve first, then upfirdn2d(up=2) (conv2d_resample.py:101-104)
-        s.zh = d.in_h; s.zw = d.in_w; s.sn = 1; s.sd = 1;
-        s.taps.off_y[0] = s.taps.off_x[0] = 0; s.taps.widx[0] = 0;
-        s.r_up = 2;
-        s.r_px0 = d.padding + (d.fw + 1) / 2; s.r_py0 = d.padding + (d.fh + 1) / 2;
-        // backward of upfirdn2d(up=2): down=2 with pad p0 = fw - px0 - 1
-        s.rb_px0 = d.fw - s.r_px0 - 1; s.rb_py0 = d.fh - s.r_py0 - 1;
-    } else {
-        UpGeom g = up_geometry(d);
-        s.zh = g.zh; s.zw = g.zw; s.sn = 1; s.sd = 2;
-        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
-            int t = ky * kw + kx;
-            s.taps.off_y[t] = g.pyt - ky; s.taps.off_x[t] = g.pxt - kx;
-            s.taps.widx[t] = d.flip_weight ? (kh - 1 - ky) * kw + (kw - 1 - kx) : t;
-        }
-        s.r_up = 1; s.r_px0 = g.bpx0; s.r_py0 = g.bpy0;
-        s.rb_px0 = d.fw - g.bpx0 - 1; s.rb_py0 = d.fh - g.bpy0 - 1;
-    }
-    return s;
-}
-
-// taps for the data gradient: input position of dz for output position of dx
-static void dgrad_taps(const vfm_modconv_desc& d, const Stage1& s, TapTable& t, int& sn, int& sd) {
-    t.ntaps = s.taps.ntaps;
-    // forward: xin = (z*s.sn + off)/s.sd  <=>  z = (xin*s.sd - off)/s.sn ; here s.sn == 1 always
-    sn = s.sd; sd = 1;
-    for (int i = 0; i < t.ntaps; i++) { t.off_y[i] = -s.taps.off_y[i]; t.off_x[i] = -s.taps.off_x[i]; t.widx[i] = s.taps.widx[i]; }
 }
 
 static int call_upfirdn(int dtype, const void* in, void* out, const float* f, int fw, int fh, int up, int down, int px0, int py0, int flip, float gain,
@@ -118,6 +70,8 @@ static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
     return cv.off + 256;
 }
 
+static bool use_tc(const vfm_modconv_desc& d) { return !d.force_generic && tc_supported(d); }
+
 }  // namespace modconv
 }  // namespace vfm
 
@@ -125,14 +79,14 @@ using namespace vfm;
 using namespace vfm::modconv;
 
 extern "C" int vfm_modconv_uses_tensor_cores(const vfm_modconv_desc* d) {
-    if (!d || d->force_generic) return 0;
-    return tc_supported(*d) ? 1 : 0;
+    if (!d) return 0;
+    return use_tc(*d) ? 1 : 0;
 }
 
 extern "C" size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction) {
     if (!d) return 0;
     size_t g = generic_workspace(*d, direction);
-    if (!d->force_generic && tc_supported(*d)) g += tc_workspace_bytes(*d, direction);
+    if (use_tc(*d)) g += tc_workspace_bytes(*d, direction);
     return g;
 }
 
@@ -148,31 +102,30 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
 
     Carver cv(p->workspace, p->workspace_bytes);
     Coefs k; carve_coefs(cv, d, k);
+    k.d = p->dcoefs;
     Stage1 s = make_stage1(d);
-    void* z = nullptr;
+    void* z = p->y;
     if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * s.zw * esize(d.dtype));
     st = compute_coefs(d, p->weight, p->styles, k, p->dcoefs, nullptr, stream); if (st) return st;
-
-    if (!d.force_generic && tc_supported(d)) {
-        cv.off = (cv.off + 255) & ~(size_t)255;
-        return tc_forward(*p, k, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
-    }
-
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
-    ConvArgs a;
-    a.in = p->x; a.w = p->weight;
-    a.w_s_co = (int64_t)d.in_channels * d.kh * d.kw; a.w_s_ci = (int64_t)d.kh * d.kw;
-    a.in_scale = k.iscale; a.out_scale = k.oscale;
-    a.aux = nullptr; a.aux_sum = nullptr;
-    a.N = d.batch; a.Cin = d.in_channels; a.Cout = d.out_channels; a.Hin = d.in_h; a.Win = d.in_w;
-    a.sn = s.sn; a.sd = s.sd; a.taps = s.taps;
-    if (d.up == 1) {
-        a.out = p->y; a.Hout = d.out_h; a.Wout = d.out_w;
-        a.add = p->noise; a.add_sn = noise_sn; a.add_sh = d.out_w;
-        return run_conv(d.dtype, a, stream);
+    const float* s1_noise = (d.up == 1) ? p->noise : nullptr;
+
+    if (use_tc(d)) {
+        cv.off = (cv.off + 255) & ~(size_t)255;
+        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, s1_noise, noise_sn, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        if (st) return st;
+    } else {
+        ConvArgs a;
+        a.in = p->x; a.out = z; a.w = p->weight;
+        a.w_s_co = (int64_t)d.in_channels * d.kh * d.kw; a.w_s_ci = (int64_t)d.kh * d.kw;
+        a.in_scale = k.iscale; a.out_scale = k.oscale;
+        a.add = s1_noise; a.add_sn = noise_sn; a.add_sh = s.zw;
+        a.aux = nullptr; a.aux_sum = nullptr;
+        a.N = d.batch; a.Cin = d.in_channels; a.Cout = d.out_channels; a.Hin = d.in_h; a.Win = d.in_w; a.Hout = s.zh; a.Wout = s.zw;
+        a.sn = s.sn; a.sd = s.sd; a.taps = s.taps;
+        st = run_conv(d.dtype, a, stream); if (st) return st;
     }
-    a.out = z; a.Hout = s.zh; a.Wout = s.zw; a.add = nullptr; a.add_sn = a.add_sh = 0;
-    st = run_conv(d.dtype, a, stream); if (st) return st;
+    if (d.up == 1) return VFM_OK;
     return call_upfirdn(d.dtype, z, p->y, d.resample_filter, d.fw, d.fh, s.r_up, 1, s.r_px0, s.r_py0, 0, (float)(d.up * d.up),
                         d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream);
 }
@@ -192,6 +145,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(p->workspace, p->workspace_bytes);
     Coefs k; carve_coefs(cv, d, k);
+    k.d = p->dcoefs;
     Stage1 s = make_stage1(d);
     void* dz = nullptr;
     if (d.up == 2) dz = cv.take<char>((size_t)N * O * s.zh * s.zw * esize(d.dtype));
@@ -210,20 +164,24 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
         st = run_dnoise(d.dtype, p->dy, N, O, HWo, per_sample, p->dnoise, stream); if (st) return st;
     }
 
-    if (!d.force_generic && tc_supported(d)) {
+    // gradient w.r.t. the stage-1 output
+    const void* dzp = p->dy;
+    if (d.up == 2) {
+        // backward of upfirdn2d (torch_utils/ops/upfirdn2d.py:251-269): swap up/down, flip the filter, same gain
+        st = call_upfirdn(d.dtype, p->dy, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
+                          N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream);
+        if (st) return st;
+        dzp = dz;
+    }
+    if (p->dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
+    if (p->dweight) VFM_CUDA_OK(cudaMemsetAsync(p->dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
+
+    if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
-        st = tc_backward(*p, k, g, dsum, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        st = tc_stage1_backward(d, s, dzp, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
+                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
     } else {
-        // gradient w.r.t. the stage-1 output
-        const void* dzp = p->dy;
-        if (d.up == 2) {
-            // backward of upfirdn2d (torch_utils/ops/upfirdn2d.py:251-269): swap up/down, flip the filter, same gain
-            st = call_upfirdn(d.dtype, p->dy, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
-                              N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream);
-            if (st) return st;
-            dzp = dz;
-        }
         if (p->dx) {
             ConvArgs a;
             a.in = dzp; a.out = p->dx; a.w = p->weight;
@@ -231,12 +189,10 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
             a.in_scale = k.oscale; a.out_scale = k.iscale; a.add = nullptr; a.add_sn = a.add_sh = 0;
             a.aux = p->dstyles ? p->x : nullptr; a.aux_sum = p->dstyles ? dsum : nullptr;
             a.N = N; a.Cin = O; a.Cout = I; a.Hin = s.zh; a.Win = s.zw; a.Hout = d.in_h; a.Wout = d.in_w;
-            dgrad_taps(d, s, a.taps, a.sn, a.sd);
-            if (p->dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
+            dgrad_taps(s, a.taps, a.sn, a.sd);
             st = run_conv(d.dtype, a, stream); if (st) return st;
         }
         if (p->dweight) {
-            VFM_CUDA_OK(cudaMemsetAsync(p->dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
             WgradArgs w;
             w.dy = dzp; w.x = p->x; w.oscale = k.oscale; w.iscale = k.iscale; w.dw = p->dweight;
             w.s_co = (int64_t)I * KK; w.s_ci = KK;

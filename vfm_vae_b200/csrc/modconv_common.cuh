@@ -1,5 +1,6 @@
 // Shared pieces of the modulated-conv implementation: the small "coefficient" kernels (pre-normalisation, demodulation
-// coefficients, gradient fix-ups) and the plan/workspace layout used by both the generic SIMT path and the tcgen05 path.
+// coefficients, gradient fix-ups), the stage-1 geometry (what "conv with up=2" means) and the workspace carver used by
+// both the generic SIMT path and the tcgen05 path.
 #pragma once
 #include "common.cuh"
 
@@ -27,12 +28,15 @@ struct Carver {
     bool ok() const { return off <= cap; }
 };
 
+inline size_t esize(int dtype) { return dtype == VFM_F16 ? 2 : (dtype == VFM_F32 ? 4 : 8); }
+
 struct Coefs {          // fp32 scratch shared by forward and backward
     float* a;           // [O]   weight pre-normalisation (1 unless fp16 && demodulate)
     float* c;           // [N]   style pre-normalisation
     float* wsq;         // [O*I] a^2 * sum_k W^2
     float* iscale;      // [N*I] s' = c * s
     float* oscale;      // [N*O] d * a
+    const float* d;     // [N*O] demodulation coefficients (the caller's dcoefs tensor)
 };
 
 inline void carve_coefs(Carver& cv, const vfm_modconv_desc& d, Coefs& k) {
@@ -41,6 +45,7 @@ inline void carve_coefs(Carver& cv, const vfm_modconv_desc& d, Coefs& k) {
     k.wsq = cv.take<float>((size_t)d.out_channels * d.in_channels);
     k.iscale = cv.take<float>((size_t)d.batch * d.in_channels);
     k.oscale = cv.take<float>((size_t)d.batch * d.out_channels);
+    k.d = nullptr;
 }
 
 // Launches the coefficient kernels: fills Coefs and dcoefs[N*O].  If `dcoefs_in` is non-NULL it is trusted (backward).
@@ -77,24 +82,64 @@ struct WgradArgs {
     int chunk_pix;           // pixels per chunk (multiple of 32)
 };
 
-// Geometry of the transposed-conv stage for up == 2 (mirrors torch_utils/ops/conv2d_resample.py:112-126).
-struct UpGeom {
-    int pxt, pyt;             // conv_transpose2d padding
-    int zh, zw;               // intermediate size
-    int bpx0, bpx1, bpy0, bpy1;   // blur padding
+// ---- "stage 1": the dense contraction of conv2d_resample (torch_utils/ops/conv2d_resample.py:46-141) ----------------
+//   up == 1          : plain conv, z == y
+//   up == 2, k == 1  : 1x1 conv at input resolution, then upfirdn2d(up=2)            (reference lines 101-104)
+//   up == 2, k  > 1  : conv_transpose2d(stride 2) to (2H+1)x(2W+1), then the blur    (reference lines 112-126)
+struct Stage1 {
+    int zh, zw;            // stage-1 output size
+    int sn, sd;            // x position = (z * sn + off) / sd
+    int pyt, pxt;          // transposed-conv padding
+    TapTable taps;         // forward taps
+    int r_up, r_px0, r_py0;      // stage-2 resampler: upfirdn2d(up = r_up, pad0 = r_p*0, gain = up^2)
+    int rb_px0, rb_py0;          // its backward (torch_utils/ops/upfirdn2d.py:251-269)
 };
-inline UpGeom up_geometry(const vfm_modconv_desc& d) {
-    UpGeom g;
-    int up = d.up, kw = d.kw, kh = d.kh, fw = d.fw, fh = d.fh;
-    int px0 = d.padding + (fw + up - 1) / 2, px1 = d.padding + (fw - up) / 2;
-    int py0 = d.padding + (fh + up - 1) / 2, py1 = d.padding + (fh - up) / 2;
-    px0 -= kw - 1; px1 -= kw - up; py0 -= kh - 1; py1 -= kh - up;
-    g.pxt = max(min(-px0, -px1), 0);
-    g.pyt = max(min(-py0, -py1), 0);
-    g.zw = (d.in_w - 1) * up + kw - 2 * g.pxt;
-    g.zh = (d.in_h - 1) * up + kh - 2 * g.pyt;
-    g.bpx0 = px0 + g.pxt; g.bpx1 = px1 + g.pxt; g.bpy0 = py0 + g.pyt; g.bpy1 = py1 + g.pyt;
-    return g;
+
+inline Stage1 make_stage1(const vfm_modconv_desc& d) {
+    Stage1 s;
+    const int kh = d.kh, kw = d.kw;
+    s.taps.ntaps = kh * kw;
+    s.pyt = s.pxt = 0;
+    if (d.up == 1) {
+        s.zh = d.out_h; s.zw = d.out_w; s.sn = 1; s.sd = 1;
+        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
+            int t = ky * kw + kx;
+            s.taps.off_y[t] = ky - d.padding; s.taps.off_x[t] = kx - d.padding;
+            s.taps.widx[t] = d.flip_weight ? t : (kh - 1 - ky) * kw + (kw - 1 - kx);
+        }
+        s.r_up = 1; s.r_px0 = s.r_py0 = s.rb_px0 = s.rb_py0 = 0;
+    } else if (kh == 1) {
+        s.zh = d.in_h; s.zw = d.in_w; s.sn = 1; s.sd = 1;
+        s.taps.off_y[0] = s.taps.off_x[0] = 0; s.taps.widx[0] = 0;
+        s.r_up = 2;
+        s.r_px0 = d.padding + (d.fw + 1) / 2; s.r_py0 = d.padding + (d.fh + 1) / 2;
+        s.rb_px0 = d.fw - s.r_px0 - 1; s.rb_py0 = d.fh - s.r_py0 - 1;
+    } else {
+        const int up = d.up;
+        int px0 = d.padding + (d.fw + up - 1) / 2, px1 = d.padding + (d.fw - up) / 2;
+        int py0 = d.padding + (d.fh + up - 1) / 2, py1 = d.padding + (d.fh - up) / 2;
+        px0 -= kw - 1; px1 -= kw - up; py0 -= kh - 1; py1 -= kh - up;
+        s.pxt = max(min(-px0, -px1), 0);
+        s.pyt = max(min(-py0, -py1), 0);
+        s.zw = (d.in_w - 1) * up + kw - 2 * s.pxt;
+        s.zh = (d.in_h - 1) * up + kh - 2 * s.pyt;
+        s.sn = 1; s.sd = 2;
+        for (int ky = 0; ky < kh; ky++) for (int kx = 0; kx < kw; kx++) {
+            int t = ky * kw + kx;
+            s.taps.off_y[t] = s.pyt - ky; s.taps.off_x[t] = s.pxt - kx;
+            s.taps.widx[t] = d.flip_weight ? (kh - 1 - ky) * kw + (kw - 1 - kx) : t;
+        }
+        s.r_up = 1; s.r_px0 = px0 + s.pxt; s.r_py0 = py0 + s.pyt;
+        s.rb_px0 = d.fw - s.r_px0 - 1; s.rb_py0 = d.fh - s.r_py0 - 1;
+    }
+    return s;
+}
+
+// taps of the data gradient: z position read for a given x position:  forward x = (z + off)/sd  <=>  z = x*sd - off
+inline void dgrad_taps(const Stage1& s, TapTable& t, int& sn, int& sd) {
+    t.ntaps = s.taps.ntaps;
+    sn = s.sd; sd = 1;
+    for (int i = 0; i < t.ntaps; i++) { t.off_y[i] = -s.taps.off_y[i]; t.off_x[i] = -s.taps.off_x[i]; t.widx[i] = s.taps.widx[i]; }
 }
 
 }  // namespace modconv

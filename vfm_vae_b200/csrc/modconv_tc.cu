@@ -1,28 +1,36 @@
 // Modulated conv on the 5th-generation tensor cores: implicit GEMM with tcgen05.mma, accumulators in TMEM, operands
 // staged by TMA.  sm_100a only.
 //
-//   M = 128 output pixels (a tw x th x tn patch of the NHWC activation tensor),  N = BN output channels,
+//   M = 128 output pixels (a tw x th x tn patch of the NHWC activation tensor),  N = 128 output channels,
 //   K = taps x Cin, walked as (tap, 64-channel chunk).
 //
 // * A operand: the activation already multiplied by the per-sample styles and transposed to NHWC fp16 by a pre-pass
 //   (nhwc_prepass_kernel).  One TMA box [64 ch, tw, th, tn] per (tap, chunk); the tap shift is a coordinate offset and
-//   the zero padding halo is TMA out-of-bounds fill -- no im2col buffer, no per-sample weights.
-// * B operand: the shared weights re-laid out as [tap][Cout][Cin] fp16 (K-major), one TMA box [64, BN, 1].
+//   the zero padding halo is TMA out-of-bounds fill -- no im2col buffer, no per-sample [N,O,I,k,k] weights.
+// * B operand: the shared weights re-laid out as [tap][Cout][Cin] fp16 (K-major), one TMA box [64, 128, 1].
 // * both land in shared memory in the canonical 128-byte-swizzled K-major layout that tcgen05 smem descriptors read.
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
-//   (tcgen05.ld 32 lanes x 16 columns, demodulation d[n,o] (* pre-normalisation a[o]) and noise applied in fp32, NCHW
-//   store).  3-stage full/empty mbarrier ring; tcgen05.commit releases smem stages and publishes the accumulator.
-// * the data gradient is the same kernel (activation = d*dy, weights transposed/flipped) with an epilogue that scales by
-//   the styles and reduces sum_p x*dxpre into dstyles with warp shuffles.
+//   (tcgen05.ld 32 lanes x 16 columns, demodulation d[n,o] and noise applied in fp32, NCHW store).  3-stage full/empty
+//   mbarrier ring; tcgen05.commit releases smem stages and publishes the accumulator.
+// * up=2 (transposed conv, stride 2) runs as 4 sub-pixel phases of the same kernel (blockIdx.z): each phase is a
+//   stride-1 conv over the input grid with the taps of matching parity, written to every other output pixel.
+// * the data gradient is the same kernel (activation = d*dz, weights transposed) with an epilogue that scales by the
+//   styles and reduces sum_p x*dxpre into dstyles with warp shuffles; for up=2 its A boxes are element-strided TMA boxes.
+// * fp32 tensors use a 2-term fp16 split of both operands (x = hi + lo/2048): three MMAs per K step
+//   (hi*hi -> acc0; hi*lo + lo*hi -> acc1), recombined in the epilogue as acc0 + acc1/2048.  That carries ~22 mantissa
+//   bits per operand -- enough for the 1e-5 fp32 parity gate, which single-pass TF32 (10 bits) cannot meet -- at 3x the
+//   fp16 cost instead of the 6x of 3xTF32.
 //
-// Numerics: fp16 operands, fp32 accumulation, fp32 epilogue -- the fp16 pre-normalisation of the reference
-// (networks/generator.py:66-68) is only needed for the activation operand here, because nothing is ever accumulated or
-// rescaled in fp16.
+// Numerics: fp16 operands, fp32 accumulation, fp32 epilogue.  The reference's fp16 pre-normalisation
+// (networks/generator.py:66-68) maps to: A = x * s' (styles normalised per sample), B = W * a[o] (weights normalised per
+// output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
 
 namespace vfm {
 namespace modconv {
+
+int run_wgrad(int dtype, WgradArgs a, cudaStream_t stream);   // generic SIMT wgrad (modconv_generic.cu)
 
 namespace {
 
@@ -52,7 +60,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -122,27 +129,40 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int BM = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_BYTES = BN * BK * 2;   // 16 KB
+constexpr float kLoScale = 2048.f;     // the lo term of the fp16 split is stored scaled by 2^11
 
-struct TcArgs {
-    int ntaps, kchunks;
-    int tap_dy[9], tap_dx[9], tap_b[9];   // A coordinate offsets and the tap's slice index in the B tensor map
-    int tw, th, tn;                        // M tile = tw x th pixels of tn consecutive samples (tw*th*tn == 128)
-    int tiles_w, tiles_h;                  // tiles per image
-    int N, H, W, Nout;                     // output geometry: [N, Nout, H, W] NCHW
-    void* out;
-    const float* oscale;                   // [N, Nout]
-    const float* add;                      // noise or NULL
-    int64_t add_sn;
-    const void* aux;                       // dgrad: x, same shape/dtype as out
-    float* aux_sum;                        // dgrad: [N, Nout] += sum_p aux * acc
+struct TcPhase {
+    int ntaps;
+    int dy[9], dx[9], tb[9];   // A coordinate offsets and the tap's slice index in the B tensor map
+    int oy, ox;                // output offset of this phase
+    int Hg, Wg;                // extent of the phase grid
 };
 
-template <int BN, class TOut, bool DGRAD>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs p) {
-    constexpr int B_BYTES = BN * BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+struct TcArgs {
+    TcPhase ph[4];
+    int kchunks;
+    int tw, th, tn;            // M tile = tw x th pixels of tn consecutive samples (tw*th*tn == 128)
+    int tiles_w, tiles_h;      // tile grid (covers the largest phase)
+    int N, Nout;
+    int out_H, out_W, out_s;   // output tensor [N, Nout, out_H, out_W]; output coordinate = g*out_s + o{y,x}
+    int a_s;                   // A coordinate = g*a_s + d{y,x}  (2 for the strided gather of the transposed conv's backward)
+    void* out;
+    const float* oscale;       // [N, Nout]
+    const float* gscale_inv;   // device scalar multiplied into the result, or NULL
+    const float* add;          // noise or NULL
+    int64_t add_sn;
+    const void* aux;           // dgrad: x, same shape/dtype as out
+    float* aux_sum;            // dgrad: [N, Nout] += sum_p aux * acc
+};
+
+template <class TOut, bool DGRAD, bool SPLIT>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, TcArgs p) {
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+    constexpr int TMEM_COLS = SPLIT ? 2 * BN : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
     uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -152,13 +172,15 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     float* s_scale = (float*)(tmem_slot + 2);    // [tn][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const TcPhase& ph = p.ph[blockIdx.z];
 
-    // tile coordinates
+    // tile coordinates (in the phase grid)
     int mt = blockIdx.x;
     const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
     const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
     const int n0 = mt * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
     const int o0 = blockIdx.y * BN;
+    if (h0 >= ph.Hg || w0 >= ph.Wg) return;      // tile outside this phase's grid (uniform for the CTA)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -168,32 +190,40 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN);      // BN fp32 accumulator columns (power of two >= 32)
+        tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < p.tn * BN; i += blockDim.x) {
-        int nl = i / BN, c = i - nl * BN;
-        int n = n0 + nl;
-        s_scale[i] = (n < p.N) ? p.oscale[(size_t)n * p.Nout + o0 + c] : 0.f;
+    {
+        const float gs = p.gscale_inv ? *p.gscale_inv : 1.f;
+        for (int i = threadIdx.x; i < p.tn * BN; i += blockDim.x) {
+            int nl = i / BN, c = i - nl * BN;
+            int n = n0 + nl;
+            s_scale[i] = (n < p.N) ? p.oscale[(size_t)n * p.Nout + o0 + c] * gs : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int iters = p.ntaps * p.kchunks;
+    const int iters = ph.ntaps * p.kchunks;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             for (int it = 0; it < iters; it++) {
                 const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                const uint32_t phs = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], phs ^ 1);
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
                 uint8_t* sa = smem + s * STAGE_BYTES;
-                tma_load_4d(sa, &tmA, &full_bar[s], kc * BK, w0 + p.tap_dx[tap], h0 + p.tap_dy[tap], n0);
-                tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * BK, o0, p.tap_b[tap]);
+                const int cw = w0 * p.a_s + ph.dx[tap], chh = h0 * p.a_s + ph.dy[tap];
+                tma_load_4d(sa, &tmA, &full_bar[s], kc * BK, cw, chh, n0);
+                tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * BK, o0, ph.tb[tap]);
+                if (SPLIT) {
+                    tma_load_4d(sa + A_BYTES + B_BYTES, &tmAlo, &full_bar[s], kc * BK, cw, chh, n0);
+                    tma_load_3d(sa + 2 * A_BYTES + B_BYTES, &tmBlo, &full_bar[s], kc * BK, o0, ph.tb[tap]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -202,16 +232,24 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             for (int it = 0; it < iters; it++) {
                 const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                const uint32_t phs = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], phs);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t adesc = make_kmajor_sw128_desc(sa);
                 const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+                const uint64_t adesc_lo = make_kmajor_sw128_desc(sa + A_BYTES + B_BYTES);
+                const uint64_t bdesc_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int k = 0; k < BK / 16; k++) {
                     // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
-                    umma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    const uint64_t ko = (uint64_t)(2 * k);
+                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+                    umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, first);
+                    if (SPLIT) {
+                        umma_f16(tmem_base + BN, adesc + ko, bdesc_lo + ko, idesc, first);
+                        umma_f16(tmem_base + BN, adesc_lo + ko, bdesc + ko, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);     // frees this smem stage once the MMAs above have read it
             }
@@ -223,15 +261,18 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int r = lg * 32 + lane;                      // accumulator row = pixel index inside the tile
         const int nl = r / (p.tw * p.th);
         const int hl = (r / p.tw) % p.th, wl = r % p.tw;
-        const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
-        const bool valid = (n < p.N) && (h < p.H) && (w < p.W);
-        const size_t HW = (size_t)p.H * p.W;
-        const size_t pix = (size_t)h * p.W + w;
+        const int n = n0 + nl, gh = h0 + hl, gw = w0 + wl;
+        const int oy = gh * p.out_s + ph.oy, ox = gw * p.out_s + ph.ox;
+        const bool valid = (n < p.N) && (gh < ph.Hg) && (gw < ph.Wg) && (oy < p.out_H) && (ox < p.out_W);
+        const size_t HW = (size_t)p.out_H * p.out_W;
+        const size_t pix = (size_t)oy * p.out_W + ox;
         float addv = 0.f;
         if (!DGRAD && p.add && valid) addv = p.add[(size_t)n * p.add_sn + pix];
         TOut* outp = (TOut*)p.out + ((size_t)n * p.Nout + o0) * HW + pix;
         const TOut* auxp = DGRAD ? (const TOut*)p.aux + ((size_t)n * p.Nout + o0) * HW + pix : nullptr;
         const float* sc = s_scale + nl * BN;
+        const bool warp_one_sample = (p.tw * p.th >= 32);
+        const float gsv = (DGRAD && p.gscale_inv) ? *p.gscale_inv : 1.f;    // undoes the global power-of-two scale of A
 
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -239,19 +280,26 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         for (int j = 0; j < BN / 16; j++) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 16), v);
+            if (SPLIT) {
+                float v1[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + j * 16), v1);
+#pragma unroll
+                for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
+            }
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const int col = j * 16 + c;
-                float acc = v[c];
-                if (DGRAD) {
-                    float part = 0.f;
-                    if (valid && p.aux_sum) part = to_acc(auxp[(size_t)col * HW]) * acc;
-                    if (p.aux_sum) {
-                        part = warp_sum(part);     // all 32 lanes of a warp belong to one sample (tw*th >= 32)
+                const float acc = v[c];
+                if (DGRAD && p.aux_sum) {
+                    float part = valid ? to_acc(auxp[(size_t)col * HW]) * (acc * gsv) : 0.f;
+                    if (warp_one_sample) {
+                        part = warp_sum(part);
                         if (lane == 0 && n < p.N) atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + col], part);
+                    } else if (valid) {
+                        atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + col], part);
                     }
                 }
-                float val = acc * sc[col] + addv;
+                const float val = acc * sc[col] + addv;
                 if (valid) outp[(size_t)col * HW] = from_acc<TOut, float>(val);
             }
         }
@@ -260,19 +308,21 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ pre-pass kernels
-// x [N,C,H,W] (TIn) * scale[n,c]  ->  xt [N,H,W,C] fp16.  64 channels x 64 pixels per CTA through shared memory:
-// coalesced reads along pixels, coalesced 16-byte writes along channels.
-template <class TIn>
-__global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, __half* __restrict__ xt,
-                                                           int C, int HW) {
-    __shared__ __half s[64][66];     // [pixel][channel], 33-word pitch: conflict-free transposed stores
+// x [N,C,H,W] (TIn) * scale[n,c] (* *gscale)  ->  xt [N,H,W,C] fp16 (hi) and, for the split path, the residual
+// (v - hi) * 2048 as a second fp16 tensor (lo).  64 channels x 64 pixels per CTA through shared memory: coalesced reads
+// along pixels, coalesced 16-byte writes along channels.
+template <class TIn, bool SPLIT>
+__global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ gscale,
+                                                           __half* __restrict__ xt, __half* __restrict__ xt_lo, int C, int HW) {
+    __shared__ __half s[SPLIT ? 2 : 1][64][66];     // [pixel][channel], 33-word pitch: conflict-free transposed stores
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
+    const float gs = gscale ? *gscale : 1.f;
     {
         const int pl = tid & 63, cg = tid >> 6;      // 4 channel groups x 64 pixels
         const int pidx = p0 + pl;
@@ -281,8 +331,10 @@ __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict
             const int cl = cg + i * 4;
             const int c = c0 + cl;
             float v = 0.f;
-            if (pidx < HW && c < C) v = to_acc(x[((size_t)n * C + c) * HW + pidx]) * scale[(size_t)n * C + c];
-            s[pl][cl] = __float2half_rn(v);
+            if (pidx < HW && c < C) v = to_acc(x[((size_t)n * C + c) * HW + pidx]) * (scale[(size_t)n * C + c] * gs);
+            const __half hi = __float2half_rn(v);
+            s[0][pl][cl] = hi;
+            if (SPLIT) s[1][pl][cl] = __float2half_rn((v - __half2float(hi)) * kLoScale);
         }
     }
     __syncthreads();
@@ -292,20 +344,25 @@ __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict
         for (int i = 0; i < 2; i++) {
             const int pl = pl0 + i * 32;
             const int pidx = p0 + pl;
-            if (pidx >= HW) continue;
-            union { uint4 u; uint32_t w[4]; } pk;
-            const uint32_t* src = (const uint32_t*)&s[pl][cv * 8];
+            if (pidx >= HW || c0 + cv * 8 + 8 > C) continue;
 #pragma unroll
-            for (int k = 0; k < 4; k++) pk.w[k] = src[k];
-            if (c0 + cv * 8 + 8 <= C) *(uint4*)(xt + ((size_t)n * HW + pidx) * C + c0 + cv * 8) = pk.u;
+            for (int part = 0; part < (SPLIT ? 2 : 1); part++) {
+                union { uint4 u; uint32_t w[4]; } pk;
+                const uint32_t* src = (const uint32_t*)&s[part][pl][cv * 8];
+#pragma unroll
+                for (int k = 0; k < 4; k++) pk.w[k] = src[k];
+                __half* dst = (part == 0 ? xt : xt_lo) + ((size_t)n * HW + pidx) * C + c0 + cv * 8;
+                *(uint4*)dst = pk.u;
+            }
         }
     }
 }
 
-// weight [O,I,KK] fp32 -> wt[t][O][I] (transpose == 0) or wt[t][I][O] (transpose == 1) fp16, t = position in the tap list
-__global__ void weight_prep_kernel(const float* __restrict__ w, __half* __restrict__ wt, int O, int I, int KK, int ntaps, const int* __restrict__ widx_dev,
-                                   int transpose, int widx0, int widx1, int widx2, int widx3, int widx4, int widx5, int widx6, int widx7, int widx8) {
-    const int widx[9] = {widx0, widx1, widx2, widx3, widx4, widx5, widx6, widx7, widx8};
+struct WidxList { int v[9]; };
+
+// weight [O,I,KK] fp32 (* a[o])  ->  wt[t][O][I] (transpose == 0) or wt[t][I][O] (transpose == 1) fp16 hi (+ lo)
+__global__ void weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ a, __half* __restrict__ wt, __half* __restrict__ wt_lo,
+                                   int O, int I, int KK, int ntaps, int transpose, WidxList widx) {
     size_t total = (size_t)ntaps * O * I;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int t = (int)(idx / ((size_t)O * I));
@@ -313,8 +370,53 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __half* __restri
         int o, i;
         if (!transpose) { o = (int)(r / I); i = (int)(r - (size_t)o * I); }
         else { i = (int)(r / O); o = (int)(r - (size_t)i * O); }
-        wt[idx] = __float2half_rn(w[((size_t)o * I + i) * KK + widx[t]]);
+        float v = w[((size_t)o * I + i) * KK + widx.v[t]] * a[o];
+        __half hi = __float2half_rn(v);
+        wt[idx] = hi;
+        if (wt_lo) wt_lo[idx] = __float2half_rn((v - __half2float(hi)) * kLoScale);
     }
+}
+
+// per-sample power-of-two normalisation of the activation scale so that |x * scale| stays far from the fp16 limit:
+//   a_scale[n,i] = in_scale[n,i] * c2[n],  o_scale[n,o] = out_scale[n,o] / c2[n],  c2 = 2^-ceil(log2(max_i |in_scale|)) if that max > 1
+__global__ void scale_prep_kernel(const float* __restrict__ in_scale, const float* __restrict__ out_scale, float* a_scale, float* o_scale, int Cin, int Cout) {
+    __shared__ float red[32];
+    __shared__ float s_c2;
+    const int n = blockIdx.x;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) m = fmaxf(m, fabsf(in_scale[(size_t)n * Cin + i]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int k = 0; k < (int)(blockDim.x + 31) / 32; k++) mm = fmaxf(mm, red[k]);
+        s_c2 = (mm > 1.f && isfinite(mm)) ? exp2f(-ceilf(log2f(mm))) : 1.f;
+    }
+    __syncthreads();
+    const float c2 = s_c2, c2i = 1.f / s_c2;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) a_scale[(size_t)n * Cin + i] = in_scale[(size_t)n * Cin + i] * c2;
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) o_scale[(size_t)n * Cout + i] = out_scale[(size_t)n * Cout + i] * c2i;
+}
+
+// amax over |x * scale[n,c]| (bit pattern of a non-negative float is monotone -> atomicMax on uint)
+template <class TIn>
+__global__ void __launch_bounds__(256) amax_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, int C, int HW, size_t total, unsigned int* amax_bits) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t plane = i / HW;
+        m = fmaxf(m, fabsf(to_acc(x[i]) * scale[plane]));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
+}
+// gs[0] = power of two bringing amax into [256, 512); gs[1] = 1 / gs[0]
+__global__ void gscale_kernel(const unsigned int* amax_bits, float* gs) {
+    float m = __uint_as_float(*amax_bits);
+    float k = (m > 0.f && isfinite(m)) ? exp2f(8.f - floorf(log2f(m))) : 1.f;
+    gs[0] = k; gs[1] = 1.f / k;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -334,14 +436,14 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box, const uint32_t* estride) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VFM_ERR_CUDA; }
     cuuint64_t gdim[5], gstride[4];
     cuuint32_t bdim[5], estr[5];
     uint64_t stride = 2;   // fp16
     for (int i = 0; i < rank; i++) {
-        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = estride ? estride[i] : 1;
         stride *= dims[i];
         if (i < rank - 1) gstride[i] = stride;
     }
@@ -351,155 +453,214 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
     return VFM_OK;
 }
 
-bool pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
-    if (W >= 32) { tw = 32; th = 4; tn = 1; }
-    else if (W == 16) { tw = 16; th = 8; tn = 1; }
-    else if (W == 8) { tw = 8; th = 8; tn = 2; }
-    else return false;
-    return (W % tw == 0) && (H % th == 0) && (N % tn == 0);
+// M tile shape with the least padding waste for a Hg x Wg grid (tw*th*tn == 128)
+void pick_tile(int Hg, int Wg, int& tw, int& th, int& tn) {
+    const int cand[][3] = {{32, 4, 1}, {16, 8, 1}, {8, 16, 1}, {8, 8, 2}, {4, 8, 4}, {4, 4, 8}};
+    double best = 1e30;
+    for (auto& c : cand) {
+        double cover = (double)ceil_div(Wg, c[0]) * c[0] * ceil_div(Hg, c[1]) * c[1];
+        double waste = cover / ((double)Wg * Hg) * (c[2] > 1 && Hg * Wg > c[0] * c[1] ? 4.0 : 1.0);   // multi-sample tiles only for tiny images
+        if (waste < best - 1e-9) { best = waste; tw = c[0]; th = c[1]; tn = c[2]; }
+    }
 }
 
-size_t smem_bytes(int BN) { return (size_t)STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256 + (size_t)2 * BN * sizeof(float); }
+size_t smem_bytes(bool split) { return (size_t)STAGES * (split ? 2 : 1) * (A_BYTES + B_BYTES) + 1024 + 256 + (size_t)8 * BN * sizeof(float); }
 
-template <int BN, class TOut, bool DGRAD>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int m_tiles, int n_tiles, double flops, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<BN, TOut, DGRAD>;
-    size_t smem = smem_bytes(BN);
+template <class TOut, bool DGRAD, bool SPLIT>
+int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
+    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT>;
+    size_t smem = smem_bytes(SPLIT);
     VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KernelTimer timer(DGRAD ? "modconv_tc_dgrad" : "modconv_tc_fwd", stream, flops, 0.0);
-    kern<<<dim3(m_tiles, n_tiles), 192, smem, stream>>>(tmA, tmB, a);
+    KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0);
+    kern<<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     return launch_status("modconv conv_tc_kernel");
 }
 
-// One implicit-GEMM conv over an NHWC fp16 activation `act` [N,H,W,Cin] with weights `wt` [ntaps][Nout][Cin]
-int run_tc_conv(int out_dtype, bool dgrad, __half* act, __half* wt, const TapTable& taps, int N, int H, int W, int Cin, int Nout,
-                void* out, const float* oscale, const float* add, int64_t add_sn, const void* aux, float* aux_sum, cudaStream_t stream) {
-    TcArgs a;
-    a.ntaps = taps.ntaps; a.kchunks = Cin / BK;
-    for (int t = 0; t < taps.ntaps; t++) { a.tap_dy[t] = taps.off_y[t]; a.tap_dx[t] = taps.off_x[t]; a.tap_b[t] = t; }
-    if (!pick_tile(N, H, W, a.tw, a.th, a.tn)) { set_error("tcgen05 path: unsupported image size %dx%d", H, W); return VFM_ERR_NO_KERNEL; }
-    a.tiles_w = W / a.tw; a.tiles_h = H / a.th;
-    a.N = N; a.H = H; a.W = W; a.Nout = Nout;
-    a.out = out; a.oscale = oscale; a.add = add; a.add_sn = add_sn; a.aux = aux; a.aux_sum = aux_sum;
-    const int BN = 128;
-    CUtensorMap tmA, tmB;
-    uint64_t adims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint32_t abox[4] = {(uint32_t)BK, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
-    int st = encode_map(&tmA, act, 4, adims, abox); if (st) return st;
-    uint64_t bdims[3] = {(uint64_t)Cin, (uint64_t)Nout, (uint64_t)taps.ntaps};
+struct TcOperands {
+    __half* act; __half* act_lo;     // NHWC [N, Ha, Wa, Cin]
+    __half* wt; __half* wt_lo;       // [ntaps][Nout][Cin]
+    int N, Ha, Wa, Cin, Nout, ntaps;
+};
+
+// One implicit-GEMM conv.  `args` must have ph[], out*, a_s, scales, add/aux already filled in; this sets the tiling.
+int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream) {
+    int Hg = 0, Wg = 0;
+    double taps_px = 0;
+    for (int i = 0; i < nphases; i++) { Hg = max(Hg, a.ph[i].Hg); Wg = max(Wg, a.ph[i].Wg); taps_px += (double)a.ph[i].ntaps * a.ph[i].Hg * a.ph[i].Wg; }
+    pick_tile(Hg, Wg, a.tw, a.th, a.tn);
+    a.tiles_w = ceil_div(Wg, a.tw); a.tiles_h = ceil_div(Hg, a.th);
+    a.kchunks = op.Cin / BK;
+    a.N = op.N; a.Nout = op.Nout;
+    CUtensorMap maps[4];
+    uint64_t adims[4] = {(uint64_t)op.Cin, (uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.N};
+    uint32_t abox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)(a.th * a.a_s), (uint32_t)a.tn};
+    uint32_t astr[4] = {1u, (uint32_t)a.a_s, (uint32_t)a.a_s, 1u};
+    uint64_t bdims[3] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps};
     uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)BN, 1u};
-    st = encode_map(&tmB, wt, 3, bdims, bbox); if (st) return st;
-    const int m_tiles = a.tiles_w * a.tiles_h * (N / a.tn), n_tiles = Nout / BN;
-    const double flops = 2.0 * N * H * W * (double)Nout * Cin * taps.ntaps;
-    if (out_dtype == VFM_F16) {
-        return dgrad ? launch_tc<128, __half, true>(tmA, tmB, a, m_tiles, n_tiles, flops, stream)
-                     : launch_tc<128, __half, false>(tmA, tmB, a, m_tiles, n_tiles, flops, stream);
-    }
-    return dgrad ? launch_tc<128, float, true>(tmA, tmB, a, m_tiles, n_tiles, flops, stream)
-                 : launch_tc<128, float, false>(tmA, tmB, a, m_tiles, n_tiles, flops, stream);
+    int st = encode_map(&maps[0], op.act, 4, adims, abox, astr); if (st) return st;
+    st = encode_map(&maps[1], op.wt, 3, bdims, bbox, nullptr); if (st) return st;
+    st = encode_map(&maps[2], f32 ? op.act_lo : op.act, 4, adims, abox, astr); if (st) return st;
+    st = encode_map(&maps[3], f32 ? op.wt_lo : op.wt, 3, bdims, bbox, nullptr); if (st) return st;
+    dim3 grid(a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn), op.Nout / BN, nphases);
+    const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
+    if (!f32) return dgrad ? launch_tc<__half, true, false>(maps, a, grid, flops, stream) : launch_tc<__half, false, false>(maps, a, grid, flops, stream);
+    return dgrad ? launch_tc<float, true, true>(maps, a, grid, flops, stream) : launch_tc<float, false, true>(maps, a, grid, flops, stream);
 }
 
-template <class TIn>
-int run_prepass(const void* x, const float* scale, __half* xt, int N, int C, int HW, cudaStream_t stream) {
+int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream) {
     dim3 grid(ceil_div(HW, 64), ceil_div(C, 64), N);
-    KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * (sizeof(TIn) + 2));
-    nhwc_prepass_kernel<TIn><<<grid, 256, 0, stream>>>((const TIn*)x, scale, xt, C, HW);
+    if (grid.z > 65535 || grid.y > 65535) { set_error("tcgen05 path: batch too large"); return VFM_ERR_INVALID; }
+    KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * ((dtype == VFM_F16 ? 2 : 4) + (split ? 4 : 2)));
+    if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, gscale, xt, xt_lo, C, HW);
+    else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
+    else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
     return launch_status("modconv nhwc_prepass_kernel");
 }
 
-int run_weight_prep(const float* w, __half* wt, int O, int I, int KK, const TapTable& taps, int transpose, cudaStream_t stream) {
-    int wi[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < taps.ntaps; t++) wi[t] = taps.widx[t];
+int run_weight_prep(const float* w, const float* a, __half* wt, __half* wt_lo, int O, int I, int KK, const TapTable& taps, int transpose, cudaStream_t stream) {
+    WidxList wl;
+    for (int t = 0; t < 9; t++) wl.v[t] = t < taps.ntaps ? taps.widx[t] : 0;
     size_t total = (size_t)taps.ntaps * O * I;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    weight_prep_kernel<<<blocks, 256, 0, stream>>>(w, wt, O, I, KK, taps.ntaps, nullptr, transpose, wi[0], wi[1], wi[2], wi[3], wi[4], wi[5], wi[6], wi[7], wi[8]);
+    weight_prep_kernel<<<blocks, 256, 0, stream>>>(w, a, wt, wt_lo, O, I, KK, taps.ntaps, transpose, wl);
     return launch_status("modconv weight_prep_kernel");
 }
 
-void fwd_taps(const vfm_modconv_desc& d, TapTable& t) {
-    t.ntaps = d.kh * d.kw;
-    for (int ky = 0; ky < d.kh; ky++)
-        for (int kx = 0; kx < d.kw; kx++) {
-            int i = ky * d.kw + kx;
-            t.off_y[i] = ky - d.padding; t.off_x[i] = kx - d.padding;
-            t.widx[i] = d.flip_weight ? i : (d.kh - 1 - ky) * d.kw + (d.kw - 1 - kx);
-        }
+bool is_f32(const vfm_modconv_desc& d) { return d.dtype == VFM_F32; }
+
+struct TcWorkspace {
+    __half *act, *act_lo, *wt, *wt_lo;
+    float *a_scale, *o_scale, *gs;
+    unsigned int* amax;
+};
+
+void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direction, TcWorkspace& w) {
+    const bool f32 = is_f32(d);
+    const size_t act_el = direction == 0 ? (size_t)d.batch * d.in_h * d.in_w * d.in_channels : (size_t)d.batch * s.zh * s.zw * d.out_channels;
+    const size_t wel = (size_t)d.kh * d.kw * d.out_channels * d.in_channels;
+    w.act = cv.take<__half>(act_el);
+    w.act_lo = f32 ? cv.take<__half>(act_el) : nullptr;
+    w.wt = cv.take<__half>(wel);
+    w.wt_lo = f32 ? cv.take<__half>(wel) : nullptr;
+    const size_t nin = (size_t)d.batch * (direction == 0 ? d.in_channels : d.out_channels);
+    const size_t nout = (size_t)d.batch * (direction == 0 ? d.out_channels : d.in_channels);
+    w.a_scale = cv.take<float>(nin);
+    w.o_scale = cv.take<float>(nout);
+    w.gs = cv.take<float>(4);
+    w.amax = (unsigned int*)(w.gs ? w.gs + 2 : nullptr);
 }
 
 }  // namespace
 
 bool tc_supported(const vfm_modconv_desc& d) {
-    if (d.dtype != VFM_F16) return false;
-    if (d.up != 1 || d.kh != d.kw || (d.kh != 3 && d.kh != 1) || d.padding != d.kh / 2) return false;
-    if (d.in_channels % 128 != 0 || d.out_channels % 128 != 0) return false;   // both are an N dimension (fwd / dgrad) and a K dimension
-    int tw, th, tn;
-    if (!pick_tile(d.batch, d.in_h, d.in_w, tw, th, tn)) return false;
+    if (d.dtype != VFM_F16 && d.dtype != VFM_F32) return false;
+    if (d.kh != d.kw || d.padding != d.kh / 2) return false;
+    if (!(d.kh == 3 || (d.kh == 1 && d.up == 1))) return false;
+    if (d.in_channels % 128 != 0 || d.out_channels % 128 != 0) return false;   // each is an N dimension (fwd / dgrad) and a K dimension
+    if (d.batch > 65535) return false;
     return get_encode_fn() != nullptr;
 }
 
 size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction) {
     Carver cv(nullptr, ~(size_t)0);
-    const size_t npix = (size_t)d.batch * d.in_h * d.in_w;
-    const size_t wel = (size_t)d.kh * d.kw * d.out_channels * d.in_channels;
-    if (direction == 0) {
-        cv.take<__half>(npix * d.in_channels);
-        cv.take<__half>(wel);
-    } else {
-        cv.take<__half>(npix * d.out_channels);   // d*dy, NHWC
-        cv.take<__half>(wel);                     // transposed weights
-    }
+    Stage1 s = make_stage1(d);
+    TcWorkspace w;
+    carve_tc(cv, d, s, direction, w);
     return cv.off + 512;
 }
 
-int tc_forward(const vfm_modconv_fwd_params& p, const Coefs& k, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const vfm_modconv_desc& d = p.d;
-    Carver cv(ws, ws_bytes);
-    const size_t npix = (size_t)d.batch * d.in_h * d.in_w;
-    __half* xt = cv.take<__half>(npix * d.in_channels);
-    __half* wt = cv.take<__half>((size_t)d.kh * d.kw * d.out_channels * d.in_channels);
-    if (!cv.ok()) { set_error("modulated_conv2d: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
-    TapTable taps; fwd_taps(d, taps);
-    int st = run_prepass<__half>(p.x, k.iscale, xt, d.batch, d.in_channels, d.in_h * d.in_w, stream); if (st) return st;
-    st = run_weight_prep(p.weight, wt, d.out_channels, d.in_channels, d.kh * d.kw, taps, 0, stream); if (st) return st;
-    const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
-    return run_tc_conv(d.dtype, false, xt, wt, taps, d.batch, d.in_h, d.in_w, d.in_channels, d.out_channels, p.y, k.oscale, p.noise, noise_sn,
-                       nullptr, nullptr, stream);
-}
-
-int run_wgrad(int dtype, WgradArgs a, cudaStream_t stream);   // generic SIMT wgrad (modconv_generic.cu) until the tcgen05 wgrad lands
-
-int tc_backward(const vfm_modconv_bwd_params& p, const Coefs& k, float* g, float* dsum, void* ws, size_t ws_bytes, cudaStream_t stream) {
-    const vfm_modconv_desc& d = p.d;
+int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z,
+                      const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
-    const size_t npix = (size_t)N * d.in_h * d.in_w;
-    __half* dyt = cv.take<__half>(npix * O);
-    __half* wtT = cv.take<__half>((size_t)KK * O * I);
+    TcWorkspace w;
+    carve_tc(cv, d, s, 0, w);
+    if (!cv.ok()) { set_error("modulated_conv2d: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
+    // A = x * s' * c2, B = W * a, epilogue scale = d / c2
+    scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O);
+    int st = launch_status("modconv scale_prep_kernel"); if (st) return st;
+    st = run_prepass(d.dtype, f32, x, w.a_scale, nullptr, w.act, w.act_lo, N, I, d.in_h * d.in_w, stream); if (st) return st;
+    st = run_weight_prep(weight, k.a, w.wt, w.wt_lo, O, I, KK, s.taps, 0, stream); if (st) return st;
+
+    TcArgs a;
+    int nph = 0;
+    if (s.sd == 1) {
+        TcPhase& ph = a.ph[0];
+        ph.ntaps = s.taps.ntaps;
+        for (int t = 0; t < ph.ntaps; t++) { ph.dy[t] = s.taps.off_y[t]; ph.dx[t] = s.taps.off_x[t]; ph.tb[t] = t; }
+        ph.oy = ph.ox = 0; ph.Hg = s.zh; ph.Wg = s.zw;
+        nph = 1; a.out_s = 1;
+    } else {
+        for (int pa = 0; pa < 2; pa++)
+            for (int pb = 0; pb < 2; pb++) {
+                TcPhase& ph = a.ph[nph];
+                ph.ntaps = 0;
+                for (int t = 0; t < s.taps.ntaps; t++) {
+                    int ny = pa + s.taps.off_y[t], nx = pb + s.taps.off_x[t];
+                    if ((ny & 1) || (nx & 1)) continue;
+                    ph.dy[ph.ntaps] = ny / 2; ph.dx[ph.ntaps] = nx / 2; ph.tb[ph.ntaps] = t;     // exact: even numerators
+                    ph.ntaps++;
+                }
+                ph.oy = pa; ph.ox = pb; ph.Hg = (s.zh - pa + 1) / 2; ph.Wg = (s.zw - pb + 1) / 2;
+                if (ph.ntaps > 0 && ph.Hg > 0 && ph.Wg > 0) nph++;
+            }
+        a.out_s = 2;
+    }
+    a.out_H = s.zh; a.out_W = s.zw; a.a_s = 1;
+    a.out = z; a.oscale = w.o_scale; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr;
+    TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, d.in_h, d.in_w, I, O, s.taps.ntaps};
+    return run_tc_conv(f32, false, op, a, nph, stream);
+}
+
+int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    const bool f32 = is_f32(d);
+    const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
+    Carver cv(ws, ws_bytes);
+    TcWorkspace w;
+    carve_tc(cv, d, s, 1, w);
     if (!cv.ok()) { set_error("modulated_conv2d backward: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
-    TapTable ftaps; fwd_taps(d, ftaps);
     int st;
-    if (p.dx) {
-        // dxpre[n,i,p] = sum_{o,t} W[o,i,widx(t)] * (d*a*dy)[n,o,p - off(t)]
-        TapTable dt = ftaps;
-        for (int t = 0; t < dt.ntaps; t++) { dt.off_y[t] = -ftaps.off_y[t]; dt.off_x[t] = -ftaps.off_x[t]; }
-        st = run_prepass<__half>(p.dy, k.oscale, dyt, N, O, d.out_h * d.out_w, stream); if (st) return st;
-        st = run_weight_prep(p.weight, wtT, O, I, KK, dt, 1, stream); if (st) return st;
-        if (p.dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
-        st = run_tc_conv(d.dtype, true, dyt, wtT, dt, N, d.in_h, d.in_w, O, I, p.dx, k.iscale, nullptr, 0, p.dstyles ? p.x : nullptr,
-                         p.dstyles ? dsum : nullptr, stream);
-        if (st) return st;
+    if (dx) {
+        // dxpre[n,i,p] = sum_{o,t} (a*W)[o,i,widx(t)] * (d*dz)[n,o,z(p,t)];  dx = s' * dxpre;  dsum = sum_p x * dxpre
+        const size_t zel = (size_t)N * O * s.zh * s.zw;
+        const float* gs = nullptr;
+        if (f32) {
+            // fp32 gradients can be arbitrarily small: bring the tensor into the fp16 sweet spot with one power-of-two scale
+            VFM_CUDA_OK(cudaMemsetAsync(w.amax, 0, sizeof(unsigned int), stream));
+            size_t want_blocks = (zel + 255) / 256;
+            int blocks = (int)(want_blocks < (size_t)kNumSMs * 8 ? want_blocks : (size_t)kNumSMs * 8);
+            amax_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dz, k.d, O, s.zh * s.zw, zel, w.amax);
+            st = launch_status("modconv amax_kernel"); if (st) return st;
+            gscale_kernel<<<1, 1, 0, stream>>>(w.amax, w.gs);
+            st = launch_status("modconv gscale_kernel"); if (st) return st;
+            gs = w.gs;
+        }
+        st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream); if (st) return st;
+        TapTable dt; int sn, sd;
+        dgrad_taps(s, dt, sn, sd);
+        st = run_weight_prep(weight, k.a, w.wt, w.wt_lo, O, I, KK, dt, 1, stream); if (st) return st;
+        TcArgs a;
+        TcPhase& ph = a.ph[0];
+        ph.ntaps = dt.ntaps;
+        for (int t = 0; t < dt.ntaps; t++) { ph.dy[t] = dt.off_y[t]; ph.dx[t] = dt.off_x[t]; ph.tb[t] = t; }
+        ph.oy = ph.ox = 0; ph.Hg = d.in_h; ph.Wg = d.in_w;
+        a.out_s = 1; a.out_H = d.in_h; a.out_W = d.in_w; a.a_s = sn;
+        a.out = dx; a.oscale = k.iscale; a.gscale_inv = gs ? gs + 1 : nullptr; a.add = nullptr; a.add_sn = 0;
+        a.aux = dsum ? x : nullptr; a.aux_sum = dsum;
+        TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, s.zh, s.zw, O, I, dt.ntaps};
+        st = run_tc_conv(f32, true, op, a, 1, stream); if (st) return st;
     }
-    if (p.dweight) {
-        VFM_CUDA_OK(cudaMemsetAsync(p.dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
-        WgradArgs w;
-        w.dy = p.dy; w.x = p.x; w.oscale = k.oscale; w.iscale = k.iscale; w.dw = p.dweight;
-        w.s_co = (int64_t)I * KK; w.s_ci = KK;
-        w.N = N; w.Co = O; w.Ci = I; w.Hd = d.out_h; w.Wd = d.out_w; w.Hx = d.in_h; w.Wx = d.in_w;
-        w.sn = 1; w.sd = 1; w.taps = ftaps; w.chunks = 0; w.chunk_pix = 0;
-        st = run_wgrad(d.dtype, w, stream); if (st) return st;
+    if (dweight) {
+        WgradArgs wa;
+        wa.dy = dz; wa.x = x; wa.oscale = k.oscale; wa.iscale = k.iscale; wa.dw = dweight;
+        wa.s_co = (int64_t)I * KK; wa.s_ci = KK;
+        wa.N = N; wa.Co = O; wa.Ci = I; wa.Hd = s.zh; wa.Wd = s.zw; wa.Hx = d.in_h; wa.Wx = d.in_w;
+        wa.sn = s.sn; wa.sd = s.sd; wa.taps = s.taps; wa.chunks = 0; wa.chunk_pix = 0;
+        st = run_wgrad(d.dtype, wa, stream); if (st) return st;
     }
-    (void)g;
     return VFM_OK;
 }
 

@@ -312,6 +312,181 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[o,i,t] = sum_{n, x-pixel q} (d*dz)[n, z(q,t), o] * (x*s')[n, q, i]      z(q,t) = q*sd - off_t
+//
+// GEMM with M = 128 output channels, N = 128 input channels, K = pixels.  Both operands come straight from the NHWC
+// tensors the data-gradient already uses: a TMA box [64 ch, tw, th, tn] is 64 pixel rows of 128 bytes, i.e. an
+// MN-major tile (channels contiguous, K = pixel rows) in the 128-byte-swizzled layout; two boxes side by side make the
+// 128-wide M (resp. N) extent.  The tap shift (and the stride 2 of the transposed conv) is the coordinate / element
+// stride of the dz box, zero padding is TMA out-of-bounds fill.  Split-K over pixel tiles, fp32 red.add into dweight.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;      // leading byte offset: next 64-channel block
+    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next group of 8 K rows
+    d |= (uint64_t)1 << 46;                                // version
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_mnmajor(int M, int N) {
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int WK = 64;                      // pixels per K block
+constexpr int WBOX_BYTES = WK * 128;        // one [64 px][64 ch] box = 8 KB
+constexpr int WOP_BYTES = 2 * WBOX_BYTES;   // 128 channels
+
+struct WgTcArgs {
+    int tw, th, tn;              // pixel tile (tw*th*tn == 64) in the x grid
+    int tiles_w, tiles_h, tiles_n;
+    int ksplit, ntaps;
+    int tap_ay[9], tap_ax[9];    // dz coordinate = q*sd + tap_a
+    int tap_widx[9];
+    int sd;
+    int O, I, KK;
+    float* dw;                   // [O][I][KK] fp32, accumulated with atomics
+    const float* rowscale;       // a[o]
+    const float* gscale;         // device scalar multiplied into the result, or NULL
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                       const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, WgTcArgs p) {
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * 2 * WOP_BYTES;
+    constexpr int TMEM_COLS = SPLIT ? 2 * BN : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
+    const int tap = blockIdx.z / p.ksplit, ks = blockIdx.z - tap * p.ksplit;
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    const int t_begin = (int)((long long)total_tiles * ks / p.ksplit), t_end = (int)((long long)total_tiles * (ks + 1) / p.ksplit);
+    const int iters = t_end - t_begin;
+    if (iters <= 0) return;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; it++) {
+                const int s = it % STAGES;
+                const uint32_t phs = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], phs ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                int t = t_begin + it;
+                const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+                const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+                const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
+                const int aw = w0 * p.sd + p.tap_ax[tap], ah = h0 * p.sd + p.tap_ay[tap];
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                tma_load_4d(sa, &tmA, &full_bar[s], o0, aw, ah, n0);
+                tma_load_4d(sa + WBOX_BYTES, &tmA, &full_bar[s], o0 + 64, aw, ah, n0);
+                tma_load_4d(sa + WOP_BYTES, &tmB, &full_bar[s], i0, w0, h0, n0);
+                tma_load_4d(sa + WOP_BYTES + WBOX_BYTES, &tmB, &full_bar[s], i0 + 64, w0, h0, n0);
+                if (SPLIT) {
+                    uint8_t* sl = sa + 2 * WOP_BYTES;
+                    tma_load_4d(sl, &tmAlo, &full_bar[s], o0, aw, ah, n0);
+                    tma_load_4d(sl + WBOX_BYTES, &tmAlo, &full_bar[s], o0 + 64, aw, ah, n0);
+                    tma_load_4d(sl + WOP_BYTES, &tmBlo, &full_bar[s], i0, w0, h0, n0);
+                    tma_load_4d(sl + WOP_BYTES + WBOX_BYTES, &tmBlo, &full_bar[s], i0 + 64, w0, h0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_mnmajor(128, 128);
+            for (int it = 0; it < iters; it++) {
+                const int s = it % STAGES;
+                const uint32_t phs = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], phs);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t adesc = make_mnmajor_sw128_desc(sa, WBOX_BYTES);
+                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + WOP_BYTES, WBOX_BYTES);
+                const uint64_t adesc_lo = make_mnmajor_sw128_desc(sa + 2 * WOP_BYTES, WBOX_BYTES);
+                const uint64_t bdesc_lo = make_mnmajor_sw128_desc(sa + 3 * WOP_BYTES, WBOX_BYTES);
+#pragma unroll
+                for (int k = 0; k < WK / 16; k++) {
+                    const uint64_t ko = (uint64_t)((k * 16 * 128) >> 4);     // 16 pixel rows of 128 bytes
+                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+                    umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, first);
+                    if (SPLIT) {
+                        umma_f16(tmem_base + BN, adesc + ko, bdesc_lo + ko, idesc, first);
+                        umma_f16(tmem_base + BN, adesc_lo + ko, bdesc + ko, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int lg = warp & 3;
+        const int o = o0 + lg * 32 + lane;
+        const float rs = p.rowscale[o] * (p.gscale ? *p.gscale : 1.f);
+        float* dst = p.dw + ((size_t)o * p.I + i0) * p.KK + p.tap_widx[tap];
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < BN / 16; j++) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 16), v);
+            if (SPLIT) {
+                float v1[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + j * 16), v1);
+#pragma unroll
+                for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) atomicAdd(dst + (size_t)(j * 16 + c) * p.KK, v[c] * rs);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// gs[2] = c2g (power of two keeping |x * s'| in fp16 range for every sample), gs[3] = 1 / (gk * c2g)
+__global__ void wgrad_scalars_kernel(const float* __restrict__ iscale, int n_el, float* gs, int has_gk) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) m = fmaxf(m, fabsf(iscale[i]));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mm = 0.f;
+        for (int k = 0; k < (int)(blockDim.x + 31) / 32; k++) mm = fmaxf(mm, red[k]);
+        float c2g = (mm > 1.f && isfinite(mm)) ? exp2f(-ceilf(log2f(mm))) : 1.f;
+        float gk = has_gk ? gs[0] : 1.f;
+        gs[2] = c2g;
+        gs[3] = 1.f / (gk * c2g);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pre-pass kernels
 // x [N,C,H,W] (TIn) * scale[n,c] (* *gscale)  ->  xt [N,H,W,C] fp16 (hi) and, for the split path, the residual
 // (v - hi) * 2048 as a second fp16 tensor (lo).  64 channels x 64 pixels per CTA through shared memory: coalesced reads
@@ -530,25 +705,82 @@ int run_weight_prep(const float* w, const float* a, __half* wt, __half* wt_lo, i
 bool is_f32(const vfm_modconv_desc& d) { return d.dtype == VFM_F32; }
 
 struct TcWorkspace {
-    __half *act, *act_lo, *wt, *wt_lo;
-    float *a_scale, *o_scale, *gs;
+    __half *act, *act_lo, *wt, *wt_lo;       // NHWC activation operand (x in forward, d*dz in backward), re-laid-out weights
+    __half *xt, *xt_lo;                      // backward only: x*s' NHWC for the weight gradient
+    float *a_scale, *o_scale, *gs;           // gs: [0] gk, [1] 1/gk, [2] c2g, [3] 1/(gk*c2g)
     unsigned int* amax;
 };
 
 void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direction, TcWorkspace& w) {
     const bool f32 = is_f32(d);
-    const size_t act_el = direction == 0 ? (size_t)d.batch * d.in_h * d.in_w * d.in_channels : (size_t)d.batch * s.zh * s.zw * d.out_channels;
+    const size_t x_el = (size_t)d.batch * d.in_h * d.in_w * d.in_channels;
+    const size_t act_el = direction == 0 ? x_el : (size_t)d.batch * s.zh * s.zw * d.out_channels;
     const size_t wel = (size_t)d.kh * d.kw * d.out_channels * d.in_channels;
     w.act = cv.take<__half>(act_el);
     w.act_lo = f32 ? cv.take<__half>(act_el) : nullptr;
     w.wt = cv.take<__half>(wel);
     w.wt_lo = f32 ? cv.take<__half>(wel) : nullptr;
+    w.xt = w.xt_lo = nullptr;
+    if (direction == 1) {
+        w.xt = cv.take<__half>(x_el);
+        w.xt_lo = f32 ? cv.take<__half>(x_el) : nullptr;
+    }
     const size_t nin = (size_t)d.batch * (direction == 0 ? d.in_channels : d.out_channels);
     const size_t nout = (size_t)d.batch * (direction == 0 ? d.out_channels : d.in_channels);
     w.a_scale = cv.take<float>(nin);
     w.o_scale = cv.take<float>(nout);
     w.gs = cv.take<float>(4);
-    w.amax = (unsigned int*)(w.gs ? w.gs + 2 : nullptr);
+    w.amax = cv.take<unsigned int>(4);
+}
+
+// 64-pixel K tile with the least padding waste for an H x W grid
+void pick_wtile(int H, int W, int& tw, int& th, int& tn) {
+    const int cand[][3] = {{16, 4, 1}, {8, 8, 1}, {32, 2, 1}, {4, 16, 1}, {4, 4, 4}, {8, 4, 2}, {2, 2, 16}};
+    double best = 1e30;
+    for (auto& c : cand) {
+        double cover = (double)ceil_div(W, c[0]) * c[0] * ceil_div(H, c[1]) * c[1];
+        double waste = cover / ((double)W * H) * (c[2] > 1 && H * W > c[0] * c[1] ? 4.0 : 1.0);
+        if (waste < best - 1e-9) { best = waste; tw = c[0]; th = c[1]; tn = c[2]; }
+    }
+}
+
+// dweight += a[o] * gscale * sum_{n,q} dzt[n, q*sd - off_t, o] * xt[n, q, i]
+int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcWorkspace& w, const float* rowscale, const float* gscale,
+                 float* dweight, cudaStream_t stream) {
+    const int N = d.batch, I = d.in_channels, O = d.out_channels;
+    WgTcArgs a;
+    pick_wtile(d.in_h, d.in_w, a.tw, a.th, a.tn);
+    a.tiles_w = ceil_div(d.in_w, a.tw); a.tiles_h = ceil_div(d.in_h, a.th); a.tiles_n = ceil_div(N, a.tn);
+    a.ntaps = s.taps.ntaps; a.sd = s.sd;
+    for (int t = 0; t < a.ntaps; t++) { a.tap_ay[t] = -s.taps.off_y[t]; a.tap_ax[t] = -s.taps.off_x[t]; a.tap_widx[t] = s.taps.widx[t]; }
+    a.O = O; a.I = I; a.KK = d.kh * d.kw;
+    a.dw = dweight; a.rowscale = rowscale; a.gscale = gscale;
+    const int tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+    const int base = (O / 128) * (I / 128) * a.ntaps;
+    a.ksplit = max(1, min(tiles, ceil_div(2 * kNumSMs, base)));
+    CUtensorMap maps[4];
+    uint64_t adims[4] = {(uint64_t)O, (uint64_t)s.zw, (uint64_t)s.zh, (uint64_t)N};
+    uint32_t abox[4] = {64u, (uint32_t)(a.tw * s.sd), (uint32_t)(a.th * s.sd), (uint32_t)a.tn};
+    uint32_t astr[4] = {1u, (uint32_t)s.sd, (uint32_t)s.sd, 1u};
+    uint64_t bdims[4] = {(uint64_t)I, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)N};
+    uint32_t bbox[4] = {64u, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
+    int st = encode_map(&maps[0], w.act, 4, adims, abox, astr); if (st) return st;
+    st = encode_map(&maps[1], w.xt, 4, bdims, bbox, nullptr); if (st) return st;
+    st = encode_map(&maps[2], f32 ? w.act_lo : w.act, 4, adims, abox, astr); if (st) return st;
+    st = encode_map(&maps[3], f32 ? w.xt_lo : w.xt, 4, bdims, bbox, nullptr); if (st) return st;
+    dim3 grid(O / 128, I / 128, a.ntaps * a.ksplit);
+    if (grid.z > 65535) { set_error("tcgen05 wgrad: grid too large"); return VFM_ERR_INVALID; }
+    const size_t smem = (size_t)STAGES * (f32 ? 2 : 1) * 2 * WOP_BYTES + 1024 + 256;
+    const double flops = 2.0 * N * d.in_h * d.in_w * (double)O * I * a.ntaps;
+    KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0);
+    if (f32) {
+        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_tc_kernel<true><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    } else {
+        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_tc_kernel<false><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    }
+    return launch_status("modconv wgrad_tc_kernel");
 }
 
 }  // namespace
@@ -623,22 +855,23 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
     carve_tc(cv, d, s, 1, w);
     if (!cv.ok()) { set_error("modulated_conv2d backward: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
     int st;
+    // A operand shared by the data and the weight gradient: (d * dz) NHWC (fp32: scaled by one power of two, gk)
+    const size_t zel = (size_t)N * O * s.zh * s.zw;
+    const float* gs = nullptr;
+    if (f32) {
+        // fp32 gradients can be arbitrarily small: bring the tensor into the fp16 sweet spot with one power-of-two scale
+        VFM_CUDA_OK(cudaMemsetAsync(w.amax, 0, sizeof(unsigned int), stream));
+        size_t want_blocks = (zel + 255) / 256;
+        int blocks = (int)(want_blocks < (size_t)kNumSMs * 8 ? want_blocks : (size_t)kNumSMs * 8);
+        amax_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dz, k.d, O, s.zh * s.zw, zel, w.amax);
+        st = launch_status("modconv amax_kernel"); if (st) return st;
+        gscale_kernel<<<1, 1, 0, stream>>>(w.amax, w.gs);
+        st = launch_status("modconv gscale_kernel"); if (st) return st;
+        gs = w.gs;
+    }
+    st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream); if (st) return st;
     if (dx) {
         // dxpre[n,i,p] = sum_{o,t} (a*W)[o,i,widx(t)] * (d*dz)[n,o,z(p,t)];  dx = s' * dxpre;  dsum = sum_p x * dxpre
-        const size_t zel = (size_t)N * O * s.zh * s.zw;
-        const float* gs = nullptr;
-        if (f32) {
-            // fp32 gradients can be arbitrarily small: bring the tensor into the fp16 sweet spot with one power-of-two scale
-            VFM_CUDA_OK(cudaMemsetAsync(w.amax, 0, sizeof(unsigned int), stream));
-            size_t want_blocks = (zel + 255) / 256;
-            int blocks = (int)(want_blocks < (size_t)kNumSMs * 8 ? want_blocks : (size_t)kNumSMs * 8);
-            amax_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dz, k.d, O, s.zh * s.zw, zel, w.amax);
-            st = launch_status("modconv amax_kernel"); if (st) return st;
-            gscale_kernel<<<1, 1, 0, stream>>>(w.amax, w.gs);
-            st = launch_status("modconv gscale_kernel"); if (st) return st;
-            gs = w.gs;
-        }
-        st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream); if (st) return st;
         TapTable dt; int sn, sd;
         dgrad_taps(s, dt, sn, sd);
         st = run_weight_prep(weight, k.a, w.wt, w.wt_lo, O, I, KK, dt, 1, stream); if (st) return st;
@@ -654,12 +887,11 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         st = run_tc_conv(f32, true, op, a, 1, stream); if (st) return st;
     }
     if (dweight) {
-        WgradArgs wa;
-        wa.dy = dz; wa.x = x; wa.oscale = k.oscale; wa.iscale = k.iscale; wa.dw = dweight;
-        wa.s_co = (int64_t)I * KK; wa.s_ci = KK;
-        wa.N = N; wa.Co = O; wa.Ci = I; wa.Hd = s.zh; wa.Wd = s.zw; wa.Hx = d.in_h; wa.Wx = d.in_w;
-        wa.sn = s.sn; wa.sd = s.sd; wa.taps = s.taps; wa.chunks = 0; wa.chunk_pix = 0;
-        st = run_wgrad(d.dtype, wa, stream); if (st) return st;
+        // B operand: x * s' * c2g NHWC; result scale a[o] / (gk * c2g)
+        wgrad_scalars_kernel<<<1, 256, 0, stream>>>(k.iscale, N * I, w.gs, gs ? 1 : 0);
+        st = launch_status("modconv wgrad_scalars_kernel"); if (st) return st;
+        st = run_prepass(d.dtype, f32, x, k.iscale, w.gs + 2, w.xt, w.xt_lo, N, I, d.in_h * d.in_w, stream); if (st) return st;
+        st = run_tc_wgrad(f32, d, s, w, k.a, w.gs + 3, dweight, stream); if (st) return st;
     }
     return VFM_OK;
 }

@@ -217,9 +217,11 @@ def run_ours(args):
     assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a CUDA device; there is no CPU fallback'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    # same numerics switches as the reference (training/training_loop.py:504-505): no TF32 in the fp32 glue layers
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    # same numerics switches as the reference: its training loop turns TF32 off for the fp32 glue layers
+    # (training/training_loop.py:504-505); its decode/reconstruct tools leave PyTorch's defaults untouched
+    if args.mode == 'train':
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()

@@ -286,20 +286,47 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
             }
+            if (DGRAD && p.aux_sum) {
+                // dstyles partial: sum over the tile's pixels of x * dxpre, 16 columns at a time
+                float part[16];
+#pragma unroll
+                for (int c = 0; c < 16; c++) part[c] = valid ? to_acc(auxp[(size_t)(j * 16 + c) * HW]) * (v[c] * gsv) : 0.f;
+                if (warp_one_sample) {
+                    // butterfly transpose-reduce over the 32 lanes: 16 shuffles for 16 columns (instead of 5 per column);
+                    // afterwards lane l (l even) holds the warp total of column (l >> 1)
+                    float a8[8], a4[4], a2[2], a1;
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const float send = b16 ? part[c] : part[c + 8], keep = b16 ? part[c + 8] : part[c];
+                        a8[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float send = b8 ? a8[c] : a8[c + 4], keep = b8 ? a8[c + 4] : a8[c];
+                        a4[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const float send = b4 ? a4[c] : a4[c + 2], keep = b4 ? a4[c + 2] : a4[c];
+                        a2[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float send = b2 ? a2[0] : a2[1], keep = b2 ? a2[1] : a2[0];
+                        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    const int n_w = __shfl_sync(0xffffffffu, n, 0);      // the warp's sample (all lanes share it)
+                    if ((lane & 1) == 0 && n_w < p.N) atomicAdd(&p.aux_sum[(size_t)n_w * p.Nout + o0 + j * 16 + (lane >> 1)], a1);
+                } else if (valid) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + j * 16 + c], part[c]);
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const int col = j * 16 + c;
-                const float acc = v[c];
-                if (DGRAD && p.aux_sum) {
-                    float part = valid ? to_acc(auxp[(size_t)col * HW]) * (acc * gsv) : 0.f;
-                    if (warp_one_sample) {
-                        part = warp_sum(part);
-                        if (lane == 0 && n < p.N) atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + col], part);
-                    } else if (valid) {
-                        atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + col], part);
-                    }
-                }
-                const float val = acc * sc[col] + addv;
+                const float val = v[c] * sc[col] + addv;
                 if (valid) outp[(size_t)col * HW] = from_acc<TOut, float>(val);
             }
         }

@@ -182,6 +182,96 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p) {
     }
 }
 
+// ---- hot path: the decoder's linear / lrelu layers on NCHW tensors ----------------------------------------------------
+// One (n,c) row per blockIdx.y: the bias is a block constant, there is no integer division anywhere, the derivative of
+// lrelu is a select on the sign of y (no y/gain division), the bias gradient is one block reduction + one atomic.
+// ~6 instructions per element, so the kernel is limited by HBM and not by instruction issue.
+template <class T, int A, int G>
+__global__ void __launch_bounds__(256) bias_act_rows_kernel(BiasActArgs p, int vec_per_row, int vec_per_block) {
+    constexpr int VEC = (int)(16 / sizeof(T));
+    constexpr int UNROLL = 4;
+    __shared__ float red[32];
+    struct alignas(16) Vec { T e[VEC]; };
+    const int64_t row = blockIdx.y;
+    const int c = (int)(row % p.size_b);
+    const float bias = (p.b && G == 0) ? to_acc(((const T*)p.b)[c]) : 0.f;
+    const float gain = (float)p.gain, alpha = (float)p.alpha, clamp = (float)p.clamp;
+    const float gpos = gain, gneg = (A == 3) ? gain * alpha : gain;
+    const bool pos_if_positive = gain > 0.f;      // sign(y) == sign(act(x)) * sign(gain)
+    const int v_begin = blockIdx.x * vec_per_block, v_end = min(v_begin + vec_per_block, vec_per_row);
+    const uint4* xin = (const uint4*)p.x + row * vec_per_row;
+    const uint4* yin = (const uint4*)p.yref + row * vec_per_row;
+    uint4* out = (uint4*)p.y + row * vec_per_row;
+    float sum = 0.f;
+    for (int v0 = v_begin + threadIdx.x; v0 < v_end; v0 += blockDim.x * UNROLL) {
+        Vec xv[UNROLL], yv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int v = v0 + u * blockDim.x;
+            if (v < v_end) {
+                *(uint4*)&xv[u] = ldg_stream(xin + v);
+                if (G == 1 && p.yref) *(uint4*)&yv[u] = ldg_stream(yin + v);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int v = v0 + u * blockDim.x;
+            if (v >= v_end) continue;
+            Vec o;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                float x = to_acc(xv[u].e[k]);
+                float r;
+                if (G == 0) {
+                    x += bias;
+                    r = x * ((x > 0.f) ? gpos : gneg);
+                    if (clamp >= 0.f) r = fminf(fmaxf(r, -clamp), clamp);
+                } else {
+                    const float yr = p.yref ? to_acc(yv[u].e[k]) : 0.f;
+                    const bool pos = (A == 1) ? true : ((yr > 0.f) == pos_if_positive && yr != 0.f);
+                    r = x * (pos ? gpos : gneg);
+                    if (clamp >= 0.f && !(yr > -clamp && yr < clamp)) r = 0.f;
+                    sum += r;
+                }
+                o.e[k] = from_acc<T, float>(r);
+            }
+            stg_stream(out + v, *(const uint4*)&o);
+        }
+    }
+    if (G == 1 && p.db) {
+        sum = block_sum(sum, red);
+        if (threadIdx.x == 0) atomicAdd(&p.db[c], sum);
+    }
+}
+
+template <class T, int A, int G>
+int launch_rows(const BiasActArgs& a, cudaStream_t stream) {
+    constexpr int VEC = (int)(16 / sizeof(T));
+    const int vec_per_row = (int)(a.step_b / VEC);
+    const int64_t rows = a.size_x / a.step_b;
+    int vec_per_block = vec_per_row;
+    // split long rows so that there are enough blocks; keep >= 4 vectors per thread when possible
+    while (vec_per_block > 256 * 8 && rows * ceil_div(vec_per_row, vec_per_block) < (int64_t)kNumSMs * 16) vec_per_block = ceil_div(vec_per_block, 2);
+    if (vec_per_block > 256 * 16) vec_per_block = 256 * 16;
+    dim3 grid(ceil_div(vec_per_row, vec_per_block), (unsigned)rows);
+    int ntens = 2 + ((G == 1 && a.yref) ? 1 : 0);
+    KernelTimer timer(G == 0 ? "bias_act_fwd" : "bias_act_grad", stream, 0.0, (double)ntens * (double)a.size_x * sizeof(T) + (double)a.size_b * sizeof(T));
+    bias_act_rows_kernel<T, A, G><<<grid, 256, 0, stream>>>(a, vec_per_row, vec_per_block);
+    return launch_status("bias_act_rows_kernel");
+}
+
+// returns VFM_ERR_NO_KERNEL when the call does not fit the hot-path kernel
+template <class T>
+int try_rows(const BiasActArgs& a, int act, int mode, cudaStream_t stream) {
+    constexpr int VEC = (int)(16 / sizeof(T));
+    if (mode != 0 || !(act == 1 || act == 3) || a.grad > 1 || a.xref || a.dy) return VFM_ERR_NO_KERNEL;
+    if (a.step_b < 256 || a.step_b % VEC != 0 || a.size_x % a.step_b != 0) return VFM_ERR_NO_KERNEL;
+    if (a.size_x / a.step_b > 65535 || a.step_b / VEC > (int64_t)0x7fffffff) return VFM_ERR_NO_KERNEL;
+    if (a.grad == 1 && act == 3 && !a.yref) return VFM_ERR_NO_KERNEL;
+    if (act == 1) return a.grad == 0 ? launch_rows<T, 1, 0>(a, stream) : launch_rows<T, 1, 1>(a, stream);
+    return a.grad == 0 ? launch_rows<T, 3, 0>(a, stream) : launch_rows<T, 3, 1>(a, stream);
+}
+
 template <class T, int A>
 int launch_mode(const BiasActArgs& a0, int mode, cudaStream_t stream) {
     BiasActArgs a = a0;
@@ -257,6 +347,10 @@ extern "C" int vfm_bias_act(const vfm_bias_act_params* p, void* stream_) {
         if (!(p->b || p->db)) mode = 0;
         else if (a.step_b % vec == 0) mode = 0;
         else if (a.step_b == 1 && a.size_b % vec == 0) mode = 1;
+    }
+    if (p->dtype != VFM_F64) {
+        int st = (p->dtype == VFM_F16) ? try_rows<__half>(a, p->act, mode, stream) : try_rows<float>(a, p->act, mode, stream);
+        if (st != VFM_ERR_NO_KERNEL) return st;
     }
     switch (p->dtype) {
         case VFM_F16: return launch_act<__half>(a, p->act, mode, stream);

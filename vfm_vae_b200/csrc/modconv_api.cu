@@ -21,7 +21,7 @@ int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, con
 bool tc_supported(const vfm_modconv_desc& d);
 size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
 // stage-1 contraction: x -> z (== y for up=1; noise only added when up == 1)
-int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z,
+int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
                       const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
@@ -48,12 +48,13 @@ static int validate(const vfm_modconv_desc& d) {
 }
 
 static int call_upfirdn(int dtype, const void* in, void* out, const float* f, int fw, int fh, int up, int down, int px0, int py0, int flip, float gain,
-                        int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream) {
+                        int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream, int in_pitch = 0) {
+    if (in_pitch == 0) in_pitch = iw;
     vfm_upfirdn2d_params u;
     u.x = in; u.f = f; u.y = out; u.dtype = dtype;
     u.upx = u.upy = up; u.downx = u.downy = down; u.padx0 = px0; u.pady0 = py0; u.flip = flip; u.gain = gain;
     u.in_w = iw; u.in_h = ih; u.channels = C; u.batch = N;
-    u.in_stride_w = 1; u.in_stride_h = iw; u.in_stride_c = (int64_t)ih * iw; u.in_stride_n = (int64_t)C * ih * iw;
+    u.in_stride_w = 1; u.in_stride_h = in_pitch; u.in_stride_c = (int64_t)ih * in_pitch; u.in_stride_n = (int64_t)C * ih * in_pitch;
     u.fw = fw; u.fh = fh; u.f_stride_w = 1; u.f_stride_h = fw;
     u.out_w = ow; u.out_h = oh;
     u.out_stride_w = 1; u.out_stride_h = ow; u.out_stride_c = (int64_t)oh * ow; u.out_stride_n = (int64_t)C * oh * ow;
@@ -65,7 +66,7 @@ static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
     Carver cv(nullptr, ~(size_t)0);
     Coefs k; carve_coefs(cv, d, k);
     Stage1 s = make_stage1(d);
-    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * s.zw * esize(d.dtype));
+    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 7) & ~7) * esize(d.dtype));
     if (direction == 1) { cv.take<float>((size_t)d.batch * d.out_channels); cv.take<float>((size_t)d.batch * d.in_channels); }
     return cv.off + 256;
 }
@@ -105,14 +106,16 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     k.d = p->dcoefs;
     Stage1 s = make_stage1(d);
     void* z = p->y;
-    if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * s.zw * esize(d.dtype));
+    // stage-1 output rows are padded to 16 bytes on the tensor-core path so that the blur stages its tiles with vector loads
+    const int zpitch = (d.up == 2 && use_tc(d)) ? ((s.zw + 7) & ~7) : s.zw;
+    if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 7) & ~7) * esize(d.dtype));
     st = compute_coefs(d, p->weight, p->styles, k, p->dcoefs, nullptr, stream); if (st) return st;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
     const float* s1_noise = (d.up == 1) ? p->noise : nullptr;
 
     if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
-        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, s1_noise, noise_sn, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
     } else {
         ConvArgs a;
@@ -127,7 +130,7 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     }
     if (d.up == 1) return VFM_OK;
     return call_upfirdn(d.dtype, z, p->y, d.resample_filter, d.fw, d.fh, s.r_up, 1, s.r_px0, s.r_py0, 0, (float)(d.up * d.up),
-                        d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream);
+                        d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream, zpitch);
 }
 
 extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream_) {

@@ -148,6 +148,8 @@ struct TcArgs {
     int tiles_w, tiles_h;      // tile grid (covers the largest phase)
     int N, Nout;
     int out_H, out_W, out_s;   // output tensor [N, Nout, out_H, out_W]; output coordinate = g*out_s + o{y,x}
+    int out_pitch;             // row pitch of the output tensor in elements (>= out_W; planes are out_H*out_pitch apart)
+    int nphases;
     int a_s;                   // A coordinate = g*a_s + d{y,x}  (2 for the strided gather of the transposed conv's backward)
     void* out;
     const float* oscale;       // [N, Nout]
@@ -172,10 +174,11 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     float* s_scale = (float*)(tmem_slot + 2);    // [tn][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TcPhase& ph = p.ph[blockIdx.z];
+    // phases vary fastest across CTAs so that the interleaved sub-pixel stores of one output tile meet in L2
+    const TcPhase& ph = p.ph[blockIdx.x % p.nphases];
 
     // tile coordinates (in the phase grid)
-    int mt = blockIdx.x;
+    int mt = blockIdx.x / p.nphases;
     const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
     const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
     const int n0 = mt * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
@@ -264,10 +267,10 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int n = n0 + nl, gh = h0 + hl, gw = w0 + wl;
         const int oy = gh * p.out_s + ph.oy, ox = gw * p.out_s + ph.ox;
         const bool valid = (n < p.N) && (gh < ph.Hg) && (gw < ph.Wg) && (oy < p.out_H) && (ox < p.out_W);
-        const size_t HW = (size_t)p.out_H * p.out_W;
-        const size_t pix = (size_t)oy * p.out_W + ox;
+        const size_t HW = (size_t)p.out_H * p.out_pitch;
+        const size_t pix = (size_t)oy * p.out_pitch + ox;
         float addv = 0.f;
-        if (!DGRAD && p.add && valid) addv = p.add[(size_t)n * p.add_sn + pix];
+        if (!DGRAD && p.add && valid) addv = p.add[(size_t)n * p.add_sn + (size_t)oy * p.out_W + ox];
         TOut* outp = (TOut*)p.out + ((size_t)n * p.Nout + o0) * HW + pix;
         const TOut* auxp = DGRAD ? (const TOut*)p.aux + ((size_t)n * p.Nout + o0) * HW + pix : nullptr;
         const float* sc = s_scale + nl * BN;
@@ -703,7 +706,8 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     st = encode_map(&maps[1], op.wt, 3, bdims, bbox, nullptr); if (st) return st;
     st = encode_map(&maps[2], f32 ? op.act_lo : op.act, 4, adims, abox, astr); if (st) return st;
     st = encode_map(&maps[3], f32 ? op.wt_lo : op.wt, 3, bdims, bbox, nullptr); if (st) return st;
-    dim3 grid(a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn), op.Nout / BN, nphases);
+    a.nphases = nphases;
+    dim3 grid(a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn) * nphases, op.Nout / BN, 1);
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
     if (!f32) return dgrad ? launch_tc<__half, true, false>(maps, a, grid, flops, stream) : launch_tc<__half, false, false>(maps, a, grid, flops, stream);
     return dgrad ? launch_tc<float, true, true>(maps, a, grid, flops, stream) : launch_tc<float, false, true>(maps, a, grid, flops, stream);
@@ -829,7 +833,7 @@ size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction) {
     return cv.off + 512;
 }
 
-int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z,
+int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
                       const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
@@ -867,7 +871,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
             }
         a.out_s = 2;
     }
-    a.out_H = s.zh; a.out_W = s.zw; a.a_s = 1;
+    a.out_H = s.zh; a.out_W = s.zw; a.out_pitch = zpitch; a.a_s = 1;
     a.out = z; a.oscale = w.o_scale; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr;
     TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, d.in_h, d.in_w, I, O, s.taps.ntaps};
     return run_tc_conv(f32, false, op, a, nph, stream);
@@ -907,7 +911,7 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         ph.ntaps = dt.ntaps;
         for (int t = 0; t < dt.ntaps; t++) { ph.dy[t] = dt.off_y[t]; ph.dx[t] = dt.off_x[t]; ph.tb[t] = t; }
         ph.oy = ph.ox = 0; ph.Hg = d.in_h; ph.Wg = d.in_w;
-        a.out_s = 1; a.out_H = d.in_h; a.out_W = d.in_w; a.a_s = sn;
+        a.out_s = 1; a.out_H = d.in_h; a.out_W = d.in_w; a.out_pitch = d.in_w; a.a_s = sn;
         a.out = dx; a.oscale = k.iscale; a.gscale_inv = gs ? gs + 1 : nullptr; a.add = nullptr; a.add_sn = 0;
         a.aux = dsum ? x : nullptr; a.aux_sum = dsum;
         TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, s.zh, s.zw, O, I, dt.ntaps};

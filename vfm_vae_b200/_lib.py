@@ -75,8 +75,14 @@ class ModconvBwdParams(C.Structure):
                 ('workspace', _vp), ('workspace_bytes', _sz)]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [('name', C.c_char * 64), ('launches', _i64), ('total_ms', _f64), ('flops', _f64), ('bytes', _f64)]
+
+
 #: every symbol include/vfm_ops.h declares, with (restype, argtypes)
 SYMBOLS = {
+    'vfm_timing_enable': (None, [C.c_int]),
+    'vfm_timing_report': (C.c_int, [C.POINTER(KernelStat), C.c_int]),
     'vfm_last_error': (C.c_char_p, []),
     'vfm_abi_version': (C.c_int, []),
     'vfm_launch_count': (C.c_uint64, []),

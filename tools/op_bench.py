@@ -95,8 +95,13 @@ for (C, H, dt) in [(128, 257, torch.float16), (256, 129, torch.float16), (512, 6
     es = 2 if dt == torch.float16 else 4
     x = torch.randn(1, N * C, H, H, device=dev, dtype=dt)
     ms = timeit(lambda: U.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4))
-    report(f'upfirdn2d blur 4x4 [1,{N * C},{H},{H}]->{H - 1} {str(dt)[6:]}', ms, nbytes=(x.numel() + N * C * (H - 1) ** 2) * es + 64)
+    report(f'upfirdn2d blur 4x4 [1,{N * C},{H},{H}]->{H - 1} {str(dt)[6:]} (dense rows)', ms, nbytes=(x.numel() + N * C * (H - 1) ** 2) * es + 64)
     del x
+    Hp = (H + 7) & ~7      # what the modulated conv's up=2 path feeds the blur: rows padded to 16 bytes
+    xp = torch.randn(1, N * C, H, Hp, device=dev, dtype=dt)[..., :H]
+    ms = timeit(lambda: U.upfirdn2d(xp, f, padding=[1, 1, 1, 1], gain=4))
+    report(f'upfirdn2d blur 4x4 [1,{N * C},{H},{H}]->{H - 1} {str(dt)[6:]} (16B-pitched rows)', ms, nbytes=(xp.numel() + N * C * (H - 1) ** 2) * es + 64)
+    del xp
 if want('upfirdn2d'):
     x = torch.randn(N, 128, 128, 128, device=dev, dtype=torch.float16)
     ms = timeit(lambda: U.upsample2d(x, f))

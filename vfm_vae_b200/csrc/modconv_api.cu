@@ -71,7 +71,15 @@ static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
     return cv.off + 256;
 }
 
-static bool use_tc(const vfm_modconv_desc& d) { return !d.force_generic && tc_supported(d); }
+// ---- streaming path for 1x1 convs with <= 4 output channels (modconv_pointwise.cu) ----
+bool pw_supported(const vfm_modconv_desc& d);
+size_t pw_workspace_bytes(const vfm_modconv_desc& d, int direction);
+int pw_stage1_forward(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, cudaStream_t stream);
+int pw_stage1_backward(const vfm_modconv_desc& d, const void* dy, const void* x, const float* weight, const Coefs& k, void* dx, float* dsum, float* dweight,
+                       void* ws, size_t ws_bytes, cudaStream_t stream);
+
+static bool use_pw(const vfm_modconv_desc& d) { return !d.force_generic && pw_supported(d); }
+static bool use_tc(const vfm_modconv_desc& d) { return !d.force_generic && !pw_supported(d) && tc_supported(d); }
 
 }  // namespace modconv
 }  // namespace vfm
@@ -88,6 +96,7 @@ extern "C" size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int dir
     if (!d) return 0;
     size_t g = generic_workspace(*d, direction);
     if (use_tc(*d)) g += tc_workspace_bytes(*d, direction);
+    if (use_pw(*d)) g += pw_workspace_bytes(*d, direction);
     return g;
 }
 
@@ -113,7 +122,10 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
     const float* s1_noise = (d.up == 1) ? p->noise : nullptr;
 
-    if (use_tc(d)) {
+    if (use_pw(d) && aligned16(p->x) && aligned16(p->y)) {
+        st = pw_stage1_forward(d, p->x, p->weight, k, z, s1_noise, noise_sn, stream);
+        if (st) return st;
+    } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
@@ -179,7 +191,12 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     if (p->dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
     if (p->dweight) VFM_CUDA_OK(cudaMemsetAsync(p->dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
 
-    if (use_tc(d)) {
+    if (use_pw(d) && aligned16(p->x) && aligned16(p->dy) && (!p->dx || aligned16(p->dx))) {
+        cv.off = (cv.off + 255) & ~(size_t)255;
+        st = pw_stage1_backward(d, dzp, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
+                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        if (st) return st;
+    } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = tc_stage1_backward(d, s, dzp, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
                                 (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);

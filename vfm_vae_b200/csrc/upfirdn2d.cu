@@ -30,6 +30,7 @@ struct UpfirdnArgs {
     int64_t add_sh, add_sn;
     // tiled only
     int xstart, ystart, tiles_x, tiles_y;
+    int vec_ok;   // input rows can be staged with 16-byte loads
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -71,28 +72,36 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnArgs p, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Tiled kernel.  Requires: in/out W-contiguous (stride_w == 1), (UP == 1 || DOWN == 1), FW % UP == 0, FH % UP == 0.
+// Tiled kernel.  Requires: in/out W-contiguous (stride_w == 1), (UP == 1 || DOWN == 1).
+//
+// Shared-memory layout: one row per input row; inside a row the columns are stored *swizzled* so that the register-patch
+// reads of a warp (lane l reads column G*l + t, G = OX*DOWN/UP input columns per thread) hit 32 different banks:
+//     column c = G*a + b  (0 <= b < G)   ->   slot  b*A + a      (A = columns per residue class)
+// The tile origin in shared memory is aligned to 16 bytes of the *global* row, so staging is one 16-byte global load per
+// thread (when the tensor's strides allow it; scalar loads otherwise) followed by V scalar shared stores (<= 2-way conflict).
 template <int UP, int DOWN, int FW, int FH>
 struct TileCfg {
     static constexpr int OX = 4, OY = (DOWN == 1) ? 4 : 2;   // outputs per thread
     static constexpr int TX = 32, TY = 8;            // threads
     static constexpr int TW = TX * OX, TH = TY * OY; // output tile
+    static constexpr int G = OX * DOWN / UP;         // input columns between neighbouring lanes (4, 2, 1 or 8)
     static constexpr int PW = ((OX - 1) * DOWN + FW - 1) / UP + 1;   // register patch
     static constexpr int PH = ((OY - 1) * DOWN + FH - 1) / UP + 1;
-    static constexpr int IW = ((TW - 1) * DOWN + FW - 1) / UP + 1;   // smem input tile
+    static constexpr int IW = ((TW - 1) * DOWN + FW - 1) / UP + 1;   // input tile (exact)
     static constexpr int IH = ((TH - 1) * DOWN + FH - 1) / UP + 1;
-    // patch rows are fetched with the widest aligned shared-memory vector the thread's column offset allows:
-    // LDS.128 (up=1), LDS.64 (up=2), LDS.32 (up=4).  Lanes of a warp walk one row contiguously -> conflict-free.
-    static constexpr int VW = (UP == 1) ? 4 : (UP == 2 ? 2 : 1);
-    static constexpr int PWV = (PW + VW - 1) / VW * VW;              // patch width rounded up to whole vectors
-    static constexpr int IWP = ((TX - 1) * OX * DOWN / UP + PWV + 3) & ~3;   // pitch covers the vector overrun
+    static constexpr int MAXSHIFT = 8;                                // alignment slack in columns (16 bytes of fp16)
+    static constexpr int NCOL = IW + MAXSHIFT;                        // columns staged per row
+    static constexpr int A = (NCOL + 8 + G - 1) / G;                  // columns per residue class (incl. vector overrun)
+    static constexpr int IWP = G * A;                                 // slots per row
+    __host__ __device__ static constexpr int slot(int c) { return (c % G) * A + (c / G); }
 };
 
 template <class T, int UP, int DOWN, int FW, int FH>
 __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
     typedef typename Acc<T>::type S;
     typedef TileCfg<UP, DOWN, FW, FH> C;
-    __shared__ __align__(32) S s_in[C::IH * C::IWP];
+    constexpr int V = (int)(16 / sizeof(T));        // elements per 16-byte global vector
+    __shared__ S s_in[C::IH * C::IWP];
     __shared__ S s_f[FH * FW];
 
     // flat block index -> (plane, tile_y, tile_x)
@@ -115,13 +124,29 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
     // tile origin in output coordinates; (ox0*DOWN - pad0) is a multiple of UP by construction of xstart/ystart
     const int ox_t = p.xstart + tile_x * C::TW, oy_t = p.ystart + tile_y * C::TH;
     const int ix_t = (ox_t * DOWN - p.padx0) / UP, iy_t = (oy_t * DOWN - p.pady0) / UP;   // exact, may be negative
+    const int ix_al = floor_div(ix_t, V) * V;        // 16-byte aligned column the staged tile starts at
+    const int shift = ix_t - ix_al;                  // 0 .. V-1, uniform over the grid (TW*DOWN/UP is a multiple of 8)
     const T* xp = (const T*)p.x + (int64_t)n * p.isn + (int64_t)c * p.isc;
-    for (int i = threadIdx.x; i < C::IH * C::IW; i += blockDim.x) {
-        int ry = i / C::IW, rx = i - ry * C::IW;
-        int ix = ix_t + rx, iy = iy_t + ry;
-        S v = (S)0;
-        if (ix >= 0 && ix < p.in_w && iy >= 0 && iy < p.in_h) v = to_acc(xp[(int64_t)iy * p.ish + ix]);
-        s_in[ry * C::IWP + rx] = v;
+    {
+        constexpr int NV = (C::NCOL + V - 1) / V;    // vectors per row
+        for (int i = threadIdx.x; i < C::IH * NV; i += blockDim.x) {
+            const int ry = i / NV, j = i - ry * NV;
+            const int iy = iy_t + ry, ix0 = ix_al + j * V;
+            struct alignas(16) Vec { T e[V]; } v;
+            const bool row_ok = (iy >= 0 && iy < p.in_h);
+            if (row_ok && p.vec_ok && ix0 >= 0 && ix0 + V <= p.in_w) {
+                *(uint4*)&v = *(const uint4*)(xp + (int64_t)iy * p.ish + ix0);
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; k++) {
+                    const int ix = ix0 + k;
+                    v.e[k] = (row_ok && ix >= 0 && ix < p.in_w) ? xp[(int64_t)iy * p.ish + ix] : from_acc<T, S>((S)0);
+                }
+            }
+            S* dst = s_in + ry * C::IWP;
+#pragma unroll
+            for (int k = 0; k < V; k++) dst[C::slot(j * V + k)] = to_acc(v.e[k]);
+        }
     }
     __syncthreads();
 
@@ -134,7 +159,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     // thread's first output (tile-relative) and first patch element (tile-relative, input coords)
     const int jx0 = lx * C::OX, jy0 = ly * C::OY;
-    const int px0 = jx0 * DOWN / UP, py0 = jy0 * DOWN / UP;   // exact: OX, OY multiples of UP
+    const int py0 = jy0 * DOWN / UP;                 // exact: OY multiple of UP
+    // slot of patch column q for this thread: column = G*lx + shift + q
+    int pslot[C::PW];
+#pragma unroll
+    for (int q = 0; q < C::PW; q++) pslot[q] = C::slot(C::G * lx + shift + q);
 
     S acc[C::OY][C::OX];
 #pragma unroll
@@ -144,17 +173,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
 
 #pragma unroll
     for (int r = 0; r < C::PH; r++) {
-        S row[C::PWV];
-        {
-            const S* src = &s_in[(py0 + r) * C::IWP + px0];
-            struct alignas(sizeof(S) * C::VW) VecT { S v[C::VW]; };
+        S row[C::PW];
+        const S* src = &s_in[(py0 + r) * C::IWP];
 #pragma unroll
-            for (int q = 0; q < C::PWV / C::VW; q++) {
-                VecT t = reinterpret_cast<const VecT*>(src)[q];
-#pragma unroll
-                for (int k = 0; k < C::VW; k++) row[q * C::VW + k] = t.v[k];
-            }
-        }
+        for (int q = 0; q < C::PW; q++) row[q] = src[pslot[q]];
 #pragma unroll
         for (int jy = 0; jy < C::OY; jy++) {
 #pragma unroll
@@ -179,7 +201,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
         int oy = oy0 + jy;
         if (oy < 0 || oy >= p.out_h) continue;
         T* rowp = yp + (int64_t)oy * p.osh;
-        T out[C::OX];
+        struct alignas(16) OutV { T e[C::OX]; } outv;
+        T* out = outv.e;
 #pragma unroll
         for (int jx = 0; jx < C::OX; jx++) {
             S v = acc[jy][jx];
@@ -275,6 +298,10 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
     a.osw = p->out_stride_w; a.osh = p->out_stride_h; a.osc = p->out_stride_c; a.osn = p->out_stride_n;
     a.add_sh = p->add_stride_h; a.add_sn = p->add_stride_n;
     a.xstart = a.ystart = a.tiles_x = a.tiles_y = 0;
+    {
+        const int64_t es = (p->dtype == VFM_F16) ? 2 : (p->dtype == VFM_F32 ? 4 : 8);
+        a.vec_ok = aligned16(p->x) && (a.ish * es) % 16 == 0 && (a.isc * es) % 16 == 0 && (a.isn * es) % 16 == 0;
+    }
     switch (p->dtype) {
         case VFM_F16: return launch<__half>(a, stream);
         case VFM_F32: return launch<float>(a, stream);

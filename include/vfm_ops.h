@@ -131,6 +131,12 @@ typedef struct {
     const float* add;
     int64_t      add_stride_h;
     int64_t      add_stride_n;
+    /* Extension (ep_enable = 0 = off): fused bias + activation on the result, y = clamp(act(y + ep_bias[c]) * ep_gain, +-ep_clamp),
+     * ep_act 1 = linear, 3 = lrelu(ep_alpha).  Lets the up=2 modulated conv fold the following bias_act into its blur. */
+    int32_t      ep_enable;
+    int32_t      ep_act;
+    double       ep_alpha, ep_gain, ep_clamp;
+    const void*  ep_bias;     /* [channels], dtype of x, or NULL */
 } vfm_upfirdn2d_params;
 
 VFM_API int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream);
@@ -226,6 +232,18 @@ typedef struct {
     float*       dcoefs;   /* [N,O] out */
     void*        workspace;
     size_t       workspace_bytes;
+    /* Optional fused layer epilogue (inference).  When ep_enable != 0 the kernel that produces y also
+     * applies what networks/generator.py:268-274 does after the conv:
+     *     y = clamp(act(y + bias[o]) * ep_gain, +-ep_clamp);   if (ep_residual) y = (ep_gamma[o] * y + ep_residual) * ep_res_scale
+     * ep_act is 1 (linear) or 3 (lrelu, slope ep_alpha).  Returns VFM_ERR_NO_KERNEL if the path chosen for this descriptor
+     * cannot fuse it; the caller then composes bias_act (+ residual arithmetic) itself, as the reference does. */
+    int32_t      ep_enable;
+    int32_t      ep_act;
+    double       ep_alpha, ep_gain, ep_clamp;   /* ep_clamp < 0 = off */
+    const void*  ep_bias;        /* [O], dtype of x, or NULL */
+    const void*  ep_residual;    /* [N,O,Hout,Wout], dtype of x, or NULL */
+    const float* ep_gamma;       /* [O] fp32 layer scale, required with ep_residual */
+    double       ep_res_scale;
 } vfm_modconv_fwd_params;
 
 typedef struct {

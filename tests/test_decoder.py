@@ -95,3 +95,18 @@ def test_decoder_cuda_fp16_blocks():
     assert rel_err(img, G.t('img')) <= 4e-3
     for i, m in enumerate(multi):
         assert rel_err(m, G.t(f'multi{i}')) <= 4e-3
+
+
+@pytest.mark.gpu
+def test_decoder_cuda_inference_fused_matches_unfused():
+    """Under no_grad the decoder takes the fused layer epilogue; it must agree with the unfused (training) composition."""
+    from vfm_vae_b200.decoder import default_ops
+    net, G = build(default_ops(), 'cuda')
+    z, ws = G.t('z', 'cuda'), G.t('ws', 'cuda')
+    img_a, multi_a = net(z, ws, None, None, force_fp32=True)            # autograd on -> unfused
+    with torch.no_grad():
+        img_b, multi_b = net(z, ws, None, None, force_fp32=True)        # fused (where the shapes allow)
+    assert rel_err(img_b, G.t('img')) <= 2e-5
+    assert rel_err(img_b, img_a) <= 2e-5
+    for a, b in zip(multi_a, multi_b):
+        assert rel_err(b, a) <= 2e-5

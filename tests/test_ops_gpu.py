@@ -409,3 +409,51 @@ def test_conv2d_resample_golden(case):
     ref = G.t(k + '_y')
     assert y.shape == ref.shape
     assert rel_err(y, ref) <= 1e-6
+
+
+# ------------------------------------------------------------------------- fused inference layer
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [
+    dict(N=2, I=128, O_=128, H=16, up=1, residual=False),
+    dict(N=2, I=128, O_=128, H=32, up=1, residual=True),
+    dict(N=2, I=256, O_=128, H=8, up=2, residual=False),
+    dict(N=2, I=128, O_=3, H=32, up=1, residual=False, torgb=True),
+], ids=lambda c: f"I{c['I']}O{c['O_']}H{c['H']}up{c['up']}{'res' if c['residual'] else ''}")
+def test_fused_layer_matches_oracle(cfg, dtype):
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
+    g = torch.Generator().manual_seed(30)
+    N, I, O_, H, up = cfg['N'], cfg['I'], cfg['O_'], cfg['H'], cfg['up']
+    torgb = cfg.get('torgb', False)
+    k = 1 if torgb else 3
+    xq = torch.randn(N, I, H, H, generator=g).to(dtype).float()
+    w = torch.randn(O_, I, k, k, generator=g) * (0.1 if torgb else 1.0)
+    s = (torch.randn(N, I, generator=g) + 1) * (1.0 / math.sqrt(I) if torgb else 1.0)
+    b = (torch.randn(O_, generator=g) * 0.2).to(dtype).float()
+    noise = None if torgb else torch.randn(H * up, H * up, generator=g) * 0.3
+    f = O.setup_filter([1, 3, 3, 1])
+    gamma = torch.rand(1, O_, 1, 1, generator=g) + 0.5
+    act, gain, clamp = ('linear', 1.0, 256.0) if torgb else ('lrelu', math.sqrt(2) * math.sqrt(0.5), 256.0 * math.sqrt(0.5))
+    yr = O.modulated_conv2d(xq, w, s, noise=noise, up=up, padding=k // 2, resample_filter=f if up == 2 else None,
+                            demodulate=not torgb, flip_weight=(up == 1))
+    yr = O.bias_act(yr, b, act=act, gain=gain, clamp=clamp)
+    if cfg['residual']:
+        yr = (gamma * yr + xq) * math.sqrt(2)
+    with torch.no_grad():
+        y = fused_modconv_bias_act(xq.to(DEV, dtype), w.to(DEV), s.to(DEV), b.to(DEV, dtype), noise=noise.to(DEV) if noise is not None else None,
+                                   up=up, padding=k // 2, resample_filter=f.to(DEV), demodulate=not torgb, flip_weight=(up == 1), act=act,
+                                   gain=gain, clamp=clamp, residual=xq.to(DEV, dtype) if cfg['residual'] else None,
+                                   gamma=gamma.to(DEV) if cfg['residual'] else None, res_scale=math.sqrt(2))
+    assert y is not None, 'fused path refused a shape it should take'
+    assert y.dtype == dtype and y.shape == yr.shape
+    assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
+
+
+def test_fused_layer_declines_what_it_cannot_do():
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
+    x = torch.randn(2, 40, 9, 13, device=DEV)            # ragged channels -> generic SIMT path, which does not fuse
+    w = torch.randn(24, 40, 3, 3, device=DEV)
+    s = torch.ones(2, 40, device=DEV)
+    with torch.no_grad():
+        assert fused_modconv_bias_act(x, w, s, torch.zeros(24, device=DEV), padding=1) is None
+    assert fused_modconv_bias_act(x.requires_grad_(True), w, s, torch.zeros(24, device=DEV), padding=1) is None   # autograd needed -> unfused

@@ -31,7 +31,8 @@ class Upfirdn2dParams(C.Structure):
                 ('fw', _i32), ('fh', _i32), ('f_stride_w', _i64), ('f_stride_h', _i64),
                 ('out_w', _i32), ('out_h', _i32),
                 ('out_stride_w', _i64), ('out_stride_h', _i64), ('out_stride_c', _i64), ('out_stride_n', _i64),
-                ('add', _vp), ('add_stride_h', _i64), ('add_stride_n', _i64)]
+                ('add', _vp), ('add_stride_h', _i64), ('add_stride_n', _i64),
+                ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64), ('ep_bias', _vp)]
 
 
 class FilteredLreluParams(C.Structure):
@@ -66,7 +67,9 @@ class ModconvDesc(C.Structure):
 
 class ModconvFwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('x', _vp), ('weight', _vp), ('styles', _vp), ('noise', _vp), ('y', _vp),
-                ('dcoefs', _vp), ('workspace', _vp), ('workspace_bytes', _sz)]
+                ('dcoefs', _vp), ('workspace', _vp), ('workspace_bytes', _sz),
+                ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64),
+                ('ep_bias', _vp), ('ep_residual', _vp), ('ep_gamma', _vp), ('ep_res_scale', _f64)]
 
 
 class ModconvBwdParams(C.Structure):

@@ -22,7 +22,7 @@ bool tc_supported(const vfm_modconv_desc& d);
 size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
 // stage-1 contraction: x -> z (== y for up=1; noise only added when up == 1)
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
-                      const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream);
+                      const float* noise, int64_t noise_sn, const Epilogue& ep, void* ws, size_t ws_bytes, cudaStream_t stream);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
                        void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -48,7 +48,8 @@ static int validate(const vfm_modconv_desc& d) {
 }
 
 static int call_upfirdn(int dtype, const void* in, void* out, const float* f, int fw, int fh, int up, int down, int px0, int py0, int flip, float gain,
-                        int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream, int in_pitch = 0) {
+                        int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream, int in_pitch = 0,
+                        const Epilogue* ep = nullptr) {
     if (in_pitch == 0) in_pitch = iw;
     vfm_upfirdn2d_params u;
     u.x = in; u.f = f; u.y = out; u.dtype = dtype;
@@ -59,6 +60,8 @@ static int call_upfirdn(int dtype, const void* in, void* out, const float* f, in
     u.out_w = ow; u.out_h = oh;
     u.out_stride_w = 1; u.out_stride_h = ow; u.out_stride_c = (int64_t)oh * ow; u.out_stride_n = (int64_t)C * oh * ow;
     u.add = add; u.add_stride_h = ow; u.add_stride_n = add_sn;
+    u.ep_enable = 0; u.ep_act = 1; u.ep_alpha = 0; u.ep_gain = 1; u.ep_clamp = -1; u.ep_bias = nullptr;
+    if (ep && ep->enable) { u.ep_enable = 1; u.ep_act = ep->act; u.ep_alpha = ep->alpha; u.ep_gain = ep->gain; u.ep_clamp = ep->clamp; u.ep_bias = ep->bias; }
     return vfm_upfirdn2d(&u, stream);
 }
 
@@ -74,7 +77,7 @@ static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
 // ---- streaming path for 1x1 convs with <= 4 output channels (modconv_pointwise.cu) ----
 bool pw_supported(const vfm_modconv_desc& d);
 size_t pw_workspace_bytes(const vfm_modconv_desc& d, int direction);
-int pw_stage1_forward(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, cudaStream_t stream);
+int pw_stage1_forward(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, const Epilogue& ep, cudaStream_t stream);
 int pw_stage1_backward(const vfm_modconv_desc& d, const void* dy, const void* x, const float* weight, const Coefs& k, void* dx, float* dsum, float* dweight,
                        void* ws, size_t ws_bytes, cudaStream_t stream);
 
@@ -121,13 +124,24 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     st = compute_coefs(d, p->weight, p->styles, k, p->dcoefs, nullptr, stream); if (st) return st;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
     const float* s1_noise = (d.up == 1) ? p->noise : nullptr;
+    // optional fused layer epilogue: goes into the stage-1 kernel for up=1 and into the blur for up=2
+    Epilogue ep = no_epilogue();
+    if (p->ep_enable) {
+        VFM_CHECK_ARG(p->ep_act == 1 || p->ep_act == 3, "modulated_conv2d: the fused epilogue supports linear and lrelu only");
+        VFM_CHECK_ARG(!p->ep_residual || p->ep_gamma, "modulated_conv2d: ep_residual needs ep_gamma");
+        const bool fusable = (use_pw(d) && aligned16(p->x) && aligned16(p->y)) || (use_tc(d) && (d.up == 1 || !p->ep_residual));
+        if (!fusable) { set_error("modulated_conv2d: no kernel fuses the epilogue for this descriptor"); return VFM_ERR_NO_KERNEL; }
+        ep.enable = 1; ep.act = p->ep_act; ep.alpha = (float)p->ep_alpha; ep.gain = (float)p->ep_gain; ep.clamp = (float)p->ep_clamp;
+        ep.res_scale = (float)p->ep_res_scale; ep.bias = p->ep_bias; ep.residual = p->ep_residual; ep.gamma = p->ep_gamma;
+    }
+    const Epilogue s1_ep = (d.up == 1) ? ep : no_epilogue();
 
     if (use_pw(d) && aligned16(p->x) && aligned16(p->y)) {
-        st = pw_stage1_forward(d, p->x, p->weight, k, z, s1_noise, noise_sn, stream);
+        st = pw_stage1_forward(d, p->x, p->weight, k, z, s1_noise, noise_sn, s1_ep, stream);
         if (st) return st;
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
-        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, s1_ep, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
     } else {
         ConvArgs a;
@@ -142,7 +156,7 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     }
     if (d.up == 1) return VFM_OK;
     return call_upfirdn(d.dtype, z, p->y, d.resample_filter, d.fw, d.fh, s.r_up, 1, s.r_px0, s.r_py0, 0, (float)(d.up * d.up),
-                        d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream, zpitch);
+                        d.batch, d.out_channels, s.zh, s.zw, d.out_h, d.out_w, p->noise, noise_sn, stream, zpitch, &ep);
 }
 
 extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream_) {

@@ -30,6 +30,22 @@ struct Carver {
 
 inline size_t esize(int dtype) { return dtype == VFM_F16 ? 2 : (dtype == VFM_F32 ? 4 : 8); }
 
+// fused layer epilogue (inference): y = clamp(act(y + bias) * gain); optionally y = (gamma * y + residual) * res_scale
+struct Epilogue {
+    int enable, act;
+    float alpha, gain, clamp, res_scale;
+    const void* bias; const void* residual; const float* gamma;
+};
+inline Epilogue no_epilogue() { Epilogue e; e.enable = 0; e.act = 1; e.alpha = 0.f; e.gain = 1.f; e.clamp = -1.f; e.res_scale = 1.f; e.bias = nullptr; e.residual = nullptr; e.gamma = nullptr; return e; }
+template <class T> __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int ch, size_t idx) {
+    if (e.bias) v += to_acc(((const T*)e.bias)[ch]);
+    if (e.act == 3) v = (v > 0.f) ? v : v * e.alpha;
+    v *= e.gain;
+    if (e.clamp >= 0.f) v = fminf(fmaxf(v, -e.clamp), e.clamp);
+    if (e.residual) v = (e.gamma[ch] * v + to_acc(((const T*)e.residual)[idx])) * e.res_scale;
+    return v;
+}
+
 struct Coefs {          // fp32 scratch shared by forward and backward
     float* a;           // [O]   weight pre-normalisation (1 unless fp16 && demodulate)
     float* c;           // [N]   style pre-normalisation

@@ -19,7 +19,7 @@ constexpr int OMAX = 4;
 template <class T>
 __global__ void __launch_bounds__(256) pw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ isc,
                                                      const float* __restrict__ osc, const float* __restrict__ add, int64_t add_sn,
-                                                     T* __restrict__ y, int C, int O, int HW) {
+                                                     T* __restrict__ y, int C, int O, int HW, Epilogue ep) {
     constexpr int VEC = (int)(16 / sizeof(T));
     extern __shared__ float s_w[];     // [C][OMAX]: W[o,c] * isc[n,c]
     const int n = blockIdx.y;
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(const T* __restrict__ x, co
         for (int v = 0; v < VEC; v++) {
             float r = acc[o][v] * sc;
             if (add) r += add[(size_t)n * add_sn + p0 + v];
+            if (ep.enable) r = apply_epilogue<T>(ep, r, o, ((size_t)n * O + o) * HW + p0 + v);
             out.e[v] = from_acc<T, float>(r);
         }
         *(uint4*)(y + ((size_t)n * O + o) * HW + p0) = *(const uint4*)&out;
@@ -156,19 +157,19 @@ size_t pw_workspace_bytes(const vfm_modconv_desc& d, int direction) {
 }
 
 template <class T>
-static int pw_forward_t(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, cudaStream_t stream) {
+static int pw_forward_t(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, const Epilogue& ep, cudaStream_t stream) {
     constexpr int VEC = (int)(16 / sizeof(T));
     const int HW = d.in_h * d.in_w;
     dim3 grid(ceil_div(HW, 256 * VEC), d.batch);
     KernelTimer timer("modconv_pointwise_fwd", stream, 2.0 * d.batch * HW * (double)d.out_channels * d.in_channels,
                       (double)d.batch * HW * (d.in_channels + d.out_channels) * sizeof(T));
     pw_fwd_kernel<T><<<grid, 256, (size_t)d.in_channels * OMAX * sizeof(float), stream>>>((const T*)x, weight, k.iscale, k.oscale, noise, noise_sn, (T*)y,
-                                                                                         d.in_channels, d.out_channels, HW);
+                                                                                         d.in_channels, d.out_channels, HW, ep);
     return launch_status("modconv pw_fwd_kernel");
 }
 
-int pw_stage1_forward(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, cudaStream_t stream) {
-    return d.dtype == VFM_F16 ? pw_forward_t<__half>(d, x, weight, k, y, noise, noise_sn, stream) : pw_forward_t<float>(d, x, weight, k, y, noise, noise_sn, stream);
+int pw_stage1_forward(const vfm_modconv_desc& d, const void* x, const float* weight, const Coefs& k, void* y, const float* noise, int64_t noise_sn, const Epilogue& ep, cudaStream_t stream) {
+    return d.dtype == VFM_F16 ? pw_forward_t<__half>(d, x, weight, k, y, noise, noise_sn, ep, stream) : pw_forward_t<float>(d, x, weight, k, y, noise, noise_sn, ep, stream);
 }
 
 template <class T>

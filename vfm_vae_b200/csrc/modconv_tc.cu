@@ -158,9 +158,12 @@ struct TcArgs {
     int64_t add_sn;
     const void* aux;           // dgrad: x, same shape/dtype as out
     float* aux_sum;            // dgrad: [N, Nout] += sum_p aux * acc
+    Epilogue ep;               // forward: optional fused bias/activation/residual
 };
 
-template <class TOut, bool DGRAD, bool SPLIT>
+// PRE: the epilogue warps prefetch their 128 per-pixel side inputs (x for the dstyles reduction, or the residual of the
+// fused layer epilogue) into registers while the MMAs run, so the epilogue never waits on HBM.
+template <class TOut, bool DGRAD, bool SPLIT, bool PRE>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                       const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, TcArgs p) {
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
@@ -171,7 +174,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-    float* s_scale = (float*)(tmem_slot + 2);    // [tn][BN]
+    float* s_scale = (float*)(tmem_slot + 2);    // [8][BN] (tn <= 8)
+    float* s_bias = s_scale + 8 * BN;            // [BN] fused-epilogue bias
+    float* s_gamma = s_bias + BN;                // [BN] fused-epilogue layer scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // phases vary fastest across CTAs so that the interleaved sub-pixel stores of one output tile meet in L2
@@ -202,6 +207,12 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
             int nl = i / BN, c = i - nl * BN;
             int n = n0 + nl;
             s_scale[i] = (n < p.N) ? p.oscale[(size_t)n * p.Nout + o0 + c] * gs : 0.f;
+        }
+        if (!DGRAD && p.ep.enable) {
+            for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+                s_bias[i] = p.ep.bias ? to_acc(((const TOut*)p.ep.bias)[o0 + i]) : 0.f;
+                s_gamma[i] = p.ep.gamma ? p.ep.gamma[o0 + i] : 1.f;
+            }
         }
     }
     tc_fence_before();
@@ -277,10 +288,42 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const bool warp_one_sample = (p.tw * p.th >= 32);
         const float gsv = (DGRAD && p.gscale_inv) ? *p.gscale_inv : 1.f;    // undoes the global power-of-two scale of A
 
+        // side input of the epilogue: x (dgrad, NCHW like the output) or the residual (fused forward, dense NCHW)
+        constexpr bool HALF = (sizeof(TOut) == 2);
+        constexpr int NPRE = PRE ? (HALF ? BN / 2 : BN) : 1;
+        uint32_t pre[NPRE];
+        bool have_side = false;
+        if (PRE) {
+            const size_t HWd = (size_t)p.out_H * p.out_W;
+            const TOut* side = DGRAD ? (p.aux_sum ? auxp : nullptr)
+                                     : (p.ep.residual ? (const TOut*)p.ep.residual + ((size_t)n * p.Nout + o0) * HWd + (size_t)oy * p.out_W + ox : nullptr);
+            const size_t cstride = DGRAD ? HW : HWd;
+            have_side = (side != nullptr);
+            if (have_side && valid) {
+#pragma unroll
+                for (int c = 0; c < BN; c += 2) {
+                    if (HALF) {
+                        const unsigned short lo = *(const unsigned short*)(side + (size_t)c * cstride);
+                        const unsigned short hi = *(const unsigned short*)(side + (size_t)(c + 1) * cstride);
+                        pre[c / 2] = (uint32_t)lo | ((uint32_t)hi << 16);
+                    } else {
+                        pre[c] = *(const uint32_t*)(side + (size_t)c * cstride);
+                        pre[c + 1] = *(const uint32_t*)(side + (size_t)(c + 1) * cstride);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NPRE; c++) pre[c] = 0u;
+            }
+        }
+        auto side_val = [&](int col) -> float {
+            if (HALF) return __half2float(__ushort_as_half((unsigned short)(pre[col >> 1] >> ((col & 1) * 16))));
+            return __uint_as_float(pre[col]);
+        };
+
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int j = 0; j < BN / 16; j++) {
+        auto process = [&](int j) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 16), v);
             if (SPLIT) {
@@ -293,7 +336,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
                 // dstyles partial: sum over the tile's pixels of x * dxpre, 16 columns at a time
                 float part[16];
 #pragma unroll
-                for (int c = 0; c < 16; c++) part[c] = valid ? to_acc(auxp[(size_t)(j * 16 + c) * HW]) * (v[c] * gsv) : 0.f;
+                for (int c = 0; c < 16; c++) part[c] = (PRE ? side_val(j * 16 + c) : 0.f) * (v[c] * gsv);
                 if (warp_one_sample) {
                     // butterfly transpose-reduce over the 32 lanes: 16 shuffles for 16 columns (instead of 5 per column);
                     // afterwards lane l (l even) holds the warp total of column (l >> 1)
@@ -329,9 +372,24 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
             for (int c = 0; c < 16; c++) {
                 const int col = j * 16 + c;
-                const float val = v[c] * sc[col] + addv;
+                float val = v[c] * sc[col] + addv;
+                if (!DGRAD && p.ep.enable) {
+                    val += s_bias[col];
+                    if (p.ep.act == 3) val = (val > 0.f) ? val : val * p.ep.alpha;
+                    val *= p.ep.gain;
+                    if (p.ep.clamp >= 0.f) val = fminf(fmaxf(val, -p.ep.clamp), p.ep.clamp);
+                    if (PRE && have_side) val = (s_gamma[col] * val + side_val(col)) * p.ep.res_scale;
+                }
                 if (valid) outp[(size_t)col * HW] = from_acc<TOut, float>(val);
             }
+                };
+        if (PRE) {
+            // side inputs live in registers indexed by column: the column loop must be fully unrolled
+#pragma unroll
+            for (int j = 0; j < BN / 16; j++) process(j);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < BN / 16; j++) process(j);
         }
         tc_fence_before();
     }
@@ -669,11 +727,11 @@ void pick_tile(int Hg, int Wg, int& tw, int& th, int& tn) {
     }
 }
 
-size_t smem_bytes(bool split) { return (size_t)STAGES * (split ? 2 : 1) * (A_BYTES + B_BYTES) + 1024 + 256 + (size_t)8 * BN * sizeof(float); }
+size_t smem_bytes(bool split) { return (size_t)STAGES * (split ? 2 : 1) * (A_BYTES + B_BYTES) + 1024 + 256 + (size_t)10 * BN * sizeof(float); }
 
-template <class TOut, bool DGRAD, bool SPLIT>
+template <class TOut, bool DGRAD, bool SPLIT, bool PRE>
 int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT>;
+    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PRE>;
     size_t smem = smem_bytes(SPLIT);
     VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0);
@@ -709,8 +767,13 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     a.nphases = nphases;
     dim3 grid(a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn) * nphases, op.Nout / BN, 1);
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
-    if (!f32) return dgrad ? launch_tc<__half, true, false>(maps, a, grid, flops, stream) : launch_tc<__half, false, false>(maps, a, grid, flops, stream);
-    return dgrad ? launch_tc<float, true, true>(maps, a, grid, flops, stream) : launch_tc<float, false, true>(maps, a, grid, flops, stream);
+    const bool pre = dgrad ? (a.aux_sum != nullptr) : (a.ep.enable && a.ep.residual != nullptr);
+    if (!f32) {
+        if (dgrad) return pre ? launch_tc<__half, true, false, true>(maps, a, grid, flops, stream) : launch_tc<__half, true, false, false>(maps, a, grid, flops, stream);
+        return pre ? launch_tc<__half, false, false, true>(maps, a, grid, flops, stream) : launch_tc<__half, false, false, false>(maps, a, grid, flops, stream);
+    }
+    if (dgrad) return pre ? launch_tc<float, true, true, true>(maps, a, grid, flops, stream) : launch_tc<float, true, true, false>(maps, a, grid, flops, stream);
+    return pre ? launch_tc<float, false, true, true>(maps, a, grid, flops, stream) : launch_tc<float, false, true, false>(maps, a, grid, flops, stream);
 }
 
 int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream) {
@@ -834,7 +897,7 @@ size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction) {
 }
 
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
-                      const float* noise, int64_t noise_sn, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                      const float* noise, int64_t noise_sn, const Epilogue& ep, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
@@ -872,7 +935,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
         a.out_s = 2;
     }
     a.out_H = s.zh; a.out_W = s.zw; a.out_pitch = zpitch; a.a_s = 1;
-    a.out = z; a.oscale = w.o_scale; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr;
+    a.out = z; a.oscale = w.o_scale; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr; a.ep = ep;
     TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, d.in_h, d.in_w, I, O, s.taps.ntaps};
     return run_tc_conv(f32, false, op, a, nph, stream);
 }
@@ -913,7 +976,7 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         ph.oy = ph.ox = 0; ph.Hg = d.in_h; ph.Wg = d.in_w;
         a.out_s = 1; a.out_H = d.in_h; a.out_W = d.in_w; a.out_pitch = d.in_w; a.a_s = sn;
         a.out = dx; a.oscale = k.iscale; a.gscale_inv = gs ? gs + 1 : nullptr; a.add = nullptr; a.add_sn = 0;
-        a.aux = dsum ? x : nullptr; a.aux_sum = dsum;
+        a.aux = dsum ? x : nullptr; a.aux_sum = dsum; a.ep = no_epilogue();
         TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, s.zh, s.zw, O, I, dt.ntaps};
         st = run_tc_conv(f32, true, op, a, 1, stream); if (st) return st;
     }

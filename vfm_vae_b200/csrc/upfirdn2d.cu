@@ -31,7 +31,16 @@ struct UpfirdnArgs {
     // tiled only
     int xstart, ystart, tiles_x, tiles_y;
     int vec_ok;   // input rows can be staged with 16-byte loads
+    int ep_enable, ep_act; float ep_alpha, ep_gain, ep_clamp; const void* ep_bias;
 };
+
+template <class T, class S> __device__ __forceinline__ S ep_apply(const UpfirdnArgs& p, S v, int c) {
+    if (p.ep_bias) v += to_acc(((const T*)p.ep_bias)[c]);
+    if (p.ep_act == 3) v = (v > (S)0) ? v : v * (S)p.ep_alpha;
+    v *= (S)p.ep_gain;
+    if (p.ep_clamp >= 0.f) v = (v > (S)p.ep_clamp) ? (S)p.ep_clamp : ((v < -(S)p.ep_clamp) ? -(S)p.ep_clamp : v);
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 template <class T>
@@ -67,6 +76,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(UpfirdnArgs p, int64_t 
             }
         }
         if (p.add) acc += (S)p.add[(int64_t)n * p.add_sn + (int64_t)oy * p.add_sh + ox];
+        if (p.ep_enable) acc = ep_apply<T, S>(p, acc, c);
         ((T*)p.y)[(int64_t)n * p.osn + (int64_t)c * p.osc + (int64_t)oy * p.osh + (int64_t)ox * p.osw] = from_acc<T, S>(acc);
     }
 }
@@ -208,6 +218,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
             S v = acc[jy][jx];
             int ox = ox0 + jx;
             if (p.add && ox >= 0 && ox < p.out_w) v += (S)p.add[(int64_t)n * p.add_sn + (int64_t)oy * p.add_sh + ox];
+            if (p.ep_enable) v = ep_apply<T, S>(p, v, c);
             out[jx] = from_acc<T, S>(v);
         }
         bool full = ox0 >= 0 && ox0 + C::OX <= p.out_w;
@@ -297,6 +308,8 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
     a.out_w = p->out_w; a.out_h = p->out_h;
     a.osw = p->out_stride_w; a.osh = p->out_stride_h; a.osc = p->out_stride_c; a.osn = p->out_stride_n;
     a.add_sh = p->add_stride_h; a.add_sn = p->add_stride_n;
+    a.ep_enable = p->ep_enable; a.ep_act = p->ep_act; a.ep_alpha = (float)p->ep_alpha; a.ep_gain = (float)p->ep_gain; a.ep_clamp = (float)p->ep_clamp; a.ep_bias = p->ep_bias;
+    VFM_CHECK_ARG(!p->ep_enable || p->ep_act == 1 || p->ep_act == 3, "upfirdn2d: fused epilogue supports linear and lrelu only");
     a.xstart = a.ystart = a.tiles_x = a.tiles_y = 0;
     {
         const int64_t es = (p->dtype == VFM_F16) ? 2 : (p->dtype == VFM_F32 ? 4 : 8);

@@ -26,8 +26,8 @@ import torch.nn.functional as F
 
 def default_ops():
     from .torch_utils.ops import bias_act, upfirdn2d
-    from .torch_utils.ops.modulated_conv2d import modulated_conv2d
-    return SimpleNamespace(bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
+    from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act
+    return SimpleNamespace(fused_layer=fused_modconv_bias_act, bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
                            setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d,
                            modulated_conv2d=modulated_conv2d)
 
@@ -204,10 +204,18 @@ class SynthesisLayer(nn.Module):
         styles = self.affine(w)
         if self.residual:
             x = self.norm(x)
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        fused = getattr(self.ops, 'fused_layer', None)
+        if fused is not None and not torch.is_grad_enabled() and self.activation in ('linear', 'lrelu'):
+            # inference: conv + noise + bias_act (+ layer-scaled residual) in one kernel epilogue
+            y = fused(x, self.weight, styles, self.bias, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
+                      flip_weight=(self.up == 1), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp,
+                      residual=x if self.residual else None, gamma=self.gamma if self.residual else None, res_scale=float(np.sqrt(2)))
+            if y is not None:
+                return y
         y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                       resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         y = y.to(dtype)
-        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         y = self.ops.bias_act(y, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
         if self.residual:
             y = (self.gamma * y).to(dtype).add_(x).mul(np.sqrt(2))
@@ -228,6 +236,11 @@ class ToRGBLayer(nn.Module):
 
     def forward(self, x, w):
         styles = self.affine(w) * self.weight_gain
+        fused = getattr(self.ops, 'fused_layer', None)
+        if fused is not None and not torch.is_grad_enabled():
+            y = fused(x, self.weight, styles, self.bias, demodulate=False, act='linear', gain=1.0, clamp=self.conv_clamp)
+            if y is not None:
+                return y
         x = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False)
         return self.ops.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 

@@ -306,8 +306,11 @@ class _ModconvPlugin:
         return bool(_lib.load().vfm_modconv_uses_tensor_cores(C.byref(d)))
 
     @staticmethod
-    def forward(x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight, force_generic=False):
-        """-> (y [N,O,Hout,Wout] in x.dtype, dcoefs [N,O] fp32)"""
+    def forward(x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight, force_generic=False, epilogue=None):
+        """-> (y [N,O,Hout,Wout] in x.dtype, dcoefs [N,O] fp32).
+
+        ``epilogue`` (inference only): dict(act='linear'|'lrelu', alpha, gain, clamp, bias, residual, gamma, res_scale) fused into the
+        kernel that writes y; returns None instead of a tuple if no kernel can fuse it for this call (caller composes)."""
         _ModconvPlugin._common_checks(x, weight, styles, noise, up, resample_filter)
         d = _ModconvPlugin._desc(x, weight, up, padding, demodulate, flip_weight, noise, resample_filter, force_generic)
         if noise is not None:
@@ -322,8 +325,29 @@ class _ModconvPlugin:
         p.d = d
         p.x, p.weight, p.styles, p.noise, p.y, p.dcoefs = _ptr(x), _ptr(weight), _ptr(styles), _ptr(noise), _ptr(y), _ptr(dcoefs)
         p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+        keep = []
+        if epilogue is not None:
+            bias, res, gamma = epilogue.get('bias'), epilogue.get('residual'), epilogue.get('gamma')
+            _check(bias is None or (bias.dtype == x.dtype and bias.is_contiguous() and bias.numel() == d.out_channels), 'epilogue bias must be [O] in the dtype of x')
+            _check(res is None or (res.dtype == x.dtype and res.is_contiguous() and tuple(res.shape) == tuple(y.shape)), 'epilogue residual must match y')
+            if gamma is not None:
+                gamma = gamma.detach().to(torch.float32).reshape(-1).contiguous()
+                _check(gamma.numel() == d.out_channels, 'epilogue gamma must have O elements')
+            keep = [bias, res, gamma]
+            p.ep_enable = 1
+            p.ep_act = {'linear': 1, 'lrelu': 3}[epilogue.get('act', 'linear')]
+            p.ep_alpha = float(epilogue.get('alpha', 0.2))
+            p.ep_gain = float(epilogue.get('gain', 1.0))
+            clamp = epilogue.get('clamp')
+            p.ep_clamp = float(clamp) if clamp is not None else -1.0
+            p.ep_bias, p.ep_residual, p.ep_gamma = _ptr(bias), _ptr(res), _ptr(gamma)
+            p.ep_res_scale = float(epilogue.get('res_scale', 1.0))
         with torch.cuda.device(x.device):
-            _lib.check(lib.vfm_modconv_forward(C.byref(p), _stream(x)), 'modulated_conv2d')
+            st = lib.vfm_modconv_forward(C.byref(p), _stream(x))
+        del keep
+        if epilogue is not None and st == _lib.VFM_ERR_NO_KERNEL:
+            return None
+        _lib.check(st, 'modulated_conv2d')
         return y, dcoefs
 
     @staticmethod

@@ -109,3 +109,37 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
                            '(the CPU oracle is oracle/ref_ops.py, for tests).')
     _init()
     return _ModulatedConv2d.apply(x, weight, styles, noise, int(up), int(padding), resample_filter, bool(demodulate), bool(flip_weight))
+
+
+def fused_modconv_bias_act(x, weight, styles, bias, noise=None, up=1, padding=0, resample_filter=None, demodulate=True,
+                           flip_weight=True, act='lrelu', alpha=0.2, gain=1.0, clamp=None, residual=None, gamma=None, res_scale=1.0):
+    """Inference-only fusion of one legacy synthesis layer:
+
+        y = modulated_conv2d(x, weight, styles, noise, up, ...)                      networks/generator.py:264-265
+        y = bias_act(y, bias, act=act, gain=gain, clamp=clamp)                       networks/generator.py:268-270
+        y = (gamma * y + residual) * res_scale            (residual layers only)     networks/generator.py:272-274
+
+    in the kernel that writes y (conv epilogue for up=1, blur epilogue for up=2, streaming kernel for ToRGB).  No autograd.
+    Returns None when no kernel can fuse this call; the caller then composes the unfused ops exactly as the reference does.
+    """
+    assert act in ('linear', 'lrelu')
+    if x.device.type != 'cuda' or torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or styles.requires_grad):
+        return None
+    if residual is not None and up != 1:
+        return None
+    _init()
+    n = x.shape[0]
+    kh = weight.shape[2]
+    xc = x.contiguous()
+    w32 = weight.detach().to(torch.float32).contiguous()
+    s32 = styles.detach().to(torch.float32).contiguous()
+    f32 = resample_filter.to(device=x.device, dtype=torch.float32).contiguous() if (up > 1 and resample_filter is not None) else None
+    if up == 1:
+        oh, ow = x.shape[2] + 2 * padding - kh + 1, x.shape[3] + 2 * padding - weight.shape[3] + 1
+    else:
+        oh, ow = x.shape[2] * up + 2 * padding - (kh - 1), x.shape[3] * up + 2 * padding - (weight.shape[3] - 1)
+    n32 = _noise_canon(noise.detach() if noise is not None else None, n, oh, ow)
+    ep = dict(act=act, alpha=alpha, gain=gain, clamp=clamp, bias=bias.detach().to(x.dtype).contiguous() if bias is not None else None,
+              residual=residual.detach().contiguous() if residual is not None else None, gamma=gamma, res_scale=res_scale)
+    out = _plugin.forward(xc, w32, s32, n32, int(up), int(padding), f32, bool(demodulate), bool(flip_weight), force_generic, epilogue=ep)
+    return None if out is None else out[0]

@@ -199,8 +199,8 @@ def timing_report():
     lib = _lib.load()
     lib.vfm_timing_report.restype = C.c_int
     lib.vfm_timing_report.argtypes = [C.POINTER(Stat), C.c_int]
-    buf = (Stat * 64)()
-    n = min(lib.vfm_timing_report(buf, 64), 64)
+    buf = (Stat * 256)()
+    n = min(lib.vfm_timing_report(buf, 256), 256)
     return [dict(name=buf[i].name.decode(), launches=int(buf[i].launches), total_ms=buf[i].total_ms, flops=buf[i].flops, bytes=buf[i].bytes)
             for i in range(n)]
 

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libvfmops.so')
+LIB_PATH = os.environ.get('VFM_LIB_PATH') or os.path.join(_HERE, 'lib', 'libvfmops.so')   # override: A/B builds of the library only
 
 VFM_F16, VFM_F32, VFM_F64 = 0, 1, 2
 VFM_OK, VFM_ERR_NO_KERNEL, VFM_ERR_INVALID, VFM_ERR_CUDA, VFM_ERR_WORKSPACE = 0, -1, -2, -3, -4

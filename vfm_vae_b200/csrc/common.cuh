@@ -23,10 +23,11 @@ void count_launch(int n = 1);
 bool timing_enabled();
 class KernelTimer {
 public:
-    KernelTimer(const char* name, cudaStream_t stream, double flops, double bytes);
+    // `tag_fmt` (optional, printf-style): a shape tag appended to the name when VFM_TIMING_DETAIL=1 (per-layer tables)
+    KernelTimer(const char* name, cudaStream_t stream, double flops, double bytes, const char* tag_fmt = nullptr, ...);
     ~KernelTimer();
 private:
-    const char* name_; cudaStream_t stream_; double flops_, bytes_; cudaEvent_t e0_; bool on_;
+    char name_[64]; cudaStream_t stream_; double flops_, bytes_; cudaEvent_t e0_; bool on_;
 };
 
 #define VFM_CHECK_ARG(cond, ...)             \

@@ -4,6 +4,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -27,9 +28,23 @@ static std::vector<TimingRecord> g_records;
 
 bool timing_enabled() { return g_timing.load(std::memory_order_relaxed) != 0; }
 
-KernelTimer::KernelTimer(const char* name, cudaStream_t stream, double flops, double bytes)
-    : name_(name), stream_(stream), flops_(flops), bytes_(bytes), e0_(nullptr), on_(timing_enabled()) {
+static bool timing_detail() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VFM_TIMING_DETAIL"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t stream, double flops, double bytes, const char* tag_fmt, ...)
+    : stream_(stream), flops_(flops), bytes_(bytes), e0_(nullptr), on_(timing_enabled()) {
     if (!on_) return;
+    int n = snprintf(name_, sizeof(name_), "%s", name);
+    if (tag_fmt && timing_detail() && n > 0 && n < (int)sizeof(name_) - 2) {
+        name_[n++] = ':';
+        va_list ap;
+        va_start(ap, tag_fmt);
+        vsnprintf(name_ + n, sizeof(name_) - n, tag_fmt, ap);
+        va_end(ap);
+    }
     if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventRecord(e0_, stream_) != cudaSuccess) { on_ = false; }
 }
 KernelTimer::~KernelTimer() {

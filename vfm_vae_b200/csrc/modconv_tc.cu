@@ -129,28 +129,38 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
-constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_BYTES = BN * BK * 2;   // 16 KB
+constexpr int BN = 128, BK = 64, STAGES = 3;   // wgrad tile (M = 128 out channels, N = in channels)
 constexpr float kLoScale = 2048.f;     // the lo term of the fp16 split is stored scaled by 2^11
+
+// ------------------------------------------------------------------------------------------------ conv / data gradient
+// GEMM orientation: M = 128 *channels* (the weight tile is the UMMA A operand), N = NPIX *pixels* (the activation tile
+// is the UMMA B operand), so the accumulator in TMEM has one channel per lane and the tile's pixels along the columns.
+// An epilogue thread therefore owns one output channel and a run of consecutive pixels: per-channel coefficients
+// (demodulation, bias, layer scale) are registers, NCHW stores / residual loads are 16-byte vectors along W, and the
+// dstyles reduction of the data gradient is a private register sum -- no shuffles, no shared memory.
+constexpr int CH = 128;                // channels per tile (UMMA M)
+constexpr int W_BYTES = CH * BK * 2;   // weight tile per stage, 16 KB
+constexpr int kConvThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kTmemCols = 512;         // the whole tensor memory: one persistent CTA per SM
 
 struct TcPhase {
     int ntaps;
-    int dy[9], dx[9], tb[9];   // A coordinate offsets and the tap's slice index in the B tensor map
+    int dy[9], dx[9], tb[9];   // pixel-operand coordinate offsets and the tap's slice index in the weight tensor map
     int oy, ox;                // output offset of this phase
     int Hg, Wg;                // extent of the phase grid
 };
 
 struct TcArgs {
-    TcPhase ph[4];
+    TcPhase ph[4];             // PAIR: index 2*py + px
     int kchunks;
-    int tw, th, tn;            // M tile = tw x th pixels of tn consecutive samples (tw*th*tn == 128)
+    int tw, th, tn;            // pixel tile = tw x th pixels of tn consecutive samples (tw*th*tn == NPIX), all powers of two
+    int tw_sh, th_sh;          // log2(tw), log2(th)
     int tiles_w, tiles_h;      // tile grid (covers the largest phase)
     int N, Nout;
     int out_H, out_W, out_s;   // output tensor [N, Nout, out_H, out_W]; output coordinate = g*out_s + o{y,x}
     int out_pitch;             // row pitch of the output tensor in elements (>= out_W; planes are out_H*out_pitch apart)
-    int nphases;
-    int a_s;                   // A coordinate = g*a_s + d{y,x}  (2 for the strided gather of the transposed conv's backward)
+    int ngroups;               // phase groups an item belongs to: 1, or 2 (PAIR: py)
+    int a_s;                   // pixel coordinate = g*a_s + d{y,x}  (2 for the strided gather of the transposed conv's backward)
     void* out;
     const float* oscale;       // [N, Nout]
     const float* gscale_inv;   // device scalar multiplied into the result, or NULL
@@ -159,244 +169,374 @@ struct TcArgs {
     const void* aux;           // dgrad: x, same shape/dtype as out
     float* aux_sum;            // dgrad: [N, Nout] += sum_p aux * acc
     Epilogue ep;               // forward: optional fused bias/activation/residual
+    int vec_out, vec_side, vec_add;   // 16-byte vector access allowed on out / (aux | residual) / noise
 };
 
-// PRE: the epilogue warps prefetch their 128 per-pixel side inputs (x for the dstyles reduction, or the residual of the
-// fused layer epilogue) into registers while the MMAs run, so the epilogue never waits on HBM.
-template <class TOut, bool DGRAD, bool SPLIT, bool PRE>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                      const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, TcArgs p) {
-    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-    constexpr int TMEM_COLS = SPLIT ? 2 * BN : BN;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 8 consecutive elements <-> registers (16-byte vectors when `vec`, else predicated scalars; n = number of valid elements)
+template <class T> __device__ __forceinline__ void load8(const T* p, float* v, int n, bool vec);
+template <> __device__ __forceinline__ void load8<__half>(const __half* p, float* v, int n, bool vec) {
+    if (vec && n == 8) {
+        union { uint4 u; __half2 h[4]; } t;
+        t.u = __ldg((const uint4*)p);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const float2 f = __half22float2(t.h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i < n) ? __half2float(p[i]) : 0.f;
+    }
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* v, int n, bool vec) {
+    if (vec && n == 8) {
+        const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (i < n) ? p[i] : 0.f;
+    }
+}
+template <class T> __device__ __forceinline__ void store8(T* p, const float* v, int n, bool vec);
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float* v, int n, bool vec) {
+    if (vec && n == 8) {
+        union { uint4 u; __half2 h[4]; } t;
+#pragma unroll
+        for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *(uint4*)p = t.u;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (i < n) p[i] = __float2half_rn(v[i]);
+    }
+}
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* v, int n, bool vec) {
+    if (vec && n == 8) {
+        *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
+        *((float4*)p + 1) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (i < n) p[i] = v[i];
+    }
+}
+
+// Persistent kernel: one CTA per SM walks over work items (phase group fastest, then channel tile, then pixel tile, so
+// CTAs that share a pixel tile run at the same time).  The shared-memory ring (TMA -> MMA) keeps running across items;
+// the accumulators are double-buffered in TMEM (tfull / tempty barriers), so the epilogue of item i overlaps the MMAs of
+// item i+1 and the per-CTA setup (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM.
+//
+// PAIR (transposed conv, stride 2): an item computes the two horizontal sub-pixel phases (px = 0, 1) of one row parity
+// into two accumulators and the epilogue interleaves them, so the stores to the 2x-resolution output are contiguous.
+// SPLIT (fp32 tensors): two accumulators per phase (hi*hi and the cross terms), recombined in the epilogue.
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmP,
+                                                                  const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPlo, TcArgs p) {
+    constexpr int P_BYTES = NPIX * BK * 2;
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (W_BYTES + P_BYTES);
+    constexpr int NSTAGE = (192 * 1024) / STAGE_BYTES;
+    constexpr int NSUB = PAIR ? 2 : 1;                          // phases per item
+    constexpr int SUB_COLS = (SPLIT ? 2 : 1) * NPIX;            // TMEM columns of one phase
+    constexpr int ITEM_COLS = NSUB * SUB_COLS;
+    constexpr int NBUF = kTmemCols / ITEM_COLS;                 // accumulator buffers (1 = no overlap, only fp32 up-layers)
+    static_assert(NBUF >= 1 && NSTAGE >= 2, "tile configuration does not fit");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
-    uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-    float* s_scale = (float*)(tmem_slot + 2);    // [8][BN] (tn <= 8)
-    float* s_bias = s_scale + 8 * BN;            // [BN] fused-epilogue bias
-    float* s_gamma = s_bias + BN;                // [BN] fused-epilogue layer scale
+    uint64_t* full_bar = (uint64_t*)(smem + NSTAGE * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NSTAGE;
+    uint64_t* tfull_bar = empty_bar + NSTAGE;                   // [NBUF] accumulators ready
+    uint64_t* tempty_bar = tfull_bar + 2;                       // [NBUF] accumulators drained
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // phases vary fastest across CTAs so that the interleaved sub-pixel stores of one output tile meet in L2
-    const TcPhase& ph = p.ph[blockIdx.x % p.nphases];
-
-    // tile coordinates (in the phase grid)
-    int mt = blockIdx.x / p.nphases;
-    const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
-    const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
-    const int n0 = mt * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
-    const int o0 = blockIdx.y * BN;
-    if (h0 >= ph.Hg || w0 >= ph.Wg) return;      // tile outside this phase's grid (uniform for the CTA)
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmP);
+        if (SPLIT) { tma_prefetch_desc(&tmWlo); tma_prefetch_desc(&tmPlo); }
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
-    }
-    {
-        const float gs = p.gscale_inv ? *p.gscale_inv : 1.f;
-        for (int i = threadIdx.x; i < p.tn * BN; i += blockDim.x) {
-            int nl = i / BN, c = i - nl * BN;
-            int n = n0 + nl;
-            s_scale[i] = (n < p.N) ? p.oscale[(size_t)n * p.Nout + o0 + c] * gs : 0.f;
-        }
-        if (!DGRAD && p.ep.enable) {
-            for (int i = threadIdx.x; i < BN; i += blockDim.x) {
-                s_bias[i] = p.ep.bias ? to_acc(((const TOut*)p.ep.bias)[o0 + i]) : 0.f;
-                s_gamma[i] = p.ep.gamma ? p.ep.gamma[o0 + i] : 1.f;
-            }
-        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int iters = ph.ntaps * p.kchunks;
+
+    const int c_tiles = p.Nout / CH;
+    const int n_tiles = (p.N + p.tn - 1) / p.tn;
+    const int total_items = p.tiles_w * p.tiles_h * n_tiles * c_tiles * p.ngroups;
+
+    // item index -> coordinates; false for items that fall outside their phase grid (skipped by every role alike)
+    auto decode = [&](int t, int& grp, int& n0, int& h0, int& w0, int& c0) -> bool {
+        grp = t % p.ngroups; t /= p.ngroups;
+        c0 = (t % c_tiles) * CH; t /= c_tiles;
+        const int tile_w = t % p.tiles_w; t /= p.tiles_w;
+        const int tile_h = t % p.tiles_h; t /= p.tiles_h;
+        n0 = t * p.tn; h0 = tile_h * p.th; w0 = tile_w * p.tw;
+        const TcPhase& ph = p.ph[grp * NSUB];                  // PAIR: px = 0 has the larger (or equal) grid
+        return h0 < ph.Hg && w0 < ph.Wg;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            for (int it = 0; it < iters; it++) {
-                const int s = it % STAGES;
-                const uint32_t phs = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], phs ^ 1);
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                uint8_t* sa = smem + s * STAGE_BYTES;
-                const int cw = w0 * p.a_s + ph.dx[tap], chh = h0 * p.a_s + ph.dy[tap];
-                tma_load_4d(sa, &tmA, &full_bar[s], kc * BK, cw, chh, n0);
-                tma_load_3d(sa + A_BYTES, &tmB, &full_bar[s], kc * BK, o0, ph.tb[tap]);
-                if (SPLIT) {
-                    tma_load_4d(sa + A_BYTES + B_BYTES, &tmAlo, &full_bar[s], kc * BK, cw, chh, n0);
-                    tma_load_3d(sa + 2 * A_BYTES + B_BYTES, &tmBlo, &full_bar[s], kc * BK, o0, ph.tb[tap]);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                int grp, n0, h0, w0, c0;
+                if (!decode(t, grp, n0, h0, w0, c0)) continue;
+#pragma unroll 1
+                for (int sub = 0; sub < NSUB; sub++) {
+                    const TcPhase& ph = p.ph[grp * NSUB + sub];
+                    const int iters = ph.ntaps * p.kchunks;
+                    for (int k = 0; k < iters; k++, it++) {
+                        const int s = it % NSTAGE;
+                        const uint32_t par = (it / NSTAGE) & 1;
+                        mbar_wait(&empty_bar[s], par ^ 1);
+                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        const int tap = k / p.kchunks, kc = k - tap * p.kchunks;
+                        uint8_t* sw = smem + s * STAGE_BYTES;
+                        const int cw = w0 * p.a_s + ph.dx[tap], chh = h0 * p.a_s + ph.dy[tap];
+                        tma_load_3d(sw, &tmW, &full_bar[s], kc * BK, c0, ph.tb[tap]);
+                        tma_load_4d(sw + W_BYTES, &tmP, &full_bar[s], kc * BK, cw, chh, n0);
+                        if (SPLIT) {
+                            tma_load_3d(sw + W_BYTES + P_BYTES, &tmWlo, &full_bar[s], kc * BK, c0, ph.tb[tap]);
+                            tma_load_4d(sw + 2 * W_BYTES + P_BYTES, &tmPlo, &full_bar[s], kc * BK, cw, chh, n0);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN);
-            for (int it = 0; it < iters; it++) {
-                const int s = it % STAGES;
-                const uint32_t phs = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], phs);
+            constexpr uint32_t idesc = make_idesc_f16(CH, NPIX);
+            uint32_t it = 0, icount = 0;
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                int grp, n0, h0, w0, c0;
+                if (!decode(t, grp, n0, h0, w0, c0)) continue;
+                const uint32_t buf = icount % NBUF;
+                mbar_wait(&tempty_bar[buf], ((icount / NBUF) & 1) ^ 1);       // the epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t adesc = make_kmajor_sw128_desc(sa);
-                const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
-                const uint64_t adesc_lo = make_kmajor_sw128_desc(sa + A_BYTES + B_BYTES);
-                const uint64_t bdesc_lo = make_kmajor_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll 1
+                for (int sub = 0; sub < NSUB; sub++) {
+                    const int iters = p.ph[grp * NSUB + sub].ntaps * p.kchunks;
+                    const uint32_t acc = tmem_base + buf * ITEM_COLS + sub * SUB_COLS;
+                    for (int k = 0; k < iters; k++, it++) {
+                        const int s = it % NSTAGE;
+                        const uint32_t par = (it / NSTAGE) & 1;
+                        mbar_wait(&full_bar[s], par);
+                        tc_fence_after();
+                        const uint32_t sw = smem_u32(smem + s * STAGE_BYTES);
+                        const uint64_t wdesc = make_kmajor_sw128_desc(sw);
+                        const uint64_t pdesc = make_kmajor_sw128_desc(sw + W_BYTES);
+                        const uint64_t wdesc_lo = make_kmajor_sw128_desc(sw + W_BYTES + P_BYTES);
+                        const uint64_t pdesc_lo = make_kmajor_sw128_desc(sw + 2 * W_BYTES + P_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++) {
-                    // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
-                    const uint64_t ko = (uint64_t)(2 * k);
-                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-                    umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, first);
-                    if (SPLIT) {
-                        umma_f16(tmem_base + BN, adesc + ko, bdesc_lo + ko, idesc, first);
-                        umma_f16(tmem_base + BN, adesc_lo + ko, bdesc + ko, idesc, 1u);
+                        for (int kk = 0; kk < BK / 16; kk++) {
+                            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
+                            const uint64_t ko = (uint64_t)(2 * kk);
+                            const uint32_t accum = (k > 0 || kk > 0) ? 1u : 0u;
+                            umma_f16(acc, wdesc + ko, pdesc + ko, idesc, accum);
+                            if (SPLIT) {
+                                umma_f16(acc + NPIX, wdesc + ko, pdesc_lo + ko, idesc, accum);
+                                umma_f16(acc + NPIX, wdesc_lo + ko, pdesc + ko, idesc, 1u);
+                            }
+                        }
+                        umma_commit(&empty_bar[s]);       // frees this smem stage once the MMAs above have read it
                     }
                 }
-                umma_commit(&empty_bar[s]);     // frees this smem stage once the MMAs above have read it
+                umma_commit(&tfull_bar[buf]);             // accumulators complete
+                icount++;
             }
-            umma_commit(accum_bar);             // accumulator complete
         }
     } else {
-        // ------------------------------------------------------------------ epilogue warps (2..5)
-        const int lg = warp & 3;                           // TMEM lane group this warp may access
-        const int r = lg * 32 + lane;                      // accumulator row = pixel index inside the tile
-        const int nl = r / (p.tw * p.th);
-        const int hl = (r / p.tw) % p.th, wl = r % p.tw;
-        const int n = n0 + nl, gh = h0 + hl, gw = w0 + wl;
-        const int oy = gh * p.out_s + ph.oy, ox = gw * p.out_s + ph.ox;
-        const bool valid = (n < p.N) && (gh < ph.Hg) && (gw < ph.Wg) && (oy < p.out_H) && (ox < p.out_W);
-        const size_t HW = (size_t)p.out_H * p.out_pitch;
-        const size_t pix = (size_t)oy * p.out_pitch + ox;
-        float addv = 0.f;
-        if (!DGRAD && p.add && valid) addv = p.add[(size_t)n * p.add_sn + (size_t)oy * p.out_W + ox];
-        TOut* outp = (TOut*)p.out + ((size_t)n * p.Nout + o0) * HW + pix;
-        const TOut* auxp = DGRAD ? (const TOut*)p.aux + ((size_t)n * p.Nout + o0) * HW + pix : nullptr;
-        const float* sc = s_scale + nl * BN;
-        const bool warp_one_sample = (p.tw * p.th >= 32);
-        const float gsv = (DGRAD && p.gscale_inv) ? *p.gscale_inv : 1.f;    // undoes the global power-of-two scale of A
+        // ------------------------------------------------------------------ epilogue warps (2..9)
+        const int lg = warp & 3;                           // TMEM lane group this warp may access (warp id % 4)
+        const int chalf = (warp - 2) >> 2;                 // which half of the tile's pixel columns
+        const float gsv = p.gscale_inv ? *p.gscale_inv : 1.f;    // undoes the global power-of-two scale of the operand
+        const size_t HW = (size_t)p.out_H * p.out_pitch;   // plane pitch of out (and of aux, same tensor shape)
+        const size_t HWd = (size_t)p.out_H * p.out_W;      // dense plane (residual)
+        const bool ep_on = !DGRAD && p.ep.enable;
+        const bool has_res = ep_on && p.ep.residual != nullptr;
+        const bool do_ds = DGRAD && p.aux_sum != nullptr;
+        const int tile_hw_sh = p.tw_sh + p.th_sh;
+        uint32_t icount = 0;
 
-        // side input of the epilogue: x (dgrad, NCHW like the output) or the residual (fused forward, dense NCHW)
-        constexpr bool HALF = (sizeof(TOut) == 2);
-        constexpr int NPRE = PRE ? (HALF ? BN / 2 : BN) : 1;
-        uint32_t pre[NPRE];
-        bool have_side = false;
-        if (PRE) {
-            const size_t HWd = (size_t)p.out_H * p.out_W;
-            const TOut* side = DGRAD ? (p.aux_sum ? auxp : nullptr)
-                                     : (p.ep.residual ? (const TOut*)p.ep.residual + ((size_t)n * p.Nout + o0) * HWd + (size_t)oy * p.out_W + ox : nullptr);
-            const size_t cstride = DGRAD ? HW : HWd;
-            have_side = (side != nullptr);
-            if (have_side && valid) {
+        for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+            int grp, n0, h0, w0, c0;
+            if (!decode(t, grp, n0, h0, w0, c0)) continue;
+            const TcPhase& ph0 = p.ph[grp * NSUB];
+            const int ch = c0 + lg * 32 + lane;
+            // per-channel coefficients of this item
+            float bias = 0.f, gam = 1.f;
+            if (ep_on) {
+                if (p.ep.bias) bias = to_acc(((const TOut*)p.ep.bias)[ch]);
+                if (has_res) gam = p.ep.gamma[ch] * p.ep.res_scale;
+            }
+            int cur_n = -1;
+            float scale = 0.f, ds_acc = 0.f;
+
+            const uint32_t buf = icount % NBUF;
+            mbar_wait(&tfull_bar[buf], (icount / NBUF) & 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + buf * ITEM_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(chalf * (NPIX / 2));
+
+            constexpr int NLD = NSUB * (SPLIT ? 2 : 1);    // TMEM loads per 16-column step
+            constexpr int NIT = NPIX / 32;                 // 16-column steps of this warp
+            uint32_t raw[2][NLD][16];
+            auto issue = [&](int step, int slot) {
 #pragma unroll
-                for (int c = 0; c < BN; c += 2) {
-                    if (HALF) {
-                        const unsigned short lo = *(const unsigned short*)(side + (size_t)c * cstride);
-                        const unsigned short hi = *(const unsigned short*)(side + (size_t)(c + 1) * cstride);
-                        pre[c / 2] = (uint32_t)lo | ((uint32_t)hi << 16);
+                for (int sub = 0; sub < NSUB; sub++) {
+                    tmem_ld16_nowait(acc + sub * SUB_COLS + step * 16, raw[slot][sub * (SPLIT ? 2 : 1)]);
+                    if (SPLIT) tmem_ld16_nowait(acc + sub * SUB_COLS + NPIX + step * 16, raw[slot][sub * 2 + 1]);
+                }
+            };
+            issue(0, 0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int step = 0; step < NIT; step++) {
+                const int slot = step & 1;
+                if (step + 1 < NIT) issue(step + 1, slot ^ 1);     // in flight while this step is processed
+                // one run of up to `maxn` (<= 8) consecutive pixels of one image row: tile columns j0 .. j0+maxn-1, whose
+                // accumulator values are raw[slot][..][r0 ..]
+                auto chunk = [&](const int j0, const int r0, const int maxn) {
+                    const int w_l = j0 & (p.tw - 1);
+                    const int h_l = (j0 >> p.tw_sh) & (p.th - 1);
+                    const int n = n0 + (j0 >> tile_hw_sh);
+                    const int gh = h0 + h_l, gw0 = w0 + w_l;
+                    if (n != cur_n) {
+                        if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
+                        ds_acc = 0.f;
+                        cur_n = n;
+                        scale = (n < p.N) ? p.oscale[(size_t)n * p.Nout + ch] * gsv : 0.f;
+                    }
+                    if (n >= p.N || gh >= ph0.Hg) return;
+                    const int oy = gh * p.out_s + ph0.oy;
+                    if (oy >= p.out_H) return;
+                    const bool full8 = (maxn == 8);
+                    // values of the chunk: v[sub][i] = pixel gw0+i of phase `sub`
+                    float v[NSUB][8];
+#pragma unroll
+                    for (int sub = 0; sub < NSUB; sub++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            float a = 0.f;
+                            if (r0 + i < 16) {
+                                a = __uint_as_float(raw[slot][sub * (SPLIT ? 2 : 1)][(r0 + i) & 15]);
+                                if (SPLIT) a += __uint_as_float(raw[slot][sub * 2 + 1][(r0 + i) & 15]) * (1.f / kLoScale);
+                            }
+                            v[sub][i] = a;
+                        }
+                    const size_t plane = (size_t)n * p.Nout + ch;
+                    if (PAIR) {
+                        // interleave the two horizontal phases: output pixels 2*gw0 .. 2*gw0 + 2*maxn - 1
+                        float o[16];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { o[2 * i] = v[0][i] * scale; o[2 * i + 1] = v[NSUB - 1][i] * scale; }
+                        const int ox0 = gw0 * 2;
+                        int nv = p.out_W - ox0; nv = nv > 2 * maxn ? 2 * maxn : nv;
+                        const int nw = (ph0.Wg - gw0) * 2;                 // columns this tile may write (its px = 0 grid)
+                        nv = nv > nw ? nw : nv;
+                        if (nv <= 0) return;
+                        TOut* outp = (TOut*)p.out + plane * HW + (size_t)oy * p.out_pitch + ox0;
+                        const bool vec = p.vec_out && full8;
+                        store8<TOut>(outp, o, nv > 8 ? 8 : nv, vec);
+                        if (nv > 8) store8<TOut>(outp + 8, o + 8, nv - 8, vec);
                     } else {
-                        pre[c] = *(const uint32_t*)(side + (size_t)c * cstride);
-                        pre[c + 1] = *(const uint32_t*)(side + (size_t)(c + 1) * cstride);
+                        int nv = ph0.Wg - gw0; nv = nv > maxn ? maxn : nv;
+                        const int ox0 = gw0 * p.out_s + ph0.ox;
+                        if (p.out_s != 1) {
+                            // strided output without pairing (not used by the decoder): scalar stores
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const int ox = ox0 + i * p.out_s;
+                                if (i < nv && ox < p.out_W) ((TOut*)p.out)[plane * HW + (size_t)oy * p.out_pitch + ox] = from_acc<TOut, float>(v[0][i] * scale);
+                            }
+                            return;
+                        }
+                        { const int lim = p.out_W - ox0; nv = nv > lim ? lim : nv; }
+                        if (nv <= 0) return;
+                        const size_t off = plane * HW + (size_t)oy * p.out_pitch + ox0;
+                        float* o = v[0];
+                        if (DGRAD) {
+                            if (do_ds) {
+                                float xs[8];
+                                load8<TOut>((const TOut*)p.aux + off, xs, nv, p.vec_side && full8);
+#pragma unroll
+                                for (int i = 0; i < 8; i++) ds_acc = fmaf(xs[i], o[i], ds_acc);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++) o[i] *= scale;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) o[i] = fmaf(o[i], scale, bias);
+                            if (p.add) {
+                                float nz[8];
+                                load8<float>(p.add + (size_t)n * p.add_sn + (size_t)oy * p.out_W + ox0, nz, nv, p.vec_add && full8);
+#pragma unroll
+                                for (int i = 0; i < 8; i++) o[i] += nz[i];
+                            }
+                            if (ep_on) {
+                                if (p.ep.act == 3) {
+                                    const float gp = p.ep.gain, gn = p.ep.gain * p.ep.alpha;
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) o[i] *= (o[i] > 0.f) ? gp : gn;
+                                } else if (p.ep.gain != 1.f) {
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) o[i] *= p.ep.gain;
+                                }
+                                if (p.ep.clamp >= 0.f) {
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) o[i] = fminf(fmaxf(o[i], -p.ep.clamp), p.ep.clamp);
+                                }
+                                if (has_res) {
+                                    float rs[8];
+                                    load8<TOut>((const TOut*)p.ep.residual + plane * HWd + (size_t)oy * p.out_W + ox0, rs, nv, p.vec_side && full8);
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) o[i] = fmaf(rs[i], p.ep.res_scale, o[i] * gam);
+                                }
+                            }
+                        }
+                        store8<TOut>((TOut*)p.out + off, o, nv, p.vec_out && full8);
                     }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < NPRE; c++) pre[c] = 0u;
-            }
-        }
-        auto side_val = [&](int col) -> float {
-            if (HALF) return __half2float(__ushort_as_half((unsigned short)(pre[col >> 1] >> ((col & 1) * 16))));
-            return __uint_as_float(pre[col]);
-        };
-
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        auto process = [&](int j) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 16), v);
-            if (SPLIT) {
-                float v1[16];
-                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + j * 16), v1);
-#pragma unroll
-                for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
-            }
-            if (DGRAD && p.aux_sum) {
-                // dstyles partial: sum over the tile's pixels of x * dxpre, 16 columns at a time
-                float part[16];
-#pragma unroll
-                for (int c = 0; c < 16; c++) part[c] = (PRE ? side_val(j * 16 + c) : 0.f) * (v[c] * gsv);
-                if (warp_one_sample) {
-                    // butterfly transpose-reduce over the 32 lanes: 16 shuffles for 16 columns (instead of 5 per column);
-                    // afterwards lane l (l even) holds the warp total of column (l >> 1)
-                    float a8[8], a4[4], a2[2], a1;
-                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const float send = b16 ? part[c] : part[c + 8], keep = b16 ? part[c + 8] : part[c];
-                        a8[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const float send = b8 ? a8[c] : a8[c + 4], keep = b8 ? a8[c + 4] : a8[c];
-                        a4[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const float send = b4 ? a4[c] : a4[c + 2], keep = b4 ? a4[c + 2] : a4[c];
-                        a2[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    {
-                        const float send = b2 ? a2[0] : a2[1], keep = b2 ? a2[1] : a2[0];
-                        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-                    const int n_w = __shfl_sync(0xffffffffu, n, 0);      // the warp's sample (all lanes share it)
-                    if ((lane & 1) == 0 && n_w < p.N) atomicAdd(&p.aux_sum[(size_t)n_w * p.Nout + o0 + j * 16 + (lane >> 1)], a1);
-                } else if (valid) {
-#pragma unroll
-                    for (int c = 0; c < 16; c++) atomicAdd(&p.aux_sum[(size_t)n * p.Nout + o0 + j * 16 + c], part[c]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 16; c++) {
-                const int col = j * 16 + c;
-                float val = v[c] * sc[col] + addv;
-                if (!DGRAD && p.ep.enable) {
-                    val += s_bias[col];
-                    if (p.ep.act == 3) val = (val > 0.f) ? val : val * p.ep.alpha;
-                    val *= p.ep.gain;
-                    if (p.ep.clamp >= 0.f) val = fminf(fmaxf(val, -p.ep.clamp), p.ep.clamp);
-                    if (PRE && have_side) val = (s_gamma[col] * val + side_val(col)) * p.ep.res_scale;
-                }
-                if (valid) outp[(size_t)col * HW] = from_acc<TOut, float>(val);
-            }
                 };
-        if (PRE) {
-            // side inputs live in registers indexed by column: the column loop must be fully unrolled
-#pragma unroll
-            for (int j = 0; j < BN / 16; j++) process(j);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < BN / 16; j++) process(j);
+                const int jbase = chalf * (NPIX / 2) + step * 16;
+                if (p.tw >= 8) {
+                    chunk(jbase, 0, 8);
+                    chunk(jbase + 8, 8, 8);
+                } else {                       // 4-pixel rows (images narrower than 8 pixels)
+                    chunk(jbase, 0, 4);
+                    chunk(jbase + 4, 4, 4);
+                    chunk(jbase + 8, 8, 4);
+                    chunk(jbase + 12, 12, 4);
+                }
+                if (step + 1 < NIT) tmem_ld_wait();
+            }
+            if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
+            // all tcgen05.ld of this warp have completed: hand the accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+            icount++;
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -716,26 +856,36 @@ int encode_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, con
     return VFM_OK;
 }
 
-// M tile shape with the least padding waste for a Hg x Wg grid (tw*th*tn == 128)
-void pick_tile(int Hg, int Wg, int& tw, int& th, int& tn) {
-    const int cand[][3] = {{32, 4, 1}, {16, 8, 1}, {8, 16, 1}, {8, 8, 2}, {4, 8, 4}, {4, 4, 8}};
+// Pixel tile (tw x th pixels of tn samples, tw*th*tn == npix, powers of two) with the least padding waste for a Hg x Wg
+// grid.  Wide tiles are preferred on ties (longer contiguous runs per epilogue thread); multi-sample tiles only when one
+// image is smaller than the tile.  `a_s` is the element stride of the TMA box (box extents are limited to 256).
+void pick_tile(int Hg, int Wg, int npix, int a_s, int& tw, int& th, int& tn) {
     double best = 1e30;
-    for (auto& c : cand) {
-        double cover = (double)ceil_div(Wg, c[0]) * c[0] * ceil_div(Hg, c[1]) * c[1];
-        double waste = cover / ((double)Wg * Hg) * (c[2] > 1 && Hg * Wg > c[0] * c[1] ? 4.0 : 1.0);   // multi-sample tiles only for tiny images
-        if (waste < best - 1e-9) { best = waste; tw = c[0]; th = c[1]; tn = c[2]; }
+    for (int w = 256; w >= 4; w >>= 1) {
+        for (int n = 1; n <= npix / w; n <<= 1) {
+            const int h = npix / (w * n);
+            if (h < 1 || w * h * n != npix) continue;
+            if (w * a_s > 256 || h * a_s > 256 || n > 256) continue;
+            if (w < 8 && Wg >= 8) continue;
+            const double cover = (double)ceil_div(Wg, w) * w * ceil_div(Hg, h) * h;
+            const double waste = cover / ((double)Wg * Hg) * (n > 1 && Hg * Wg > w * h ? 4.0 : 1.0);
+            if (waste < best - 1e-9) { best = waste; tw = w; th = h; tn = n; }
+        }
     }
 }
+int ilog2(int v) { int r = 0; while ((1 << r) < v) r++; return r; }
 
-size_t smem_bytes(bool split) { return (size_t)STAGES * (split ? 2 : 1) * (A_BYTES + B_BYTES) + 1024 + 256 + (size_t)10 * BN * sizeof(float); }
+size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 256; }
 
-template <class TOut, bool DGRAD, bool SPLIT, bool PRE>
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX>
 int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PRE>;
-    size_t smem = smem_bytes(SPLIT);
+    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PAIR, NPIX>;
+    size_t smem = smem_bytes();
     VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0);
-    kern<<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0,
+                      "i%do%dh%d%s%s%s", a.kchunks * BK, a.Nout, a.out_H, PAIR ? "p" : "", (!DGRAD && a.ep.enable) ? "e" : "",
+                      (DGRAD ? a.aux_sum != nullptr : (a.ep.enable && a.ep.residual)) ? "r" : "");
+    kern<<<grid, kConvThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     return launch_status("modconv conv_tc_kernel");
 }
 
@@ -746,40 +896,54 @@ struct TcOperands {
 };
 
 // One implicit-GEMM conv.  `args` must have ph[], out*, a_s, scales, add/aux already filled in; this sets the tiling.
+// nphases == 4: the phases are the sub-pixel phases of a stride-2 transposed conv in the order 2*py + px (PAIR kernel).
 int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream) {
+    const bool pair = (nphases == 4);
+    if (nphases != 1 && nphases != 4) { set_error("tcgen05 conv: unsupported phase structure"); return VFM_ERR_INVALID; }
+    if (pair && (dgrad || a.ep.enable || a.add)) { set_error("tcgen05 conv: the paired-phase kernel has no fused epilogue"); return VFM_ERR_INVALID; }
+    const int npix = (!f32 && !pair) ? 256 : 128;
     int Hg = 0, Wg = 0;
     double taps_px = 0;
     for (int i = 0; i < nphases; i++) { Hg = max(Hg, a.ph[i].Hg); Wg = max(Wg, a.ph[i].Wg); taps_px += (double)a.ph[i].ntaps * a.ph[i].Hg * a.ph[i].Wg; }
-    pick_tile(Hg, Wg, a.tw, a.th, a.tn);
+    pick_tile(Hg, Wg, npix, a.a_s, a.tw, a.th, a.tn);
+    a.tw_sh = ilog2(a.tw); a.th_sh = ilog2(a.th);
     a.tiles_w = ceil_div(Wg, a.tw); a.tiles_h = ceil_div(Hg, a.th);
     a.kchunks = op.Cin / BK;
     a.N = op.N; a.Nout = op.Nout;
+    a.ngroups = pair ? 2 : 1;
+    // 16-byte vector access: every 8-pixel chunk starts at a multiple of 8 pixels of a row, rows and planes must keep that alignment
+    const int es = f32 ? 4 : 2, va = 16 / es;
+    a.vec_out = aligned16(a.out) && a.out_pitch % va == 0 && a.tw >= 8;
+    const void* side = dgrad ? a.aux : a.ep.residual;
+    a.vec_side = side && aligned16(side) && (dgrad ? a.out_pitch : a.out_W) % va == 0 && a.tw >= 8;
+    a.vec_add = a.add && aligned16(a.add) && a.out_W % 4 == 0 && (a.add_sn % 4) == 0 && a.tw >= 8;
     CUtensorMap maps[4];
-    uint64_t adims[4] = {(uint64_t)op.Cin, (uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.N};
-    uint32_t abox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)(a.th * a.a_s), (uint32_t)a.tn};
-    uint32_t astr[4] = {1u, (uint32_t)a.a_s, (uint32_t)a.a_s, 1u};
-    uint64_t bdims[3] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps};
-    uint32_t bbox[3] = {(uint32_t)BK, (uint32_t)BN, 1u};
-    int st = encode_map(&maps[0], op.act, 4, adims, abox, astr); if (st) return st;
-    st = encode_map(&maps[1], op.wt, 3, bdims, bbox, nullptr); if (st) return st;
-    st = encode_map(&maps[2], f32 ? op.act_lo : op.act, 4, adims, abox, astr); if (st) return st;
-    st = encode_map(&maps[3], f32 ? op.wt_lo : op.wt, 3, bdims, bbox, nullptr); if (st) return st;
-    a.nphases = nphases;
-    dim3 grid(a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn) * nphases, op.Nout / BN, 1);
+    uint64_t pdims[4] = {(uint64_t)op.Cin, (uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.N};
+    uint32_t pbox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)(a.th * a.a_s), (uint32_t)a.tn};
+    uint32_t pstr[4] = {1u, (uint32_t)a.a_s, (uint32_t)a.a_s, 1u};
+    uint64_t wdims[3] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps};
+    uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)CH, 1u};
+    int st = encode_map(&maps[0], op.wt, 3, wdims, wbox, nullptr); if (st) return st;
+    st = encode_map(&maps[1], op.act, 4, pdims, pbox, pstr); if (st) return st;
+    st = encode_map(&maps[2], f32 ? op.wt_lo : op.wt, 3, wdims, wbox, nullptr); if (st) return st;
+    st = encode_map(&maps[3], f32 ? op.act_lo : op.act, 4, pdims, pbox, pstr); if (st) return st;
+    const long long total_items = (long long)a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn) * a.ngroups * (op.Nout / CH);
+    dim3 grid((unsigned)(total_items < kNumSMs ? total_items : kNumSMs), 1, 1);      // persistent: one CTA per SM
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
-    const bool pre = dgrad ? (a.aux_sum != nullptr) : (a.ep.enable && a.ep.residual != nullptr);
     if (!f32) {
-        if (dgrad) return pre ? launch_tc<__half, true, false, true>(maps, a, grid, flops, stream) : launch_tc<__half, true, false, false>(maps, a, grid, flops, stream);
-        return pre ? launch_tc<__half, false, false, true>(maps, a, grid, flops, stream) : launch_tc<__half, false, false, false>(maps, a, grid, flops, stream);
+        if (dgrad) return launch_tc<__half, true, false, false, 256>(maps, a, grid, flops, stream);
+        if (pair) return launch_tc<__half, false, false, true, 128>(maps, a, grid, flops, stream);
+        return launch_tc<__half, false, false, false, 256>(maps, a, grid, flops, stream);
     }
-    if (dgrad) return pre ? launch_tc<float, true, true, true>(maps, a, grid, flops, stream) : launch_tc<float, true, true, false>(maps, a, grid, flops, stream);
-    return pre ? launch_tc<float, false, true, true>(maps, a, grid, flops, stream) : launch_tc<float, false, true, false>(maps, a, grid, flops, stream);
+    if (dgrad) return launch_tc<float, true, true, false, 128>(maps, a, grid, flops, stream);
+    if (pair) return launch_tc<float, false, true, true, 128>(maps, a, grid, flops, stream);
+    return launch_tc<float, false, true, false, 128>(maps, a, grid, flops, stream);
 }
 
 int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream) {
     dim3 grid(ceil_div(HW, 64), ceil_div(C, 64), N);
     if (grid.z > 65535 || grid.y > 65535) { set_error("tcgen05 path: batch too large"); return VFM_ERR_INVALID; }
-    KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * ((dtype == VFM_F16 ? 2 : 4) + (split ? 4 : 2)));
+    KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * ((dtype == VFM_F16 ? 2 : 4) + (split ? 4 : 2)), "c%dhw%d", C, HW);
     if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, gscale, xt, xt_lo, C, HW);
     else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
     else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
@@ -866,7 +1030,7 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     if (grid.z > 65535) { set_error("tcgen05 wgrad: grid too large"); return VFM_ERR_INVALID; }
     const size_t smem = (size_t)STAGES * (f32 ? 2 : 1) * 2 * WOP_BYTES + 1024 + 256;
     const double flops = 2.0 * N * d.in_h * d.in_w * (double)O * I * a.ntaps;
-    KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0);
+    KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0, "i%do%dh%ds%d", I, O, d.in_h, s.sd);
     if (f32) {
         VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         wgrad_tc_kernel<true><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
@@ -921,7 +1085,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     } else {
         for (int pa = 0; pa < 2; pa++)
             for (int pb = 0; pb < 2; pb++) {
-                TcPhase& ph = a.ph[nph];
+                TcPhase& ph = a.ph[nph];            // index 2*py + px: what the paired-phase kernel expects
                 ph.ntaps = 0;
                 for (int t = 0; t < s.taps.ntaps; t++) {
                     int ny = pa + s.taps.off_y[t], nx = pb + s.taps.off_x[t];
@@ -930,7 +1094,8 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
                     ph.ntaps++;
                 }
                 ph.oy = pa; ph.ox = pb; ph.Hg = (s.zh - pa + 1) / 2; ph.Wg = (s.zw - pb + 1) / 2;
-                if (ph.ntaps > 0 && ph.Hg > 0 && ph.Wg > 0) nph++;
+                if (ph.ntaps == 0 || ph.Hg <= 0 || ph.Wg <= 0) { set_error("modulated_conv2d: degenerate sub-pixel phase"); return VFM_ERR_NO_KERNEL; }
+                nph++;
             }
         a.out_s = 2;
     }

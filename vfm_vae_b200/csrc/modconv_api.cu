@@ -69,7 +69,7 @@ static size_t generic_workspace(const vfm_modconv_desc& d, int direction) {
     Carver cv(nullptr, ~(size_t)0);
     Coefs k; carve_coefs(cv, d, k);
     Stage1 s = make_stage1(d);
-    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 7) & ~7) * esize(d.dtype));
+    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 15) & ~15) * esize(d.dtype));
     if (direction == 1) { cv.take<float>((size_t)d.batch * d.out_channels); cv.take<float>((size_t)d.batch * d.in_channels); }
     return cv.off + 256;
 }
@@ -118,9 +118,9 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     k.d = p->dcoefs;
     Stage1 s = make_stage1(d);
     void* z = p->y;
-    // stage-1 output rows are padded to 16 bytes on the tensor-core path so that the blur stages its tiles with vector loads
-    const int zpitch = (d.up == 2 && use_tc(d)) ? ((s.zw + 7) & ~7) : s.zw;
-    if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 7) & ~7) * esize(d.dtype));
+    // stage-1 output rows are padded to 32 bytes on the tensor-core path so that the blur stages its tiles with vector loads
+    const int zpitch = (d.up == 2 && use_tc(d)) ? ((s.zw + 15) & ~15) : s.zw;
+    if (d.up == 2) z = cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 15) & ~15) * esize(d.dtype));
     st = compute_coefs(d, p->weight, p->styles, k, p->dcoefs, nullptr, stream); if (st) return st;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)d.out_h * d.out_w : 0;
     const float* s1_noise = (d.up == 1) ? p->noise : nullptr;

@@ -26,6 +26,7 @@
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 namespace vfm {
 namespace modconv {
@@ -184,47 +185,63 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 8 consecutive elements <-> registers (16-byte vectors when `vec`, else predicated scalars; n = number of valid elements)
-template <class T> __device__ __forceinline__ void load8(const T* p, float* v, int n, bool vec);
-template <> __device__ __forceinline__ void load8<__half>(const __half* p, float* v, int n, bool vec) {
-    if (vec && n == 8) {
-        union { uint4 u; __half2 h[4]; } t;
-        t.u = __ldg((const uint4*)p);
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// 16 consecutive elements: raw 32-bit words (8 for fp16, 16 for fp32) -> floats
+template <class T> struct Raw16 { static constexpr int W = (sizeof(T) == 2) ? 8 : 16; };
+template <class T> __device__ __forceinline__ void raw16_load(const T* p, uint32_t* r) {
+    ldg256(p, r);
+    if (sizeof(T) == 4) ldg256((const char*)p + 32, r + 8);
+}
+template <class T> __device__ __forceinline__ void raw16_unpack(const uint32_t* r, float* v);
+template <> __device__ __forceinline__ void raw16_unpack<__half>(const uint32_t* r, float* v) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const float2 f = __half22float2(t.h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    for (int i = 0; i < 8; i++) { const float2 f = __half22float2(*(const __half2*)&r[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void raw16_unpack<float>(const uint32_t* r, float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// n = number of valid elements; vec = all 16 valid and 32-byte aligned
+template <class T> __device__ __forceinline__ void load16(const T* p, float* v, int n, bool vec) {
+    if (vec && n == 16) {
+        uint32_t r[Raw16<T>::W];
+        raw16_load<T>(p, r);
+        raw16_unpack<T>(r, v);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (i < n) ? __half2float(p[i]) : 0.f;
+        for (int i = 0; i < 16; i++) v[i] = (i < n) ? to_acc(p[i]) : 0.f;
     }
 }
-template <> __device__ __forceinline__ void load8<float>(const float* p, float* v, int n, bool vec) {
-    if (vec && n == 8) {
-        const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+template <class T> __device__ __forceinline__ void store16(T* p, const float* v, int n, bool vec);
+template <> __device__ __forceinline__ void store16<__half>(__half* p, const float* v, int n, bool vec) {
+    if (vec && n == 16) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); r[i] = *(const uint32_t*)&h; }
+        stg256(p, r);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = (i < n) ? p[i] : 0.f;
+        for (int i = 0; i < 16; i++) if (i < n) p[i] = __float2half_rn(v[i]);
     }
 }
-template <class T> __device__ __forceinline__ void store8(T* p, const float* v, int n, bool vec);
-template <> __device__ __forceinline__ void store8<__half>(__half* p, const float* v, int n, bool vec) {
-    if (vec && n == 8) {
-        union { uint4 u; __half2 h[4]; } t;
+template <> __device__ __forceinline__ void store16<float>(float* p, const float* v, int n, bool vec) {
+    if (vec && n == 16) {
+        uint32_t r[16];
 #pragma unroll
-        for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        *(uint4*)p = t.u;
+        for (int i = 0; i < 16; i++) r[i] = __float_as_uint(v[i]);
+        stg256(p, r);
+        stg256(p + 8, r + 8);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (i < n) p[i] = __float2half_rn(v[i]);
-    }
-}
-template <> __device__ __forceinline__ void store8<float>(float* p, const float* v, int n, bool vec) {
-    if (vec && n == 8) {
-        *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
-        *((float4*)p + 1) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) if (i < n) p[i] = v[i];
+        for (int i = 0; i < 16; i++) if (i < n) p[i] = v[i];
     }
 }
 
@@ -254,6 +271,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     uint64_t* tfull_bar = empty_bar + NSTAGE;                   // [NBUF] accumulators ready
     uint64_t* tempty_bar = tfull_bar + 2;                       // [NBUF] accumulators drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* s_noise = (float*)(tmem_slot + 4);                   // [2][NPIX] noise of the current / next item's pixels
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -365,166 +383,250 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         // ------------------------------------------------------------------ epilogue warps (2..9)
         const int lg = warp & 3;                           // TMEM lane group this warp may access (warp id % 4)
         const int chalf = (warp - 2) >> 2;                 // which half of the tile's pixel columns
+        const int et = threadIdx.x - 64;                   // 0..255 among the epilogue threads
         const float gsv = p.gscale_inv ? *p.gscale_inv : 1.f;    // undoes the global power-of-two scale of the operand
         const size_t HW = (size_t)p.out_H * p.out_pitch;   // plane pitch of out (and of aux, same tensor shape)
         const size_t HWd = (size_t)p.out_H * p.out_W;      // dense plane (residual)
         const bool ep_on = !DGRAD && p.ep.enable;
         const bool has_res = ep_on && p.ep.residual != nullptr;
+        const bool has_add = !DGRAD && p.add != nullptr;
         const bool do_ds = DGRAD && p.aux_sum != nullptr;
+        const bool wide = p.tw >= 16;                      // every 16-column step lies inside one image row
+        const TOut* side_base = DGRAD ? (do_ds ? (const TOut*)p.aux : nullptr) : (has_res ? (const TOut*)p.ep.residual : nullptr);
+        const size_t side_plane = DGRAD ? HW : HWd;
+        const int side_pitch = DGRAD ? p.out_pitch : p.out_W;
         const int tile_hw_sh = p.tw_sh + p.th_sh;
+        constexpr int NIT = NPIX / 32;                     // 16-column steps (= 16-pixel chunks) of this warp
+        constexpr int RW = Raw16<TOut>::W;                 // 32-bit words of 16 elements
+        constexpr bool PRE = !PAIR;                        // side inputs exist only without pairing
         uint32_t icount = 0;
+
+        // tile column -> image coordinates
+        auto locate = [&](int j, int n0, int h0, int w0, int& n, int& gh, int& gw) {
+            gw = w0 + (j & (p.tw - 1));
+            gh = h0 + ((j >> p.tw_sh) & (p.th - 1));
+            n = n0 + (j >> tile_hw_sh);
+        };
 
         for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
             int grp, n0, h0, w0, c0;
             if (!decode(t, grp, n0, h0, w0, c0)) continue;
             const TcPhase& ph0 = p.ph[grp * NSUB];
             const int ch = c0 + lg * 32 + lane;
-            // per-channel coefficients of this item
+            const uint32_t buf = icount % NBUF;
+            float* nz_tile = s_noise + (icount & 1) * NPIX;
+
+            // ---- everything that does not depend on the accumulators is fetched while the MMAs of this item still run ----
+            if (has_add) {
+                // noise of the tile's pixels: one pixel per thread -> shared memory (double-buffered by item parity)
+                if (et < NPIX) {
+                    int n, gh, gw;
+                    locate(et, n0, h0, w0, n, gh, gw);
+                    const int oy = gh * p.out_s + ph0.oy, ox = gw * p.out_s + ph0.ox;
+                    float v = 0.f;
+                    if (n < p.N && gh < ph0.Hg && gw < ph0.Wg && oy < p.out_H && ox < p.out_W) v = __ldg(p.add + (size_t)n * p.add_sn + (size_t)oy * p.out_W + ox);
+                    nz_tile[et] = v;
+                }
+            }
             float bias = 0.f, gam = 1.f;
             if (ep_on) {
                 if (p.ep.bias) bias = to_acc(((const TOut*)p.ep.bias)[ch]);
                 if (has_res) gam = p.ep.gamma[ch] * p.ep.res_scale;
             }
+            // side input (x of the dstyles reduction / residual of the fused layer): this thread's 16-pixel chunks, prefetched
+            uint32_t pre[PRE ? NIT * RW : 1];
+            uint32_t pre_ok = 0;
+            if (PRE && side_base && wide && p.vec_side) {
+#pragma unroll
+                for (int c = 0; c < NIT; c++) {
+                    int n, gh, gw;
+                    locate(chalf * (NPIX / 2) + c * 16, n0, h0, w0, n, gh, gw);
+                    const bool ok = n < p.N && gh < ph0.Hg && gw + 16 <= ph0.Wg && gw + 16 <= p.out_W && gh < p.out_H;
+                    if (ok) {
+                        raw16_load<TOut>(side_base + ((size_t)n * p.Nout + ch) * side_plane + (size_t)gh * side_pitch + gw, &pre[c * RW]);
+                        pre_ok |= 1u << c;
+                    }
+                }
+            }
+            if (has_add) asm volatile("bar.sync 1, 256;" ::: "memory");
+
             int cur_n = -1;
             float scale = 0.f, ds_acc = 0.f;
+            auto set_sample = [&](int n) {
+                if (n == cur_n) return;
+                if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
+                ds_acc = 0.f;
+                cur_n = n;
+                scale = (n >= 0 && n < p.N) ? p.oscale[(size_t)n * p.Nout + ch] * gsv : 0.f;
+            };
+            set_sample(n0);
 
-            const uint32_t buf = icount % NBUF;
             mbar_wait(&tfull_bar[buf], (icount / NBUF) & 1);
             tc_fence_after();
             const uint32_t acc = tmem_base + buf * ITEM_COLS + ((uint32_t)(lg * 32) << 16) + (uint32_t)(chalf * (NPIX / 2));
-
             constexpr int NLD = NSUB * (SPLIT ? 2 : 1);    // TMEM loads per 16-column step
-            constexpr int NIT = NPIX / 32;                 // 16-column steps of this warp
-            uint32_t raw[2][NLD][16];
-            auto issue = [&](int step, int slot) {
+
+            // forward epilogue of NV values in place: (+bias) + noise -> activation -> clamp -> layer-scaled residual
+            auto finish_fwd = [&](float* o, const float* nz, const float* rs, auto nv_tag) {
+                constexpr int NV = decltype(nv_tag)::value;
 #pragma unroll
-                for (int sub = 0; sub < NSUB; sub++) {
-                    tmem_ld16_nowait(acc + sub * SUB_COLS + step * 16, raw[slot][sub * (SPLIT ? 2 : 1)]);
-                    if (SPLIT) tmem_ld16_nowait(acc + sub * SUB_COLS + NPIX + step * 16, raw[slot][sub * 2 + 1]);
+                for (int i = 0; i < NV; i++) o[i] = fmaf(o[i], scale, bias);
+                if (has_add) {
+#pragma unroll
+                    for (int i = 0; i < NV; i++) o[i] += nz[i];
+                }
+                if (ep_on) {
+                    if (p.ep.act == 3) {
+                        const float gp = p.ep.gain, gn = p.ep.gain * p.ep.alpha;
+#pragma unroll
+                        for (int i = 0; i < NV; i++) o[i] *= (o[i] > 0.f) ? gp : gn;
+                    } else if (p.ep.gain != 1.f) {
+#pragma unroll
+                        for (int i = 0; i < NV; i++) o[i] *= p.ep.gain;
+                    }
+                    if (p.ep.clamp >= 0.f) {
+#pragma unroll
+                        for (int i = 0; i < NV; i++) o[i] = fminf(fmaxf(o[i], -p.ep.clamp), p.ep.clamp);
+                    }
+                    if (has_res) {
+#pragma unroll
+                        for (int i = 0; i < NV; i++) o[i] = fmaf(rs[i], p.ep.res_scale, o[i] * gam);
+                    }
                 }
             };
-            issue(0, 0);
-            tmem_ld_wait();
+
+            if (wide) {
+                uint32_t raw[2][NLD][16];
+                auto issue = [&](int step, int slot) {
 #pragma unroll
-            for (int step = 0; step < NIT; step++) {
-                const int slot = step & 1;
-                if (step + 1 < NIT) issue(step + 1, slot ^ 1);     // in flight while this step is processed
-                // one run of up to `maxn` (<= 8) consecutive pixels of one image row: tile columns j0 .. j0+maxn-1, whose
-                // accumulator values are raw[slot][..][r0 ..]
-                auto chunk = [&](const int j0, const int r0, const int maxn) {
-                    const int w_l = j0 & (p.tw - 1);
-                    const int h_l = (j0 >> p.tw_sh) & (p.th - 1);
-                    const int n = n0 + (j0 >> tile_hw_sh);
-                    const int gh = h0 + h_l, gw0 = w0 + w_l;
-                    if (n != cur_n) {
-                        if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
-                        ds_acc = 0.f;
-                        cur_n = n;
-                        scale = (n < p.N) ? p.oscale[(size_t)n * p.Nout + ch] * gsv : 0.f;
+                    for (int sub = 0; sub < NSUB; sub++) {
+                        tmem_ld16_nowait(acc + sub * SUB_COLS + step * 16, raw[slot][sub * (SPLIT ? 2 : 1)]);
+                        if (SPLIT) tmem_ld16_nowait(acc + sub * SUB_COLS + NPIX + step * 16, raw[slot][sub * 2 + 1]);
                     }
-                    if (n >= p.N || gh >= ph0.Hg) return;
-                    const int oy = gh * p.out_s + ph0.oy;
-                    if (oy >= p.out_H) return;
-                    const bool full8 = (maxn == 8);
-                    // values of the chunk: v[sub][i] = pixel gw0+i of phase `sub`
-                    float v[NSUB][8];
+                };
+                issue(0, 0);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int sub = 0; sub < NSUB; sub++)
+                for (int step = 0; step < NIT; step++) {
+                    const int slot = step & 1;
+                    if (step + 1 < NIT) issue(step + 1, slot ^ 1);     // in flight while this step is processed
+                    do {
+                        const int jw = step * 16;                      // column inside this warp's half
+                        int n, gh, gw0;
+                        locate(chalf * (NPIX / 2) + jw, n0, h0, w0, n, gh, gw0);
+                        set_sample(n);
+                        const int oy = gh * p.out_s + ph0.oy;
+                        if (n >= p.N || gh >= ph0.Hg || oy >= p.out_H) break;
+                        float v[NSUB][16];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            float a = 0.f;
-                            if (r0 + i < 16) {
-                                a = __uint_as_float(raw[slot][sub * (SPLIT ? 2 : 1)][(r0 + i) & 15]);
-                                if (SPLIT) a += __uint_as_float(raw[slot][sub * 2 + 1][(r0 + i) & 15]) * (1.f / kLoScale);
+                        for (int sub = 0; sub < NSUB; sub++)
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                float a = __uint_as_float(raw[slot][sub * (SPLIT ? 2 : 1)][i]);
+                                if (SPLIT) a += __uint_as_float(raw[slot][sub * 2 + 1][i]) * (1.f / kLoScale);
+                                v[sub][i] = a;
                             }
-                            v[sub][i] = a;
-                        }
-                    const size_t plane = (size_t)n * p.Nout + ch;
-                    if (PAIR) {
-                        // interleave the two horizontal phases: output pixels 2*gw0 .. 2*gw0 + 2*maxn - 1
-                        float o[16];
+                        const size_t plane = (size_t)n * p.Nout + ch;
+                        if (PAIR) {
+                            // interleave the two horizontal phases: output pixels 2*gw0 .. 2*gw0+31
+                            float o[32];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) { o[2 * i] = v[0][i] * scale; o[2 * i + 1] = v[NSUB - 1][i] * scale; }
-                        const int ox0 = gw0 * 2;
-                        int nv = p.out_W - ox0; nv = nv > 2 * maxn ? 2 * maxn : nv;
-                        const int nw = (ph0.Wg - gw0) * 2;                 // columns this tile may write (its px = 0 grid)
-                        nv = nv > nw ? nw : nv;
-                        if (nv <= 0) return;
-                        TOut* outp = (TOut*)p.out + plane * HW + (size_t)oy * p.out_pitch + ox0;
-                        const bool vec = p.vec_out && full8;
-                        store8<TOut>(outp, o, nv > 8 ? 8 : nv, vec);
-                        if (nv > 8) store8<TOut>(outp + 8, o + 8, nv - 8, vec);
-                    } else {
-                        int nv = ph0.Wg - gw0; nv = nv > maxn ? maxn : nv;
+                            for (int i = 0; i < 16; i++) { o[2 * i] = v[0][i] * scale; o[2 * i + 1] = v[NSUB - 1][i] * scale; }
+                            const int ox0 = gw0 * 2;
+                            int nv = p.out_W - ox0; nv = nv > 32 ? 32 : nv;
+                            const int nw = (ph0.Wg - gw0) * 2;             // columns this tile may write (its px = 0 grid)
+                            nv = nv > nw ? nw : nv;
+                            if (nv <= 0) break;
+                            TOut* outp = (TOut*)p.out + plane * HW + (size_t)oy * p.out_pitch + ox0;
+                            store16<TOut>(outp, o, nv > 16 ? 16 : nv, p.vec_out);
+                            if (nv > 16) store16<TOut>(outp + 16, o + 16, nv - 16, p.vec_out);
+                            break;
+                        }
+                        int nv = ph0.Wg - gw0; nv = nv > 16 ? 16 : nv;
                         const int ox0 = gw0 * p.out_s + ph0.ox;
                         if (p.out_s != 1) {
                             // strided output without pairing (not used by the decoder): scalar stores
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
+                            for (int i = 0; i < 16; i++) {
                                 const int ox = ox0 + i * p.out_s;
                                 if (i < nv && ox < p.out_W) ((TOut*)p.out)[plane * HW + (size_t)oy * p.out_pitch + ox] = from_acc<TOut, float>(v[0][i] * scale);
                             }
-                            return;
+                            break;
                         }
                         { const int lim = p.out_W - ox0; nv = nv > lim ? lim : nv; }
-                        if (nv <= 0) return;
+                        if (nv <= 0) break;
                         const size_t off = plane * HW + (size_t)oy * p.out_pitch + ox0;
                         float* o = v[0];
+                        float sd[16];
+                        if (PRE && side_base) {
+                            if (pre_ok & (1u << step)) raw16_unpack<TOut>(&pre[step * RW], sd);
+                            else load16<TOut>(side_base + plane * side_plane + (size_t)oy * side_pitch + ox0, sd, nv, false);
+                        }
                         if (DGRAD) {
                             if (do_ds) {
-                                float xs[8];
-                                load8<TOut>((const TOut*)p.aux + off, xs, nv, p.vec_side && full8);
 #pragma unroll
-                                for (int i = 0; i < 8; i++) ds_acc = fmaf(xs[i], o[i], ds_acc);
+                                for (int i = 0; i < 16; i++) ds_acc = fmaf(sd[i], o[i], ds_acc);
                             }
 #pragma unroll
-                            for (int i = 0; i < 8; i++) o[i] *= scale;
+                            for (int i = 0; i < 16; i++) o[i] *= scale;
                         } else {
+                            float nz[16];
+                            if (has_add) {
 #pragma unroll
-                            for (int i = 0; i < 8; i++) o[i] = fmaf(o[i], scale, bias);
-                            if (p.add) {
-                                float nz[8];
-                                load8<float>(p.add + (size_t)n * p.add_sn + (size_t)oy * p.out_W + ox0, nz, nv, p.vec_add && full8);
-#pragma unroll
-                                for (int i = 0; i < 8; i++) o[i] += nz[i];
-                            }
-                            if (ep_on) {
-                                if (p.ep.act == 3) {
-                                    const float gp = p.ep.gain, gn = p.ep.gain * p.ep.alpha;
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) o[i] *= (o[i] > 0.f) ? gp : gn;
-                                } else if (p.ep.gain != 1.f) {
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) o[i] *= p.ep.gain;
-                                }
-                                if (p.ep.clamp >= 0.f) {
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) o[i] = fminf(fmaxf(o[i], -p.ep.clamp), p.ep.clamp);
-                                }
-                                if (has_res) {
-                                    float rs[8];
-                                    load8<TOut>((const TOut*)p.ep.residual + plane * HWd + (size_t)oy * p.out_W + ox0, rs, nv, p.vec_side && full8);
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) o[i] = fmaf(rs[i], p.ep.res_scale, o[i] * gam);
+                                for (int q = 0; q < 4; q++) {
+                                    const float4 a4 = *(const float4*)(nz_tile + chalf * (NPIX / 2) + jw + 4 * q);
+                                    nz[4 * q] = a4.x; nz[4 * q + 1] = a4.y; nz[4 * q + 2] = a4.z; nz[4 * q + 3] = a4.w;
                                 }
                             }
+                            finish_fwd(o, nz, sd, std::integral_constant<int, 16>());
                         }
-                        store8<TOut>((TOut*)p.out + off, o, nv, p.vec_out && full8);
-                    }
-                };
-                const int jbase = chalf * (NPIX / 2) + step * 16;
-                if (p.tw >= 8) {
-                    chunk(jbase, 0, 8);
-                    chunk(jbase + 8, 8, 8);
-                } else {                       // 4-pixel rows (images narrower than 8 pixels)
-                    chunk(jbase, 0, 4);
-                    chunk(jbase + 4, 4, 4);
-                    chunk(jbase + 8, 8, 4);
-                    chunk(jbase + 12, 12, 4);
+                        store16<TOut>((TOut*)p.out + off, o, nv, p.vec_out);
+                    } while (0);
+                    if (step + 1 < NIT) tmem_ld_wait();
                 }
-                if (step + 1 < NIT) tmem_ld_wait();
+            } else {
+                // tiles of rows shorter than 16 pixels (images up to 8x8): one element at a time, compact code
+#pragma unroll 1
+                for (int step = 0; step < NIT; step++) {
+                    uint32_t raw[NLD][16];
+#pragma unroll
+                    for (int sub = 0; sub < NSUB; sub++) {
+                        tmem_ld16_nowait(acc + sub * SUB_COLS + step * 16, raw[sub * (SPLIT ? 2 : 1)]);
+                        if (SPLIT) tmem_ld16_nowait(acc + sub * SUB_COLS + NPIX + step * 16, raw[sub * 2 + 1]);
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int jw = step * 16 + i;
+                        int n, gh, gw;
+                        locate(chalf * (NPIX / 2) + jw, n0, h0, w0, n, gh, gw);
+                        set_sample(n);
+                        if (n >= p.N || gh >= ph0.Hg) continue;
+                        const size_t plane = (size_t)n * p.Nout + ch;
+#pragma unroll
+                        for (int sub = 0; sub < NSUB; sub++) {
+                            const TcPhase& ph = p.ph[grp * NSUB + sub];
+                            const int oy = gh * p.out_s + ph.oy, ox = gw * p.out_s + ph.ox;
+                            if (gw >= ph.Wg || oy >= p.out_H || ox >= p.out_W) continue;
+                            float a = __uint_as_float(raw[sub * (SPLIT ? 2 : 1)][i]);
+                            if (SPLIT) a += __uint_as_float(raw[sub * 2 + 1][i]) * (1.f / kLoScale);
+                            const size_t off = plane * HW + (size_t)oy * p.out_pitch + ox;
+                            float o[1], nz[1], sd[1];
+                            o[0] = a;
+                            if (DGRAD) {
+                                if (do_ds) ds_acc = fmaf(to_acc(side_base[off]), a, ds_acc);
+                                o[0] = a * scale;
+                            } else {
+                                nz[0] = has_add ? nz_tile[chalf * (NPIX / 2) + jw] : 0.f;
+                                sd[0] = has_res ? to_acc(side_base[plane * HWd + (size_t)oy * p.out_W + ox]) : 0.f;
+                                finish_fwd(o, nz, sd, std::integral_constant<int, 1>());
+                            }
+                            ((TOut*)p.out)[off] = from_acc<TOut, float>(o[0]);
+                        }
+                    }
+                }
             }
-            if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
+            set_sample(-2);        // flush the dstyles partial of the last sample
             // all tcgen05.ld of this warp have completed: hand the accumulator buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -866,7 +968,7 @@ void pick_tile(int Hg, int Wg, int npix, int a_s, int& tw, int& th, int& tn) {
             const int h = npix / (w * n);
             if (h < 1 || w * h * n != npix) continue;
             if (w * a_s > 256 || h * a_s > 256 || n > 256) continue;
-            if (w < 8 && Wg >= 8) continue;
+            if (w < 16 && Wg >= 16) continue;
             const double cover = (double)ceil_div(Wg, w) * w * ceil_div(Hg, h) * h;
             const double waste = cover / ((double)Wg * Hg) * (n > 1 && Hg * Wg > w * h ? 4.0 : 1.0);
             if (waste < best - 1e-9) { best = waste; tw = w; th = h; tn = n; }
@@ -875,7 +977,7 @@ void pick_tile(int Hg, int Wg, int npix, int a_s, int& tw, int& th, int& tn) {
 }
 int ilog2(int v) { int r = 0; while ((1 << r) < v) r++; return r; }
 
-size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 256; }
+size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 256 + 2 * 256 * sizeof(float); }
 
 template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX>
 int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
@@ -912,11 +1014,12 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     a.N = op.N; a.Nout = op.Nout;
     a.ngroups = pair ? 2 : 1;
     // 16-byte vector access: every 8-pixel chunk starts at a multiple of 8 pixels of a row, rows and planes must keep that alignment
-    const int es = f32 ? 4 : 2, va = 16 / es;
-    a.vec_out = aligned16(a.out) && a.out_pitch % va == 0 && a.tw >= 8;
+    const int va = f32 ? 8 : 16;       // elements per 32 bytes
+    auto aligned32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+    a.vec_out = aligned32(a.out) && a.out_pitch % va == 0 && a.tw >= 16;
     const void* side = dgrad ? a.aux : a.ep.residual;
-    a.vec_side = side && aligned16(side) && (dgrad ? a.out_pitch : a.out_W) % va == 0 && a.tw >= 8;
-    a.vec_add = a.add && aligned16(a.add) && a.out_W % 4 == 0 && (a.add_sn % 4) == 0 && a.tw >= 8;
+    a.vec_side = side && aligned32(side) && (dgrad ? a.out_pitch : a.out_W) % va == 0 && a.tw >= 16;
+    a.vec_add = 0;
     CUtensorMap maps[4];
     uint64_t pdims[4] = {(uint64_t)op.Cin, (uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.N};
     uint32_t pbox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)(a.th * a.a_s), (uint32_t)a.tn};

@@ -237,6 +237,250 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Streaming blur: up == down == 1, filter <= 4x4 (the modulated conv's post-transposed-conv FIR and its backward, which
+// is where almost all upfirdn2d bytes of the decoder go).  No shared memory: a thread owns 8 consecutive output
+// columns and walks down a strip of rows.  Per input row it issues ONE 16-byte (fp16) / 32-byte (fp32) load of its own
+// 8 columns, takes the <= 3 halo columns on either side from the neighbouring lanes with warp shuffles (global loads only
+// at strip edges), and keeps the four partially accumulated output rows in registers, so every input element is
+// converted once and every output row leaves as one aligned vector store.  A rank-1 filter (the decoder's
+// [1,3,3,1] x [1,3,3,1]) is detected in the kernel and evaluated separably (8 instead of 16 FMAs per output).
+// Requires 16-byte aligned rows on both sides; everything else goes to the tiled / generic kernels.
+template <class T, int PX>
+__global__ void __launch_bounds__(128) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+    constexpr int NL = PX;                 // halo columns on the left
+    constexpr int NR = 3 - PX;             // halo columns on the right
+    constexpr int EW = (int)(4 / sizeof(T));   // elements per 32-bit word (2 for fp16, 1 for fp32)
+    constexpr int NW = 8 / EW;             // words of the thread's own 8 columns
+    const int CG = 1 << cg_log2;           // column groups per row (power of two; groups past the row end idle)
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cgi = (int)(gid & (CG - 1));
+    int64_t rest = gid >> cg_log2;
+    const int strip = (int)(rest % strips);
+    const int64_t plane = rest / strips;
+    const bool alive = plane < (int64_t)p.channels * p.batch;
+    const int c = alive ? (int)(plane % p.channels) : 0, n = alive ? (int)(plane / p.channels) : 0;
+    const int lane = threadIdx.x & 31;
+    const int lmask = (CG < 32 ? CG : 32) - 1;
+    const bool edge_l = (lane & lmask) == 0, edge_r = (lane & lmask) == lmask;
+
+    // correlation taps with the gain folded in (fp32 product, like the reference's scaled filter tensor); missing taps = 0
+    float f[4][4];
+#pragma unroll
+    for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+        for (int tx = 0; tx < 4; tx++) {
+            float v = 0.f;
+            if (tx < p.fw && ty < p.fh) {
+                const int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
+                v = __ldg(&p.f[fy * p.fsh + fx * p.fsw]) * (float)p.gain;
+            }
+            f[ty][tx] = v;
+        }
+    // rank-1 test: f == fy (x) fx with fx = pivot row / pivot, fy = pivot column
+    float fxs[4], fys[4];
+    bool sep;
+    {
+        int pi = 0, pj = 0; float best = -1.f;
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) if (fabsf(f[ty][tx]) > best) { best = fabsf(f[ty][tx]); pi = ty; pj = tx; }
+        float piv = 1.f, prow[4], pcol[4];
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) {
+                if (ty == pi && tx == pj) piv = f[ty][tx];
+                if (ty == pi) prow[tx] = f[ty][tx];
+                if (tx == pj) pcol[ty] = f[ty][tx];
+            }
+        const float inv = (best > 0.f) ? 1.f / piv : 0.f;
+        sep = best > 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { fxs[i] = prow[i] * inv; fys[i] = pcol[i]; }
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(f[ty][tx] - fys[ty] * fxs[tx]) <= 1e-6f * best);
+    }
+
+    const int ox0 = cgi * 8;
+    const int oy_begin = strip * strip_rows;
+    const int oy_end = min(oy_begin + strip_rows, p.out_h);
+    const bool active = alive && ox0 < p.out_w && oy_begin < oy_end;
+    const T* xp = (const T*)p.x + (int64_t)n * p.isn + (int64_t)c * p.isc;
+    T* yp = (T*)p.y + (int64_t)n * p.osn + (int64_t)c * p.osc;
+    const float bias = (p.ep_enable && p.ep_bias) ? to_acc(((const T*)p.ep_bias)[c]) : 0.f;
+
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b] = 0.f;
+
+    // input rows iy = oy - pady0 + ty  ->  rows [oy_begin - pady0, oy_end - 1 - pady0 + 3]
+    const int iy_first = oy_begin - p.pady0;
+    const int nrows = active ? (oy_end - oy_begin + 3) : 0;
+    const int nrows_warp = __reduce_max_sync(0xffffffffu, nrows);      // shuffles need the whole warp in the loop
+
+    auto load_row = [&](int iy, float* in) {      // in[0..10] = input columns ox0 - PX .. ox0 - PX + 10
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = 0u;
+        const bool row_ok = active && iy >= 0 && iy < p.in_h;
+        const T* rp = xp + (int64_t)iy * p.ish;
+        if (row_ok && ox0 < p.in_w) {
+            if (ox0 + 8 <= p.in_w) {
+                if (NW == 4) { const uint4 u = ldg_stream(rp + ox0); w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; }
+                else { const uint4 u0 = ldg_stream(rp + ox0), u1 = ldg_stream(rp + ox0 + 4); w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[NW - 4] = u1.x; w[NW - 3] = u1.y; w[NW - 2] = u1.z; w[NW - 1] = u1.w; }
+            } else {
+                // the vector straddles the row end: element-wise, zero beyond in_w (the pitch padding is not data)
+                T e[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) e[i] = (ox0 + i < p.in_w) ? rp[ox0 + i] : from_acc<T, float>(0.f);
+#pragma unroll
+                for (int i = 0; i < NW; i++) w[i] = ((const uint32_t*)e)[i];
+            }
+        }
+        // halo words from the neighbouring lanes (their own columns), global loads at the strip edges
+        constexpr int WL = (NL + EW - 1) / EW, WR = (NR + EW - 1) / EW;    // halo words needed on each side
+        uint32_t hl[WL > 0 ? WL : 1], hr[WR > 0 ? WR : 1];
+#pragma unroll
+        for (int i = 0; i < WL; i++) hl[i] = __shfl_up_sync(0xffffffffu, w[NW - WL + i], 1);
+#pragma unroll
+        for (int i = 0; i < WR; i++) hr[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
+        if (WL > 0 && edge_l) {
+            T e[WL * EW];
+#pragma unroll
+            for (int i = 0; i < WL * EW; i++) { const int ix = ox0 - WL * EW + i; e[i] = (row_ok && ix >= 0 && ix < p.in_w) ? rp[ix] : from_acc<T, float>(0.f); }
+#pragma unroll
+            for (int i = 0; i < WL; i++) hl[i] = ((const uint32_t*)e)[i];
+        }
+        if (WR > 0 && edge_r) {
+            T e[WR * EW];
+#pragma unroll
+            for (int i = 0; i < WR * EW; i++) { const int ix = ox0 + 8 + i; e[i] = (row_ok && ix < p.in_w) ? rp[ix] : from_acc<T, float>(0.f); }
+#pragma unroll
+            for (int i = 0; i < WR; i++) hr[i] = ((const uint32_t*)e)[i];
+        }
+        // unpack: columns ox0 - NL .. ox0 + 7 + NR
+        float own[8], left[WL * EW > 0 ? WL * EW : 1], right[WR * EW > 0 ? WR * EW : 1];
+        if (EW == 2) {
+#pragma unroll
+            for (int i = 0; i < NW; i++) { const float2 t = __half22float2(*(const __half2*)&w[i]); own[2 * i] = t.x; own[2 * i + 1] = t.y; }
+#pragma unroll
+            for (int i = 0; i < WL; i++) { const float2 t = __half22float2(*(const __half2*)&hl[i]); left[2 * i] = t.x; left[2 * i + 1] = t.y; }
+#pragma unroll
+            for (int i = 0; i < WR; i++) { const float2 t = __half22float2(*(const __half2*)&hr[i]); right[2 * i] = t.x; right[2 * i + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; i++) own[i] = __uint_as_float(w[i]);
+#pragma unroll
+            for (int i = 0; i < WL; i++) left[i] = __uint_as_float(hl[i]);
+#pragma unroll
+            for (int i = 0; i < WR; i++) right[i] = __uint_as_float(hr[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NL; i++) in[i] = left[WL * EW - NL + i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) in[NL + i] = own[i];
+#pragma unroll
+        for (int i = 0; i < NR; i++) in[NL + 8 + i] = right[i];
+    };
+
+    auto emit = [&](int oy, float* o) {
+        if (p.add) {
+            const float* ap = p.add + (int64_t)n * p.add_sn + (int64_t)oy * p.add_sh + ox0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) o[i] += __ldg(ap + i);
+        }
+        if (p.ep_enable) {
+            const float gp = p.ep_gain, gn = (p.ep_act == 3) ? p.ep_gain * p.ep_alpha : p.ep_gain;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float v = o[i] + bias;
+                v *= (v > 0.f) ? gp : gn;
+                if (p.ep_clamp >= 0.f) v = fminf(fmaxf(v, -p.ep_clamp), p.ep_clamp);
+                o[i] = v;
+            }
+        }
+        T* rp = yp + (int64_t)oy * p.osh + ox0;
+        if (ox0 + 8 <= p.out_w) {
+            if (EW == 2) {
+                union { uint4 u; __half2 h[4]; } t;
+#pragma unroll
+                for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+                stg_stream(rp, t.u);
+            } else {
+                stg_stream(rp, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                stg_stream(rp + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) rp[i] = from_acc<T, float>(o[i]);
+        }
+    };
+
+    // input row r (0-based inside the strip) feeds output rows r - ty (ty = 0..3); output row r - 3 is complete after it
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows_warp; r0 += 4) {
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            const int r = r0 + rr;
+            if (r >= nrows_warp) break;
+            float in[11];
+            load_row(iy_first + r, in);
+            if (sep) {
+                float h[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) h[i] = fxs[0] * in[i] + fxs[1] * in[i + 1] + fxs[2] * in[i + 2] + fxs[3] * in[i + 3];
+#pragma unroll
+                for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(fys[ty], h[i], acc[(rr - ty) & 3][i]);
+            } else {
+#pragma unroll
+                for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+                    for (int tx = 0; tx < 4; tx++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
+            }
+            // output row (r - 3) used accumulator slot (rr - 3) & 3 == (rr + 1) & 3
+            const int oy = oy_begin + r - 3;
+            if (active && r >= 3 && oy < oy_end) emit(oy, acc[(rr + 1) & 3]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[(rr + 1) & 3][i] = 0.f;
+        }
+    }
+}
+
+template <class T>
+int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
+    const int groups = ceil_div(a.out_w, 8);
+    int cg_log2 = 0;
+    while ((1 << cg_log2) < groups) cg_log2++;
+    // strips: enough threads to fill the machine, few enough that the 3-row halo stays cheap
+    const int64_t planes = (int64_t)a.channels * a.batch;
+    int strip_rows = 32;
+    while (strip_rows > 8 && planes * ceil_div(a.out_h, strip_rows) * (1 << cg_log2) < (int64_t)kNumSMs * 2048) strip_rows >>= 1;
+    const int strips = ceil_div(a.out_h, strip_rows);
+    const int64_t threads = planes * strips * (1 << cg_log2);
+    const int64_t blocks = ceil_div64(threads, 128);
+    if (blocks > 0x7fffffffLL) { set_error("upfirdn2d: grid too large"); return VFM_ERR_INVALID; }
+    KernelTimer timer("upfirdn2d_blur", stream, 0.0,
+                      ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T) + (double)a.fw * a.fh * 4,
+                      "w%dc%d", a.out_w, a.channels);
+    switch (a.padx0) {
+        case 0: upfirdn2d_blur<T, 0><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+        case 1: upfirdn2d_blur<T, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+        case 2: upfirdn2d_blur<T, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+        default: upfirdn2d_blur<T, 3><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+    }
+    return launch_status("upfirdn2d_blur");
+}
+
 template <class T, int UP, int DOWN, int FW, int FH>
 constexpr bool tiled_fits() {
     typedef TileCfg<UP, DOWN, FW, FH> C;
@@ -265,6 +509,14 @@ template <class T>
 int launch(UpfirdnArgs a, cudaStream_t stream) {
     bool wcontig = (a.isw == 1 && a.osw == 1);
     bool sym = (a.upx == a.upy && a.downx == a.downy);
+    if constexpr (sizeof(T) <= 4) {
+        // streaming blur: up = down = 1, <= 4x4 taps, 16-byte aligned rows, and the left padding inside the halo it handles
+        const int es = (int)sizeof(T);
+        const bool rows16 = a.vec_ok && aligned16(a.y) && (a.osh * es) % 16 == 0 && (a.osc * es) % 16 == 0 && (a.osn * es) % 16 == 0;
+        if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw <= 4 && a.fh <= 4 && rows16 &&
+            a.padx0 >= 0 && a.padx0 <= 3 && a.out_w <= a.in_w + a.padx0 && (!a.add || a.add_sh >= a.out_w))
+            return launch_blur<T>(a, stream);
+    }
     if (wcontig && sym && a.out_w >= 32 && a.out_h >= 8) {
         int up = a.upx, down = a.downx;
         if (up == 1 && down == 1 && a.fw <= 4 && a.fh <= 4) return launch_tiled<T, 1, 1, 4, 4>(a, stream);

@@ -169,6 +169,43 @@ def test_upfirdn2d_decoder_shapes(dtype, cfg, channels_last):
     assert rel_err(dx, dxr) <= tol
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('cfg', [
+    # (N, C, H, W, filter, padding [x0,x1,y0,y1], flip)  -- all with 16-byte aligned rows => the streaming blur kernel
+    dict(shape=(2, 5, 24, 64), f='binom4', pad=[1, 1, 1, 1], flip=False),            # the decoder's post-convT blur geometry
+    dict(shape=(2, 3, 33, 264), f='binom4', pad=[2, 2, 2, 2], flip=True),            # its backward (out = in + 1)
+    dict(shape=(1, 4, 16, 8), f='binom4', pad=[0, 3, 3, 0], flip=False),             # one column group, lopsided padding
+    dict(shape=(3, 2, 9, 16), f='rand4', pad=[3, 0, 0, 3], flip=False),              # non-separable filter
+    dict(shape=(1, 2, 40, 512), f='rand4', pad=[1, 2, 2, 1], flip=True),             # rows wider than one warp (halo across warps)
+    dict(shape=(2, 2, 20, 40), f='rand3', pad=[1, 1, 1, 1], flip=False),             # 3x3 taps, 5 column groups (non power of two)
+    dict(shape=(1, 3, 12, 48), f='binom4', pad=[2, -1, 1, -2], flip=False),          # negative padding on the far sides (crop)
+])
+def test_upfirdn2d_streaming_blur(dtype, cfg):
+    V = _ops()
+    g = torch.Generator().manual_seed(11)
+    f = {'binom4': O.setup_filter([1, 3, 3, 1]), 'rand4': torch.randn(4, 4, generator=g), 'rand3': torch.randn(3, 3, generator=g)}[cfg['f']]
+    xq = torch.randn(cfg['shape'], generator=g).to(dtype).float()
+    kw = dict(padding=cfg['pad'], flip_filter=cfg['flip'], gain=4.0)
+    xr = xq.clone().requires_grad_(True)
+    yr = O.upfirdn2d(xr, f, **kw)
+    dyq = torch.randn(yr.shape, generator=g).to(dtype).float()
+    dxr, = torch.autograd.grad(yr, xr, dyq)
+    x = xq.to(DEV, dtype).requires_grad_(True)
+    y = V.upfirdn2d.upfirdn2d(x, f.to(DEV), **kw)
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert y.shape == yr.shape
+    assert rel_err(y, yr) <= tol
+    dx, = torch.autograd.grad(y, x, dyq.to(DEV, dtype))
+    assert rel_err(dx, dxr) <= tol
+    # pitched rows (what the modulated conv hands to the blur): a W-slice of a wider tensor
+    wide = torch.zeros(*cfg['shape'][:3], cfg['shape'][3] + 16, device=DEV, dtype=dtype)
+    wide[..., :cfg['shape'][3] - 3] = xq[..., :cfg['shape'][3] - 3].to(DEV, dtype)
+    wide[..., cfg['shape'][3] - 3:] = 7.0     # junk in the pitch padding must never be read as data
+    xs = wide[..., :cfg['shape'][3] - 3]
+    ys = V.upfirdn2d.upfirdn2d(xs, f.to(DEV), **kw)
+    assert rel_err(ys, O.upfirdn2d(xq[..., :cfg['shape'][3] - 3], f, **kw)) <= tol
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

@@ -246,12 +246,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
 // converted once and every output row leaves as one aligned vector store.  A rank-1 filter (the decoder's
 // [1,3,3,1] x [1,3,3,1]) is detected in the kernel and evaluated separably (8 instead of 16 FMAs per output).
 // Requires 16-byte aligned rows on both sides; everything else goes to the tiled / generic kernels.
-template <class T, int PX>
-__global__ void __launch_bounds__(128) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+struct BlurTaps { float f[4][4]; float fx[4], fy[4]; };
+
+template <class T, int PX, bool SEP>
+__device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& k, int cg_log2, int strips, int strip_rows) {
     constexpr int NL = PX;                 // halo columns on the left
     constexpr int NR = 3 - PX;             // halo columns on the right
     constexpr int EW = (int)(4 / sizeof(T));   // elements per 32-bit word (2 for fp16, 1 for fp32)
     constexpr int NW = 8 / EW;             // words of the thread's own 8 columns
+    constexpr int WL = (NL + EW - 1) / EW, WR = (NR + EW - 1) / EW;    // halo words needed on each side
+    constexpr int NE = WL + WR;            // halo words an edge lane fetches itself
     const int CG = 1 << cg_log2;           // column groups per row (power of two; groups past the row end idle)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cgi = (int)(gid & (CG - 1));
@@ -264,107 +268,89 @@ __global__ void __launch_bounds__(128) upfirdn2d_blur(UpfirdnArgs p, int cg_log2
     const int lmask = (CG < 32 ? CG : 32) - 1;
     const bool edge_l = (lane & lmask) == 0, edge_r = (lane & lmask) == lmask;
 
-    // correlation taps with the gain folded in (fp32 product, like the reference's scaled filter tensor); missing taps = 0
-    float f[4][4];
-#pragma unroll
-    for (int ty = 0; ty < 4; ty++)
-#pragma unroll
-        for (int tx = 0; tx < 4; tx++) {
-            float v = 0.f;
-            if (tx < p.fw && ty < p.fh) {
-                const int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
-                v = __ldg(&p.f[fy * p.fsh + fx * p.fsw]) * (float)p.gain;
-            }
-            f[ty][tx] = v;
-        }
-    // rank-1 test: f == fy (x) fx with fx = pivot row / pivot, fy = pivot column
-    float fxs[4], fys[4];
-    bool sep;
-    {
-        int pi = 0, pj = 0; float best = -1.f;
-#pragma unroll
-        for (int ty = 0; ty < 4; ty++)
-#pragma unroll
-            for (int tx = 0; tx < 4; tx++) if (fabsf(f[ty][tx]) > best) { best = fabsf(f[ty][tx]); pi = ty; pj = tx; }
-        float piv = 1.f, prow[4], pcol[4];
-#pragma unroll
-        for (int ty = 0; ty < 4; ty++)
-#pragma unroll
-            for (int tx = 0; tx < 4; tx++) {
-                if (ty == pi && tx == pj) piv = f[ty][tx];
-                if (ty == pi) prow[tx] = f[ty][tx];
-                if (tx == pj) pcol[ty] = f[ty][tx];
-            }
-        const float inv = (best > 0.f) ? 1.f / piv : 0.f;
-        sep = best > 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { fxs[i] = prow[i] * inv; fys[i] = pcol[i]; }
-#pragma unroll
-        for (int ty = 0; ty < 4; ty++)
-#pragma unroll
-            for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(f[ty][tx] - fys[ty] * fxs[tx]) <= 1e-6f * best);
-    }
-
     const int ox0 = cgi * 8;
     const int oy_begin = strip * strip_rows;
     const int oy_end = min(oy_begin + strip_rows, p.out_h);
-    const bool active = alive && ox0 < p.out_w && oy_begin < oy_end;
+    const bool active = alive && ox0 < p.out_w && oy_begin < oy_end;      // produces outputs
+    const bool feeds = alive && oy_begin < oy_end;                         // loads input (also for its neighbours' halos)
+    const bool add_vec = p.add && ((reinterpret_cast<uintptr_t>(p.add) & 15u) == 0) && (p.add_sh & 3) == 0 && (p.add_sn & 3) == 0;
     const T* xp = (const T*)p.x + (int64_t)n * p.isn + (int64_t)c * p.isc;
     T* yp = (T*)p.y + (int64_t)n * p.osn + (int64_t)c * p.osc;
-    const float bias = (p.ep_enable && p.ep_bias) ? to_acc(((const T*)p.ep_bias)[c]) : 0.f;
+    // fused layer epilogue y = clamp(gain * act(blur + add + bias)):  with gain > 0 the gain is folded into the taps (by the
+    // caller of blur_body), the bias into the initial value of the accumulators, and lrelu(v) = max(v, alpha * v) for 0 <= alpha <= 1
+    const float eg = p.ep_enable ? p.ep_gain : 1.f;                       // > 0 (checked on the host)
+    const float acc_init = (p.ep_enable && p.ep_bias) ? to_acc(((const T*)p.ep_bias)[c]) * eg : 0.f;
+    const bool lrelu = p.ep_enable && p.ep_act == 3;
+    const float alpha = p.ep_alpha;
 
     float acc[4][8];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = 0.f;
+        for (int b = 0; b < 8; b++) acc[a][b] = acc_init;
 
     // input rows iy = oy - pady0 + ty  ->  rows [oy_begin - pady0, oy_end - 1 - pady0 + 3]
-    const int iy_first = oy_begin - p.pady0;
-    const int nrows = active ? (oy_end - oy_begin + 3) : 0;
+    const int nrows = feeds ? (oy_end - oy_begin + 3) : 0;
     const int nrows_warp = __reduce_max_sync(0xffffffffu, nrows);      // shuffles need the whole warp in the loop
 
-    auto load_row = [&](int iy, float* in) {      // in[0..10] = input columns ox0 - PX .. ox0 - PX + 10
-        uint32_t w[NW];
+    // Loads never wait for their data inside fetch(): a vector / word that straddles the row end is loaded whole (it is
+    // aligned and contains at least one valid element, so it lies inside the allocation) and the columns >= in_w are
+    // masked to zero when the words are unpacked.  keep[i] = byte mask of word i of {own, left halo, right halo}.
+    uint32_t keep[NW + NE];
+    bool partial = false;
+    {
+        auto word_mask = [&](int ix) -> uint32_t {          // word covering columns ix .. ix + EW - 1
+            if (EW == 1) return (ix >= 0 && ix < p.in_w) ? 0xffffffffu : 0u;
+            if (ix < 0 || ix >= p.in_w) return 0u;
+            return (ix + 1 < p.in_w) ? 0xffffffffu : 0x0000ffffu;
+        };
 #pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = 0u;
-        const bool row_ok = active && iy >= 0 && iy < p.in_h;
-        const T* rp = xp + (int64_t)iy * p.ish;
-        if (row_ok && ox0 < p.in_w) {
-            if (ox0 + 8 <= p.in_w) {
-                if (NW == 4) { const uint4 u = ldg_stream(rp + ox0); w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; }
-                else { const uint4 u0 = ldg_stream(rp + ox0), u1 = ldg_stream(rp + ox0 + 4); w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[NW - 4] = u1.x; w[NW - 3] = u1.y; w[NW - 2] = u1.z; w[NW - 1] = u1.w; }
-            } else {
-                // the vector straddles the row end: element-wise, zero beyond in_w (the pitch padding is not data)
-                T e[8];
+        for (int i = 0; i < NW; i++) keep[i] = word_mask(ox0 + i * EW);
 #pragma unroll
-                for (int i = 0; i < 8; i++) e[i] = (ox0 + i < p.in_w) ? rp[ox0 + i] : from_acc<T, float>(0.f);
+        for (int i = 0; i < WL; i++) keep[NW + i] = word_mask(ox0 - (WL - i) * EW);
 #pragma unroll
-                for (int i = 0; i < NW; i++) w[i] = ((const uint32_t*)e)[i];
-            }
+        for (int i = 0; i < WR; i++) keep[NW + WL + i] = word_mask(ox0 + 8 + i * EW);
+#pragma unroll
+        for (int i = 0; i < NW + NE; i++) partial = partial || (keep[i] != 0xffffffffu);
+    }
+    // rows this thread may load: inside the image and not beyond the last row its strip needs
+    const unsigned in_h_eff = feeds ? (unsigned)max(0, min(p.in_h, oy_end - p.pady0 + 3)) : 0u;
+    const bool own_ok = ox0 < p.in_w, own_hi_ok = ox0 + 4 < p.in_w;
+    bool el_ok[WL > 0 ? WL : 1], er_ok[WR > 0 ? WR : 1];
+#pragma unroll
+    for (int i = 0; i < WL; i++) el_ok[i] = edge_l && keep[NW + i] != 0u;
+#pragma unroll
+    for (int i = 0; i < WR; i++) er_ok[i] = edge_r && keep[NW + WL + i] != 0u;
+    // running fetch cursor: row iy_f at rp_f (only dereferenced when the row exists)
+    int iy_f = oy_begin - p.pady0;
+    const T* rp_f = xp + ox0 + (int64_t)iy_f * p.ish;
+    auto fetch = [&](uint32_t* w) {
+#pragma unroll
+        for (int i = 0; i < NW + NE; i++) w[i] = 0u;
+        const bool ok = (unsigned)iy_f < in_h_eff;
+        if (ok && own_ok) {
+            const uint4 u0 = ldg_stream(rp_f);
+            w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w;
         }
-        // halo words from the neighbouring lanes (their own columns), global loads at the strip edges
-        constexpr int WL = (NL + EW - 1) / EW, WR = (NR + EW - 1) / EW;    // halo words needed on each side
+        if (NW == 8 && ok && own_hi_ok) { const uint4 u1 = ldg_stream(rp_f + 4); w[NW - 4] = u1.x; w[NW - 3] = u1.y; w[NW - 2] = u1.z; w[NW - 1] = u1.w; }
+#pragma unroll
+        for (int i = 0; i < WL; i++) if (ok && el_ok[i]) w[NW + i] = __ldg((const uint32_t*)(rp_f - (WL - i) * EW));
+#pragma unroll
+        for (int i = 0; i < WR; i++) if (ok && er_ok[i]) w[NW + WL + i] = __ldg((const uint32_t*)(rp_f + 8 + i * EW));
+        rp_f += p.ish;
+        iy_f++;
+    };
+    // in[0..10] = input columns ox0 - PX .. ox0 - PX + 10, from the thread's own words and its neighbours'
+    auto expand = [&](uint32_t* w, float* in) {
+        if (partial) {          // thread-constant; lanes whose vectors lie wholly inside the row skip the masking
+#pragma unroll
+            for (int i = 0; i < NW + NE; i++) w[i] &= keep[i];
+        }
         uint32_t hl[WL > 0 ? WL : 1], hr[WR > 0 ? WR : 1];
 #pragma unroll
-        for (int i = 0; i < WL; i++) hl[i] = __shfl_up_sync(0xffffffffu, w[NW - WL + i], 1);
+        for (int i = 0; i < WL; i++) { const uint32_t t = __shfl_up_sync(0xffffffffu, w[NW - WL + i], 1); hl[i] = edge_l ? w[NW + i] : t; }
 #pragma unroll
-        for (int i = 0; i < WR; i++) hr[i] = __shfl_down_sync(0xffffffffu, w[i], 1);
-        if (WL > 0 && edge_l) {
-            T e[WL * EW];
-#pragma unroll
-            for (int i = 0; i < WL * EW; i++) { const int ix = ox0 - WL * EW + i; e[i] = (row_ok && ix >= 0 && ix < p.in_w) ? rp[ix] : from_acc<T, float>(0.f); }
-#pragma unroll
-            for (int i = 0; i < WL; i++) hl[i] = ((const uint32_t*)e)[i];
-        }
-        if (WR > 0 && edge_r) {
-            T e[WR * EW];
-#pragma unroll
-            for (int i = 0; i < WR * EW; i++) { const int ix = ox0 + 8 + i; e[i] = (row_ok && ix < p.in_w) ? rp[ix] : from_acc<T, float>(0.f); }
-#pragma unroll
-            for (int i = 0; i < WR; i++) hr[i] = ((const uint32_t*)e)[i];
-        }
-        // unpack: columns ox0 - NL .. ox0 + 7 + NR
+        for (int i = 0; i < WR; i++) { const uint32_t t = __shfl_down_sync(0xffffffffu, w[i], 1); hr[i] = edge_r ? w[NW + WL + i] : t; }
         float own[8], left[WL * EW > 0 ? WL * EW : 1], right[WR * EW > 0 ? WR * EW : 1];
         if (EW == 2) {
 #pragma unroll
@@ -388,72 +374,147 @@ __global__ void __launch_bounds__(128) upfirdn2d_blur(UpfirdnArgs p, int cg_log2
 #pragma unroll
         for (int i = 0; i < NR; i++) in[NL + 8 + i] = right[i];
     };
-
-    auto emit = [&](int oy, float* o) {
-        if (p.add) {
-            const float* ap = p.add + (int64_t)n * p.add_sn + (int64_t)oy * p.add_sh + ox0;
+    // the fused addend (noise) of an output row, fetched two rows before it is needed (running cursor oy_a / ap)
+    int oy_a = oy_begin;
+    const float* ap = p.add ? p.add + (int64_t)n * p.add_sn + (int64_t)oy_begin * p.add_sh + ox0 : nullptr;
+    const bool full_store = ox0 + 8 <= p.out_w;
+    auto fetch_add = [&](float* a) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) o[i] += __ldg(ap + i);
-        }
-        if (p.ep_enable) {
-            const float gp = p.ep_gain, gn = (p.ep_act == 3) ? p.ep_gain * p.ep_alpha : p.ep_gain;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float v = o[i] + bias;
-                v *= (v > 0.f) ? gp : gn;
-                if (p.ep_clamp >= 0.f) v = fminf(fmaxf(v, -p.ep_clamp), p.ep_clamp);
-                o[i] = v;
-            }
-        }
-        T* rp = yp + (int64_t)oy * p.osh + ox0;
-        if (ox0 + 8 <= p.out_w) {
-            if (EW == 2) {
-                union { uint4 u; __half2 h[4]; } t;
-#pragma unroll
-                for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
-                stg_stream(rp, t.u);
+        for (int i = 0; i < 8; i++) a[i] = 0.f;
+        if (active && oy_a < oy_end) {
+            if (add_vec && full_store) {
+                const float4 a0 = __ldg((const float4*)ap), a1 = __ldg((const float4*)ap + 1);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
             } else {
-                stg_stream(rp, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
-                stg_stream(rp + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
-            }
-        } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) rp[i] = from_acc<T, float>(o[i]);
+                for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) a[i] = __ldg(ap + i);
+            }
         }
+        ap += p.add_sh;
+        oy_a++;
+    };
+    const bool has_clamp = p.ep_enable && p.ep_clamp >= 0.f;
+    const unsigned emit_rows = active ? (unsigned)(oy_end - oy_begin) : 0u;      // output rows this thread stores
+    int orow = -3;                                                                // output row (strip-relative) completed by the current input row
+    T* op = yp + ox0 + (int64_t)(oy_begin - 3) * p.osh;                           // its address (dereferenced only for 0 <= orow < emit_rows)
+    auto emit = [&](float* o, const float* addv) {
+        if ((unsigned)orow < emit_rows) {
+            if (p.add) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = fmaf(addv[i], eg, o[i]);
+            }
+            if (lrelu) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = fmaxf(o[i], o[i] * alpha);
+            }
+            if (has_clamp) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) o[i] = fminf(fmaxf(o[i], -p.ep_clamp), p.ep_clamp);
+            }
+            if (full_store) {
+                if (EW == 2) {
+                    union { uint4 u; __half2 h[4]; } t;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+                    stg_stream(op, t.u);
+                } else {
+                    stg_stream(op, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                    stg_stream(op + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) op[i] = from_acc<T, float>(o[i]);
+            }
+        }
+        op += p.osh;
+        orow++;
     };
 
-    // input row r (0-based inside the strip) feeds output rows r - ty (ty = 0..3); output row r - 3 is complete after it
+    // input row r (0-based inside the strip) feeds output rows r - ty (ty = 0..3); output row r - 3 is complete after it.
+    // A ring of four row vectors is kept in flight (a slot is refilled with row r + 4 as soon as row r has been unpacked)
+    // and the addend of an output row is fetched two rows before it is needed.
+    uint32_t wq[4][NW + NE];
+    float addq[2][8];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) fetch(wq[rr]);
+    if (p.add) { fetch_add(addq[1]); fetch_add(addq[0]); }
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows_warp; r0 += 4) {
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
-            const int r = r0 + rr;
-            if (r >= nrows_warp) break;
             float in[11];
-            load_row(iy_first + r, in);
-            if (sep) {
+            expand(wq[rr], in);
+            fetch(wq[rr]);
+            if (SEP) {
                 float h[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = fxs[0] * in[i] + fxs[1] * in[i + 1] + fxs[2] * in[i + 2] + fxs[3] * in[i + 3];
+                for (int i = 0; i < 8; i++) h[i] = k.fx[0] * in[i] + k.fx[1] * in[i + 1] + k.fx[2] * in[i + 2] + k.fx[3] * in[i + 3];
 #pragma unroll
                 for (int ty = 0; ty < 4; ty++)
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(fys[ty], h[i], acc[(rr - ty) & 3][i]);
+                    for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(k.fy[ty], h[i], acc[(rr - ty) & 3][i]);
             } else {
 #pragma unroll
                 for (int ty = 0; ty < 4; ty++)
 #pragma unroll
                     for (int tx = 0; tx < 4; tx++)
 #pragma unroll
-                        for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
+                        for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(k.f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
             }
             // output row (r - 3) used accumulator slot (rr - 3) & 3 == (rr + 1) & 3
-            const int oy = oy_begin + r - 3;
-            if (active && r >= 3 && oy < oy_end) emit(oy, acc[(rr + 1) & 3]);
+            const bool emitted = orow >= 0;
+            emit(acc[(rr + 1) & 3], addq[rr & 1]);
+            if (p.add && emitted) fetch_add(addq[rr & 1]);
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[(rr + 1) & 3][i] = 0.f;
+            for (int i = 0; i < 8; i++) acc[(rr + 1) & 3][i] = acc_init;
         }
     }
+}
+
+template <class T, int PX>
+__global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+    // correlation taps with the gain folded in (fp32 product, like the reference's scaled filter tensor); missing taps = 0
+    BlurTaps k;
+#pragma unroll
+    for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+        for (int tx = 0; tx < 4; tx++) {
+            float v = 0.f;
+            if (tx < p.fw && ty < p.fh) {
+                const int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
+                v = __ldg(&p.f[fy * p.fsh + fx * p.fsw]) * (float)p.gain;
+                if (p.ep_enable) v *= p.ep_gain;          // fused epilogue gain (positive), see blur_body
+            }
+            k.f[ty][tx] = v;
+        }
+    // rank-1 test: f == fy (x) fx with fx = pivot row / pivot, fy = pivot column
+    bool sep;
+    {
+        int pi = 0, pj = 0; float best = -1.f;
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) if (fabsf(k.f[ty][tx]) > best) { best = fabsf(k.f[ty][tx]); pi = ty; pj = tx; }
+        float piv = 1.f, prow[4], pcol[4];
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) {
+                if (ty == pi && tx == pj) piv = k.f[ty][tx];
+                if (ty == pi) prow[tx] = k.f[ty][tx];
+                if (tx == pj) pcol[ty] = k.f[ty][tx];
+            }
+        const float inv = (best > 0.f) ? 1.f / piv : 0.f;
+        sep = best > 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { k.fx[i] = prow[i] * inv; k.fy[i] = pcol[i]; }
+#pragma unroll
+        for (int ty = 0; ty < 4; ty++)
+#pragma unroll
+            for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(k.f[ty][tx] - k.fy[ty] * k.fx[tx]) <= 1e-6f * best);
+    }
+    if (sep) blur_body<T, PX, true>(p, k, cg_log2, strips, strip_rows);
+    else blur_body<T, PX, false>(p, k, cg_log2, strips, strip_rows);
 }
 
 template <class T>
@@ -463,7 +524,7 @@ int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     while ((1 << cg_log2) < groups) cg_log2++;
     // strips: enough threads to fill the machine, few enough that the 3-row halo stays cheap
     const int64_t planes = (int64_t)a.channels * a.batch;
-    int strip_rows = 32;
+    int strip_rows = 64;
     while (strip_rows > 8 && planes * ceil_div(a.out_h, strip_rows) * (1 << cg_log2) < (int64_t)kNumSMs * 2048) strip_rows >>= 1;
     const int strips = ceil_div(a.out_h, strip_rows);
     const int64_t threads = planes * strips * (1 << cg_log2);
@@ -514,7 +575,8 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
         const int es = (int)sizeof(T);
         const bool rows16 = a.vec_ok && aligned16(a.y) && (a.osh * es) % 16 == 0 && (a.osc * es) % 16 == 0 && (a.osn * es) % 16 == 0;
         if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw <= 4 && a.fh <= 4 && rows16 &&
-            a.padx0 >= 0 && a.padx0 <= 3 && a.out_w <= a.in_w + a.padx0 && (!a.add || a.add_sh >= a.out_w))
+            a.padx0 >= 0 && a.padx0 <= 3 && (!a.add || a.add_sh >= a.out_w) &&
+            (!a.ep_enable || (a.ep_gain > 0.f && (a.ep_act != 3 || (a.ep_alpha >= 0.f && a.ep_alpha <= 1.f)))))
             return launch_blur<T>(a, stream);
     }
     if (wcontig && sym && a.out_w >= 32 && a.out_h >= 8) {

@@ -208,6 +208,225 @@ __global__ void __launch_bounds__(256) filtered_lrelu_kernel(FlrArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Specialised fused kernel for separable fu and fd with compile-time up/down factors and <= 6 taps per polyphase
+// (fu_w <= 6*UP, fd_w <= 6*DOWN: the StyleGAN3 family, e.g. 12-tap up2/down2).  Same five stages as the generic kernel,
+// but every FIR stage is register-blocked: a thread loads a short run of samples once (128-bit shared-memory loads where
+// the layout allows), keeps the taps in registers and produces 8 (or 8x4) outputs from them, so the inner loops are pure
+// FFMA with compile-time polyphase indexing.  The phase alignment of the zero-inserted signal is a run-time property
+// of the padding; it is absorbed by starting the thread blocks of the up passes at column/row (c - UP), c = (pad0 -
+// tile origin) mod UP, which makes the phase of a thread's i-th output a compile-time function of i.
+template <int UP, int DOWN> struct SepCfg {
+    static constexpr int TU = 6;                                   // taps per polyphase of the up filter
+    static constexpr int FU = TU * UP, FD = 6 * DOWN;              // padded tap counts
+    static constexpr int TO = (DOWN == 4) ? 16 : 32;               // output tile (square)
+    static constexpr int TUA = (TO - 1) * DOWN + FD;               // intermediate samples needed per dimension
+    static constexpr int RD4 = (7 * DOWN + FD + 3) / 4;            // float4 loads of one 8-output run of the horizontal down pass
+    static constexpr int TUNEED = ((TO / 8 - 1) * 8 * DOWN + RD4 * 4 > TUA) ? (TO / 8 - 1) * 8 * DOWN + RD4 * 4 : TUA;
+    static constexpr int TUR = (TUNEED + 3) & ~3;
+    static constexpr int TUP = (TUR % 8 == 0) ? TUR + 4 : TUR;     // row pitch of the intermediates: == 4 (mod 8) -> conflict-free float4 columns
+    static constexpr int NB = (TUP + UP + 7) / 8;                  // 8-sample thread blocks of the up passes: every column < TUP is
+                                                                   // a real intermediate sample (its sign byte may be shared with the next tile)
+    static constexpr int NIN = (UP == 1) ? 8 + TU - 1 : 8 / UP + TU;   // input samples feeding one 8-sample block
+    static constexpr int TI = (8 * NB + FU) / UP + 2;              // input tile per dimension
+    static constexpr int TIP = TI | 1;                             // odd pitch
+    static constexpr int TOP = TO + 4;                             // pitch of the horizontally down-filtered rows (== 4 mod 8)
+    static constexpr int r4(int v) { return (v + 3) & ~3; }
+    static constexpr int OFF_FD = r4(FU), OFF_IN = OFF_FD + r4(FD), OFF_UX = OFF_IN + r4(TI * TIP), OFF_U = OFF_UX + TI * TUP,
+                         OFF_DX = OFF_U + TUA * TUP, smem_floats = OFF_DX + TUA * TOP;
+};
+
+// out[i] (i < 8) = sum_k g[phase(i) + UP*k] * in[base(i) + k]: eight consecutive samples of an up-FIR whose first sample
+// is phase-aligned (zero-inserted coordinate of tap 0 is a multiple of UP)
+template <int UP, int TU, class V> __device__ __forceinline__ void up8(const float* g, const V* in, V* out) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        constexpr int dummy = 0; (void)dummy;
+        const int t0 = (UP - i % UP) % UP, base = (i + UP - 1) / UP;
+        V acc = in[base] * g[t0];
+#pragma unroll
+        for (int k = 1; k < TU; k++) acc = acc + in[base + k] * g[t0 + UP * k];
+        out[i] = acc;
+    }
+}
+struct F4 { float x, y, z, w; };
+__device__ __forceinline__ F4 operator*(const F4& a, float s) { return F4{a.x * s, a.y * s, a.z * s, a.w * s}; }
+__device__ __forceinline__ F4 operator+(const F4& a, const F4& b) { return F4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+
+template <class T, int UP, int DOWN, int SIGN>
+__global__ void __launch_bounds__(256) flr_sep_kernel(FlrArgs p) {
+    typedef SepCfg<UP, DOWN> C;
+    extern __shared__ __align__(16) float smem[];
+    float* s_fu = smem;                       // [FU]
+    float* s_fd = smem + C::OFF_FD;           // [FD]
+    float* s_in = smem + C::OFF_IN;           // [TI][TIP]
+    float* s_ux = smem + C::OFF_UX;           // [TI][TUP]   (16-byte aligned, like s_u and s_dx)
+    float* s_u = smem + C::OFF_U;             // [TUA][TUP]
+    float* s_dx = smem + C::OFF_DX;           // [TUA][TOP]
+
+    const int tid = threadIdx.x;
+    int64_t bid = blockIdx.x;
+    const int tile_x = (int)(bid % p.tiles_x); bid /= p.tiles_x;
+    const int tile_y = (int)(bid % p.tiles_y); bid /= p.tiles_y;
+    const int c = (int)(bid % p.channels), n = (int)(bid / p.channels);
+    const int64_t plane = (int64_t)n * p.channels + c;
+
+    // correlation taps (flip == 0 means true convolution -> reversed), zero-extended to the padded counts
+    for (int i = tid; i < C::FU; i += 256) s_fu[i] = (i < p.fu_w) ? p.fu[(p.flip ? i : p.fu_w - 1 - i) * p.fu_sw] : 0.f;
+    for (int i = tid; i < C::FD; i += 256) s_fd[i] = (i < p.fd_w) ? p.fd[(p.flip ? i : p.fd_w - 1 - i) * p.fd_sw] : 0.f;
+
+    const int ox0 = tile_x * C::TO, oy0 = tile_y * C::TO;
+    const int ux0 = ox0 * DOWN, uy0 = oy0 * DOWN;                       // first intermediate sample of the tile
+    const int cx = ((p.pad_x0 - ux0) % UP + UP) % UP, cy = ((p.pad_y0 - uy0) % UP + UP) % UP;
+    const int sx0 = cx - UP, sy0 = cy - UP;                             // first column / row of the up-pass thread blocks (negative)
+    const int ix0 = (ux0 + sx0 - p.pad_x0) / UP, iy0 = (uy0 + sy0 - p.pad_y0) / UP;   // exact divisions: first input sample of the tile
+
+    // ---- stage 1: input tile + bias (zero outside the image) ----
+    {
+        const float bias = to_acc(*(const T*)((const char*)p.b + (int64_t)c * p.b_stride * (int64_t)sizeof(T)));
+        const T* xp = (const T*)p.x + (int64_t)n * p.xsn + (int64_t)c * p.xsc;
+        for (int i = tid; i < C::TI * C::TI; i += 256) {
+            const int ry = i / C::TI, rx = i - ry * C::TI;
+            const int ix = ix0 + rx, iy = iy0 + ry;
+            float v = 0.f;
+            if (ix >= 0 && ix < p.x_w && iy >= 0 && iy < p.x_h) v = to_acc(xp[(int64_t)iy * p.xsh + (int64_t)ix * p.xsw]) + bias;
+            s_in[ry * C::TIP + rx] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: horizontal up-FIR.  item = (input row ry, block b): columns 8b + sx0 .. +7 ----
+    {
+        float g[C::FU];
+#pragma unroll
+        for (int i = 0; i < C::FU; i++) g[i] = s_fu[i];
+        for (int it = tid; it < C::TI * C::NB; it += 256) {
+            const int b = it / C::TI, ry = it - b * C::TI;             // lanes along rows: odd pitch -> conflict-free
+            const float* src = s_in + ry * C::TIP + (8 * b) / UP;       // (ux0 + 8b + sx0 - pad)/UP - ix0 == 8b/UP
+            float in[C::NIN], out[8];
+#pragma unroll
+            for (int k = 0; k < C::NIN; k++) in[k] = src[k];
+            up8<UP, C::TU, float>(g, in, out);
+            float* dst = s_ux + ry * C::TUP + 8 * b + sx0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const int rux = 8 * b + sx0 + i; if (rux >= 0 && rux < C::TUP) dst[i] = out[i]; }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 3: vertical up-FIR + gain / lrelu / clamp (+ signs).  item = (4-column group, block rb): rows 8rb + sy0 .. +7 ----
+    {
+        float g[C::FU];
+#pragma unroll
+        for (int i = 0; i < C::FU; i++) g[i] = s_fu[i];
+        const float act_gain = (float)(UP * UP) * p.gain;
+        constexpr int NG = C::TUP / 4;
+        for (int it = tid; it < NG * C::NB; it += 256) {
+            const int rb = it / NG, g4 = it - rb * NG;                 // lanes along column groups: consecutive float4
+            const float* src = s_ux + ((8 * rb) / UP) * C::TUP + 4 * g4;
+            F4 in[C::NIN], out[8];
+#pragma unroll
+            for (int k = 0; k < C::NIN; k++) { const float4 t = *(const float4*)(src + k * C::TUP); in[k] = F4{t.x, t.y, t.z, t.w}; }
+            up8<UP, C::TU, F4>(g, in, out);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int ruy = 8 * rb + sy0 + i;
+                if (ruy < 0 || ruy >= C::TUA) continue;
+                float v[4] = {out[i].x * act_gain, out[i].y * act_gain, out[i].z * act_gain, out[i].w * act_gain};
+                const int sy = uy0 + ruy + (SIGN == 2 ? p.s_ofs_y : 0);
+                if (SIGN == 2) {
+                    if (sy >= 0 && sy < p.s_h) {
+                        const uint8_t* srow = p.s + (plane * p.s_h + sy) * (int64_t)p.s_w_bytes;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int sx = ux0 + 4 * g4 + k + p.s_ofs_x;
+                            if (sx >= 0 && sx < p.s_w_active) {
+                                const uint32_t sb = (uint32_t)srow[sx >> 2] >> ((sx & 3) << 1);
+                                if (sb & 1) v[k] *= p.slope;
+                                if (sb & 2) v[k] = 0.f;
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        uint32_t code = 0;
+                        if (v[k] < 0.f) { v[k] *= p.slope; code = 1; }
+                        if (fabsf(v[k]) > p.clamp) { v[k] = copysignf(p.clamp, v[k]); code = 2; }
+                        packed |= code << (2 * k);
+                    }
+                    if (SIGN == 1) {
+                        const int sx = ux0 + 4 * g4;                     // write mode: sign offset is zero, ux0 is a multiple of 4
+                        if (sx < p.s_w_active && sy < p.s_h) p.s[(plane * p.s_h + sy) * (int64_t)p.s_w_bytes + (sx >> 2)] = (uint8_t)packed;
+                    }
+                }
+                *(float4*)(s_u + ruy * C::TUP + 4 * g4) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 4: horizontal down-FIR.  item = (intermediate row, q): outputs 8q .. 8q+7 ----
+    {
+        float h[C::FD];
+#pragma unroll
+        for (int i = 0; i < C::FD; i++) h[i] = s_fd[i];
+        constexpr int NQ = C::TO / 8;
+        for (int it = tid; it < C::TUA * NQ; it += 256) {
+            const int q = it / C::TUA, ruy = it - q * C::TUA;          // lanes along rows: pitch == 4 (mod 8) -> conflict-free float4
+            const float* src = s_u + ruy * C::TUP + 8 * q * DOWN;
+            float in[C::RD4 * 4];
+#pragma unroll
+            for (int k = 0; k < C::RD4; k++) { const float4 t = *(const float4*)(src + 4 * k); in[4 * k] = t.x; in[4 * k + 1] = t.y; in[4 * k + 2] = t.z; in[4 * k + 3] = t.w; }
+            float out[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float acc = in[i * DOWN] * h[0];
+#pragma unroll
+                for (int t = 1; t < C::FD; t++) acc = fmaf(in[i * DOWN + t], h[t], acc);
+                out[i] = acc;
+            }
+            float* dst = s_dx + ruy * C::TOP + 8 * q;
+            *(float4*)dst = make_float4(out[0], out[1], out[2], out[3]);
+            *(float4*)(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 5: vertical down-FIR + store.  item = (output row pair, 4-column group) ----
+    {
+        float h[C::FD];
+#pragma unroll
+        for (int i = 0; i < C::FD; i++) h[i] = s_fd[i];
+        T* yp = (T*)p.y + (int64_t)n * p.ysn + (int64_t)c * p.ysc;
+        constexpr int NG = C::TO / 4, NR = C::TO / 2;
+        for (int it = tid; it < NG * NR; it += 256) {
+            const int rp = it / NG, g4 = it - rp * NG;
+            const float* src = s_dx + (2 * rp * DOWN) * C::TOP + 4 * g4;
+            F4 acc[2] = {F4{0.f, 0.f, 0.f, 0.f}, F4{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int k = 0; k < DOWN + C::FD; k++) {
+                const float4 t = *(const float4*)(src + k * C::TOP);
+                const F4 v = F4{t.x, t.y, t.z, t.w};
+                if (k < C::FD) acc[0] = acc[0] + v * h[k];
+                if (k >= DOWN) acc[1] = acc[1] + v * h[k - DOWN];
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int oy = oy0 + 2 * rp + r;
+                if (oy >= p.y_h) continue;
+                const float o[4] = {acc[r].x, acc[r].y, acc[r].z, acc[r].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int ox = ox0 + 4 * g4 + k;
+                    if (ox < p.y_w) yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = from_acc<T, float>(o[k]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 struct FlrActArgs {
     void* x; uint8_t* s;
     double gain, slope, clamp;
@@ -270,6 +489,38 @@ int launch_fused(FlrArgs a, int sign, size_t smem, cudaStream_t stream) {
     return launch_status("filtered_lrelu_kernel");
 }
 
+template <class T, int UP, int DOWN>
+int launch_sep(FlrArgs a, int sign, cudaStream_t stream) {
+    typedef SepCfg<UP, DOWN> C;
+    void (*kern)(FlrArgs) = (sign == 1) ? flr_sep_kernel<T, UP, DOWN, 1> : (sign == 2) ? flr_sep_kernel<T, UP, DOWN, 2> : flr_sep_kernel<T, UP, DOWN, 0>;
+    const size_t smem = ((size_t)C::smem_floats + 8) * sizeof(float);
+    VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    a.tow = a.toh = C::TO;
+    a.tiles_x = ceil_div(a.y_w, C::TO);
+    a.tiles_y = ceil_div(a.y_h, C::TO);
+    int64_t blocks = (int64_t)a.tiles_x * a.tiles_y * a.channels * a.batch;
+    if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu: grid too large"); return VFM_ERR_INVALID; }
+    double planes = (double)a.channels * a.batch;
+    KernelTimer timer("filtered_lrelu_sep", stream, 0.0,
+                      ((double)a.x_w * a.x_h + (double)a.y_w * a.y_h) * planes * sizeof(T) + (double)a.channels * sizeof(T) +
+                      (sign ? planes * a.s_h * a.s_w_bytes : 0.0), "u%dd%dw%d", UP, DOWN, a.y_w);
+    kern<<<(unsigned)blocks, 256, smem, stream>>>(a);
+    return launch_status("flr_sep_kernel");
+}
+
+// returns VFM_ERR_NO_KERNEL when the specialised kernel does not cover the configuration
+template <class T>
+int try_sep(const FlrArgs& a, int sign, cudaStream_t stream) {
+    if (a.fu_h != 0 || a.fd_h != 0) return VFM_ERR_NO_KERNEL;                       // both filters separable
+    if (a.fu_w > 6 * a.up || a.fd_w > 6 * a.down) return VFM_ERR_NO_KERNEL;         // <= 6 taps per polyphase
+    if (a.up == 2 && a.down == 2) return launch_sep<T, 2, 2>(a, sign, stream);
+    if (a.up == 4 && a.down == 2) return launch_sep<T, 4, 2>(a, sign, stream);
+    if (a.up == 2 && a.down == 4) return launch_sep<T, 2, 4>(a, sign, stream);
+    if (a.up == 2 && a.down == 1) return launch_sep<T, 2, 1>(a, sign, stream);
+    if (a.up == 1 && a.down == 2) return launch_sep<T, 1, 2>(a, sign, stream);
+    return VFM_ERR_NO_KERNEL;
+}
+
 template <class T>
 int launch_act(FlrActArgs a, int sign, cudaStream_t stream) {
     int w = (sign == 1) ? max(a.x_w, a.s_w) : a.x_w;
@@ -319,6 +570,12 @@ extern "C" int vfm_filtered_lrelu(const vfm_filtered_lrelu_params* p, void* stre
     a.b_stride = p->b_stride;
     a.s_w_bytes = p->s_w_bytes; a.s_h = p->s_h; a.s_ofs_x = p->s_ofs_x; a.s_ofs_y = p->s_ofs_y; a.s_w_active = p->s_w_active;
 
+    {
+        const int sign = p->write_signs ? 1 : (p->read_signs ? 2 : 0);
+        a.tow = a.toh = a.tuw = a.tuh = a.tiw = a.tih = a.tiles_x = a.tiles_y = 0;
+        const int st = (p->dtype == VFM_F16) ? try_sep<__half>(a, sign, stream) : try_sep<float>(a, sign, stream);
+        if (st != VFM_ERR_NO_KERNEL) return st;
+    }
     // pick the largest square-ish output tile whose intermediates fit in ~100 KB (2 CTAs per SM)
     const size_t budget = 100 * 1024;
     size_t smem = 0;

@@ -336,16 +336,32 @@ def run_ours(args):
             if s['bytes'] > 0:
                 entry['gbs'] = round(s['bytes'] / (s['total_ms'] * 1e-3) / 1e9, 1)
             kernels.append(entry)
+        # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+        # (profiles/r01b_traffic.json, written by tools/ncu_summarize.py); None when no capture covers the kernel
+        def ncu_traffic(name):
+            key = {'modconv_tc_fwd': 'conv_tc_kernel<__half, 0, 0', 'modconv_tc_fwd_split': 'conv_tc_kernel<float, 0, 1',
+                   'modconv_nhwc_prepass': 'nhwc_prepass_kernel<__half', 'upfirdn2d_blur': 'upfirdn2d_blur<__half'}.get(name.split(':')[0])
+            try:
+                tr = json.load(open(os.path.join(REPO, 'profiles', 'r01b_traffic.json')))
+            except Exception:
+                return None
+            sel = [v for k, v in tr.items() if key and key in k]
+            n = sum(v['launches'] for v in sel)
+            return sum(v['launches'] * v['dram_bytes_per_launch'] for v in sel) / n if n else None
         if stats:
             top = stats[0]
             if top['flops'] > 0:
                 ach = top['flops'] / (top['total_ms'] * 1e-3) / 1e12
                 roofline = {'kernel': top['name'], 'bound': 'tensor', 'achieved': ach, 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': ach / tc_peak,
-                            'traffic': None, 'peak_source': tc_src, 'share_of_step': top['total_ms'] / ms}
+                            'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
+                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01b_ncu_full_decode.md)',
+                            'algorithmic_per_launch': top['flops'] / max(top['launches'], 1), 'peak_source': tc_src, 'share_of_step': top['total_ms'] / ms}
             else:
                 ach = top['bytes'] / (top['total_ms'] * 1e-3) / 1e9
                 roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                            'traffic': None, 'peak_source': hbm_src, 'share_of_step': top['total_ms'] / ms}
+                            'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
+                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01b_ncu_full_decode.md)',
+                            'algorithmic_per_launch': top['bytes'] / max(top['launches'], 1), 'peak_source': hbm_src, 'share_of_step': top['total_ms'] / ms}
         line = {
             'metric': f'images/sec ({args.mode})', 'value': total_imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

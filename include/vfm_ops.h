@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 1
+#define VFM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -244,6 +244,13 @@ typedef struct {
     const void*  ep_residual;    /* [N,O,Hout,Wout], dtype of x, or NULL */
     const float* ep_gamma;       /* [O] fp32 layer scale, required with ep_residual */
     double       ep_res_scale;
+    /* Optional per-(sample, channel) affine map of the input (the GroupNorm32 prologue of the residual layers,
+     * networks/generator.py:261-263, in the form vfm_group_norm_affine produces): the conv sees x * x_scale[n,i] + x_shift[n,i]
+     * (zero padding applies to the mapped tensor).  With ep_res_affine != 0 the same map is applied to ep_residual, which
+     * then is the raw x (I == O).  Only the tcgen05 path implements it; other paths return VFM_ERR_NO_KERNEL. */
+    const float* x_scale;        /* [N,I] fp32 or NULL */
+    const float* x_shift;        /* [N,I] fp32 or NULL (requires x_scale) */
+    int32_t      ep_res_affine;
 } vfm_modconv_fwd_params;
 
 typedef struct {
@@ -262,6 +269,24 @@ typedef struct {
     void*        workspace;
     size_t       workspace_bytes;
 } vfm_modconv_bwd_params;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GroupNorm statistics as an affine map (see vfm_modconv_fwd_params::x_scale): for x [N,C,H*W] contiguous,
+ *   scale[n,c] = rstd[n,g(c)] * gamma[c],   shift[n,c] = beta[c] - mean[n,g(c)] * scale[n,c]
+ * with the biased variance and eps of torch.nn.GroupNorm evaluated in fp32 (networks/utils/shared.py GroupNorm32).
+ */
+typedef struct {
+    const void*  x;          /* [N,C,HW] contiguous, `dtype` (f16 / f32) */
+    const float* gamma;      /* [C] or NULL (= 1) */
+    const float* beta;       /* [C] or NULL (= 0) */
+    float*       scale;      /* [N,C] out */
+    float*       shift;      /* [N,C] out */
+    int32_t      dtype;
+    int32_t      batch, channels, groups;
+    int64_t      hw;
+    double       eps;
+} vfm_group_norm_affine_params;
+VFM_API int vfm_group_norm_affine(const vfm_group_norm_affine_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

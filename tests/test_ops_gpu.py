@@ -387,6 +387,10 @@ def _modconv_vs_oracle(N, I, O_, H, W, k, up, demod, dtype, noise_kind, generic,
     dict(N=3, I=256, O_=128, H=8, W=8, k=3, up=2, demod=True, noise_kind='random'),
     dict(N=2, I=128, O_=128, H=4, W=4, k=3, up=2, demod=True, noise_kind='const'),       # block-0 sized: multi-sample tiles
     dict(N=1, I=128, O_=256, H=33, W=20, k=3, up=1, demod=True, noise_kind='const'),      # ragged image, partial tiles
+    # fp16 rows of a multiple of 64 pixels: the forward reads x straight from NCHW (MN-major TMA boxes, per-sample weights)
+    dict(N=2, I=256, O_=128, H=12, W=64, k=3, up=1, demod=True, noise_kind='random'),
+    dict(N=1, I=128, O_=128, H=6, W=128, k=3, up=1, demod=True, noise_kind='const'),      # partial tile rows
+    dict(N=2, I=128, O_=256, H=8, W=64, k=1, up=1, demod=False, noise_kind=None),
 ], ids=lambda c: f"N{c['N']}I{c['I']}O{c['O_']}H{c['H']}k{c['k']}up{c['up']}")
 def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
     _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)
@@ -454,6 +458,8 @@ def test_conv2d_resample_golden(case):
 @pytest.mark.parametrize('cfg', [
     dict(N=2, I=128, O_=128, H=16, up=1, residual=False),
     dict(N=2, I=128, O_=128, H=32, up=1, residual=True),
+    dict(N=2, I=256, O_=128, H=64, up=1, residual=False),     # direct-NCHW forward path (fp16)
+    dict(N=1, I=128, O_=128, H=64, up=1, residual=True),
     dict(N=2, I=256, O_=128, H=8, up=2, residual=False),
     dict(N=2, I=128, O_=3, H=32, up=1, residual=False, torgb=True),
 ], ids=lambda c: f"I{c['I']}O{c['O_']}H{c['H']}up{c['up']}{'res' if c['residual'] else ''}")
@@ -481,6 +487,46 @@ def test_fused_layer_matches_oracle(cfg, dtype):
                                    up=up, padding=k // 2, resample_filter=f.to(DEV), demodulate=not torgb, flip_weight=(up == 1), act=act,
                                    gain=gain, clamp=clamp, residual=xq.to(DEV, dtype) if cfg['residual'] else None,
                                    gamma=gamma.to(DEV) if cfg['residual'] else None, res_scale=math.sqrt(2))
+    assert y is not None, 'fused path refused a shape it should take'
+    assert y.dtype == dtype and y.shape == yr.shape
+    assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [
+    dict(N=2, C=128, H=16, groups=32, residual=True),
+    dict(N=3, C=256, H=8, groups=32, residual=True),       # multi-sample tiles: the affine map changes inside a tile
+    dict(N=1, C=128, H=64, groups=32, residual=True),
+    dict(N=2, C=128, H=32, groups=16, residual=False),     # input map only
+], ids=lambda c: f"C{c['C']}H{c['H']}g{c['groups']}{'res' if c['residual'] else ''}")
+def test_fused_residual_layer_with_group_norm(cfg, dtype):
+    """GroupNorm32 -> modconv -> bias_act -> (gamma*y + x_norm)*sqrt2 (networks/generator.py:261-274) with the normalisation folded
+    into the conv (one statistics pass): against the same chain composed from the oracle ops and torch's group_norm in fp32."""
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
+    from vfm_vae_b200.plugins import modconv_plugin as P
+    g = torch.Generator().manual_seed(31)
+    N, Cc, H = cfg['N'], cfg['C'], cfg['H']
+    xq = (torch.randn(N, Cc, H, H, generator=g) * 3 + torch.randn(N, Cc, 1, 1, generator=g) * 2).to(dtype).float()
+    w = torch.randn(Cc, Cc, 3, 3, generator=g)
+    s = torch.randn(N, Cc, generator=g) + 1
+    b = (torch.randn(Cc, generator=g) * 0.2).to(dtype).float()
+    noise = torch.randn(H, H, generator=g) * 0.3
+    gn_w, gn_b = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.3
+    gamma = torch.rand(1, Cc, 1, 1, generator=g) + 0.5
+    gain, clamp = 1.0, 256.0 * math.sqrt(0.5)
+    xn = torch.nn.functional.group_norm(xq, cfg['groups'], gn_w, gn_b, eps=1e-5)
+    # the affine form of the statistics, on its own
+    sc, sh = P.group_norm_affine(xq.to(DEV, dtype), gn_w.to(DEV), gn_b.to(DEV), cfg['groups'], 1e-5)
+    assert rel_err(xq * sc.cpu()[:, :, None, None] + sh.cpu()[:, :, None, None], xn) <= 1e-5
+    yr = O.modulated_conv2d(xn, w, s, noise=noise, up=1, padding=1, demodulate=True, flip_weight=True)
+    yr = O.bias_act(yr, b, act='lrelu', gain=gain, clamp=clamp)
+    if cfg['residual']:
+        yr = (gamma * yr + xn) * math.sqrt(2)
+    xd = xq.to(DEV, dtype)
+    with torch.no_grad():
+        y = fused_modconv_bias_act(xd, w.to(DEV), s.to(DEV), b.to(DEV, dtype), noise=noise.to(DEV), up=1, padding=1, act='lrelu', gain=gain,
+                                   clamp=clamp, residual=xd if cfg['residual'] else None, gamma=gamma.to(DEV) if cfg['residual'] else None,
+                                   res_scale=math.sqrt(2), group_norm=dict(weight=gn_w.to(DEV), bias=gn_b.to(DEV), num_groups=cfg['groups'], eps=1e-5))
     assert y is not None, 'fused path refused a shape it should take'
     assert y.dtype == dtype and y.shape == yr.shape
     assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]

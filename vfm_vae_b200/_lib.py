@@ -69,7 +69,13 @@ class ModconvFwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('x', _vp), ('weight', _vp), ('styles', _vp), ('noise', _vp), ('y', _vp),
                 ('dcoefs', _vp), ('workspace', _vp), ('workspace_bytes', _sz),
                 ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64),
-                ('ep_bias', _vp), ('ep_residual', _vp), ('ep_gamma', _vp), ('ep_res_scale', _f64)]
+                ('ep_bias', _vp), ('ep_residual', _vp), ('ep_gamma', _vp), ('ep_res_scale', _f64),
+                ('x_scale', _vp), ('x_shift', _vp), ('ep_res_affine', _i32)]
+
+
+class GroupNormAffineParams(C.Structure):
+    _fields_ = [('x', _vp), ('gamma', _vp), ('beta', _vp), ('scale', _vp), ('shift', _vp), ('dtype', _i32),
+                ('batch', _i32), ('channels', _i32), ('groups', _i32), ('hw', _i64), ('eps', _f64)]
 
 
 class ModconvBwdParams(C.Structure):
@@ -97,6 +103,7 @@ SYMBOLS = {
     'vfm_modconv_forward': (C.c_int, [C.POINTER(ModconvFwdParams), _vp]),
     'vfm_modconv_backward': (C.c_int, [C.POINTER(ModconvBwdParams), _vp]),
     'vfm_modconv_uses_tensor_cores': (C.c_int, [C.POINTER(ModconvDesc)]),
+    'vfm_group_norm_affine': (C.c_int, [C.POINTER(GroupNormAffineParams), _vp]),
 }
 
 _lib = None
@@ -117,8 +124,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 1:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 1)')
+    if lib.vfm_abi_version() != 2:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 2)')
     _lib = lib
     return lib
 

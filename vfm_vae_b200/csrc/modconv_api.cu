@@ -22,7 +22,8 @@ bool tc_supported(const vfm_modconv_desc& d);
 size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
 // stage-1 contraction: x -> z (== y for up=1; noise only added when up == 1)
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
-                      const float* noise, int64_t noise_sn, const Epilogue& ep, void* ws, size_t ws_bytes, cudaStream_t stream);
+                      const float* noise, int64_t noise_sn, const Epilogue& ep, const float* x_scale, const float* x_shift,
+                      void* ws, size_t ws_bytes, cudaStream_t stream);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
                        void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -134,6 +135,12 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
         ep.enable = 1; ep.act = p->ep_act; ep.alpha = (float)p->ep_alpha; ep.gain = (float)p->ep_gain; ep.clamp = (float)p->ep_clamp;
         ep.res_scale = (float)p->ep_res_scale; ep.bias = p->ep_bias; ep.residual = p->ep_residual; ep.gamma = p->ep_gamma;
     }
+    if (p->x_scale || p->x_shift || p->ep_res_affine) {
+        VFM_CHECK_ARG(p->x_scale && p->x_shift, "modulated_conv2d: x_scale and x_shift must be given together");
+        VFM_CHECK_ARG(!p->ep_res_affine || (p->ep_residual && d.in_channels == d.out_channels), "modulated_conv2d: ep_res_affine needs ep_residual and I == O");
+        if (!use_tc(d) || (use_pw(d) && aligned16(p->x) && aligned16(p->y))) { set_error("modulated_conv2d: the input affine map is only implemented on the tcgen05 path"); return VFM_ERR_NO_KERNEL; }
+        if (p->ep_res_affine) { ep.res_a = p->x_scale; ep.res_b = p->x_shift; }
+    }
     const Epilogue s1_ep = (d.up == 1) ? ep : no_epilogue();
 
     if (use_pw(d) && aligned16(p->x) && aligned16(p->y)) {
@@ -141,7 +148,8 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
         if (st) return st;
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
-        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, s1_ep, (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+        st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, s1_ep, p->x_scale, p->x_shift,
+                               (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
     } else {
         ConvArgs a;

@@ -35,8 +35,9 @@ struct Epilogue {
     int enable, act;
     float alpha, gain, clamp, res_scale;
     const void* bias; const void* residual; const float* gamma;
+    const float* res_a; const float* res_b;     // optional per-(n, channel) affine map of the residual (tcgen05 path only)
 };
-inline Epilogue no_epilogue() { Epilogue e; e.enable = 0; e.act = 1; e.alpha = 0.f; e.gain = 1.f; e.clamp = -1.f; e.res_scale = 1.f; e.bias = nullptr; e.residual = nullptr; e.gamma = nullptr; return e; }
+inline Epilogue no_epilogue() { Epilogue e; e.enable = 0; e.act = 1; e.alpha = 0.f; e.gain = 1.f; e.clamp = -1.f; e.res_scale = 1.f; e.bias = nullptr; e.residual = nullptr; e.gamma = nullptr; e.res_a = nullptr; e.res_b = nullptr; return e; }
 template <class T> __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, int ch, size_t idx) {
     if (e.bias) v += to_acc(((const T*)e.bias)[ch]);
     if (e.act == 3) v = (v > 0.f) ? v : v * e.alpha;

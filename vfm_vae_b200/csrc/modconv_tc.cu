@@ -452,12 +452,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
             int cur_n = -1;
             float scale = 0.f, ds_acc = 0.f;
+            float res_a = p.ep.res_scale, res_b = 0.f;          // residual term = raw * res_a + res_b  (layer scale folded in)
             auto set_sample = [&](int n) {
                 if (n == cur_n) return;
                 if (do_ds && cur_n >= 0 && cur_n < p.N) atomicAdd(&p.aux_sum[(size_t)cur_n * p.Nout + ch], ds_acc * gsv);
                 ds_acc = 0.f;
                 cur_n = n;
                 scale = (n >= 0 && n < p.N) ? p.oscale[(size_t)n * p.Nout + ch] * gsv : 0.f;
+                if (!DGRAD && has_res && p.ep.res_a && n >= 0 && n < p.N) {
+                    res_a = p.ep.res_a[(size_t)n * p.Nout + ch] * p.ep.res_scale;
+                    res_b = p.ep.res_b[(size_t)n * p.Nout + ch] * p.ep.res_scale;
+                }
             };
             set_sample(n0);
 
@@ -490,7 +495,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                     }
                     if (has_res) {
 #pragma unroll
-                        for (int i = 0; i < NV; i++) o[i] = fmaf(rs[i], p.ep.res_scale, o[i] * gam);
+                        for (int i = 0; i < NV; i++) o[i] = fmaf(rs[i], res_a, fmaf(o[i], gam, res_b));
                     }
                 }
             };
@@ -822,8 +827,8 @@ __global__ void wgrad_scalars_kernel(const float* __restrict__ iscale, int n_el,
 // (v - hi) * 2048 as a second fp16 tensor (lo).  64 channels x 64 pixels per CTA through shared memory: coalesced reads
 // along pixels, coalesced 16-byte writes along channels.
 template <class TIn, bool SPLIT>
-__global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ gscale,
-                                                           __half* __restrict__ xt, __half* __restrict__ xt_lo, int C, int HW) {
+__global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           const float* __restrict__ gscale, __half* __restrict__ xt, __half* __restrict__ xt_lo, int C, int HW) {
     __shared__ __half s[SPLIT ? 2 : 1][64][66];     // [pixel][channel], 33-word pitch: conflict-free transposed stores
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
@@ -836,7 +841,10 @@ __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict
             const int cl = cg + i * 4;
             const int c = c0 + cl;
             float v = 0.f;
-            if (pidx < HW && c < C) v = to_acc(x[((size_t)n * C + c) * HW + pidx]) * (scale[(size_t)n * C + c] * gs);
+            if (pidx < HW && c < C) {
+                v = to_acc(x[((size_t)n * C + c) * HW + pidx]) * (scale[(size_t)n * C + c] * gs);
+                if (shift) v += shift[(size_t)n * C + c] * gs;
+            }
             const __half hi = __float2half_rn(v);
             s[0][pl][cl] = hi;
             if (SPLIT) s[1][pl][cl] = __float2half_rn((v - __half2float(hi)) * kLoScale);
@@ -884,7 +892,9 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, const float* __r
 
 // per-sample power-of-two normalisation of the activation scale so that |x * scale| stays far from the fp16 limit:
 //   a_scale[n,i] = in_scale[n,i] * c2[n],  o_scale[n,o] = out_scale[n,o] / c2[n],  c2 = 2^-ceil(log2(max_i |in_scale|)) if that max > 1
-__global__ void scale_prep_kernel(const float* __restrict__ in_scale, const float* __restrict__ out_scale, float* a_scale, float* o_scale, int Cin, int Cout) {
+//   with an input affine map x -> x * xa + xb:  a_scale *= xa,  a_shift[n,i] = in_scale * c2 * xb
+__global__ void scale_prep_kernel(const float* __restrict__ in_scale, const float* __restrict__ out_scale, float* a_scale, float* o_scale, int Cin, int Cout,
+                                  const float* __restrict__ xa = nullptr, const float* __restrict__ xb = nullptr, float* a_shift = nullptr) {
     __shared__ float red[32];
     __shared__ float s_c2;
     const int n = blockIdx.x;
@@ -901,7 +911,11 @@ __global__ void scale_prep_kernel(const float* __restrict__ in_scale, const floa
     }
     __syncthreads();
     const float c2 = s_c2, c2i = 1.f / s_c2;
-    for (int i = threadIdx.x; i < Cin; i += blockDim.x) a_scale[(size_t)n * Cin + i] = in_scale[(size_t)n * Cin + i] * c2;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+        const float sc = in_scale[(size_t)n * Cin + i] * c2;
+        a_scale[(size_t)n * Cin + i] = xa ? sc * xa[(size_t)n * Cin + i] : sc;
+        if (a_shift) a_shift[(size_t)n * Cin + i] = xb ? sc * xb[(size_t)n * Cin + i] : 0.f;
+    }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) o_scale[(size_t)n * Cout + i] = out_scale[(size_t)n * Cout + i] * c2i;
 }
 
@@ -1043,13 +1057,14 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     return launch_tc<float, false, true, false, 128>(maps, a, grid, flops, stream);
 }
 
-int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream) {
+int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream,
+                const float* shift = nullptr) {
     dim3 grid(ceil_div(HW, 64), ceil_div(C, 64), N);
     if (grid.z > 65535 || grid.y > 65535) { set_error("tcgen05 path: batch too large"); return VFM_ERR_INVALID; }
     KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * ((dtype == VFM_F16 ? 2 : 4) + (split ? 4 : 2)), "c%dhw%d", C, HW);
-    if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, gscale, xt, xt_lo, C, HW);
-    else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
-    else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, gscale, xt, xt_lo, C, HW);
+    if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, shift, gscale, xt, xt_lo, C, HW);
+    else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW);
+    else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW);
     return launch_status("modconv nhwc_prepass_kernel");
 }
 
@@ -1068,7 +1083,7 @@ bool is_f32(const vfm_modconv_desc& d) { return d.dtype == VFM_F32; }
 struct TcWorkspace {
     __half *act, *act_lo, *wt, *wt_lo;       // NHWC activation operand (x in forward, d*dz in backward), re-laid-out weights
     __half *xt, *xt_lo;                      // backward only: x*s' NHWC for the weight gradient
-    float *a_scale, *o_scale, *gs;           // gs: [0] gk, [1] 1/gk, [2] c2g, [3] 1/(gk*c2g)
+    float *a_scale, *a_shift, *o_scale, *gs; // gs: [0] gk, [1] 1/gk, [2] c2g, [3] 1/(gk*c2g)
     unsigned int* amax;
 };
 
@@ -1089,6 +1104,7 @@ void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direct
     const size_t nin = (size_t)d.batch * (direction == 0 ? d.in_channels : d.out_channels);
     const size_t nout = (size_t)d.batch * (direction == 0 ? d.out_channels : d.in_channels);
     w.a_scale = cv.take<float>(nin);
+    w.a_shift = cv.take<float>(nin);
     w.o_scale = cv.take<float>(nout);
     w.gs = cv.take<float>(4);
     w.amax = cv.take<unsigned int>(4);
@@ -1164,7 +1180,8 @@ size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction) {
 }
 
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
-                      const float* noise, int64_t noise_sn, const Epilogue& ep, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                      const float* noise, int64_t noise_sn, const Epilogue& ep, const float* x_scale, const float* x_shift,
+                      void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
@@ -1172,9 +1189,9 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     carve_tc(cv, d, s, 0, w);
     if (!cv.ok()) { set_error("modulated_conv2d: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
     // A = x * s' * c2, B = W * a, epilogue scale = d / c2
-    scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O);
+    scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O, x_scale, x_shift, x_scale ? w.a_shift : nullptr);
     int st = launch_status("modconv scale_prep_kernel"); if (st) return st;
-    st = run_prepass(d.dtype, f32, x, w.a_scale, nullptr, w.act, w.act_lo, N, I, d.in_h * d.in_w, stream); if (st) return st;
+    st = run_prepass(d.dtype, f32, x, w.a_scale, nullptr, w.act, w.act_lo, N, I, d.in_h * d.in_w, stream, x_scale ? w.a_shift : nullptr); if (st) return st;
     st = run_weight_prep(weight, k.a, w.wt, w.wt_lo, O, I, KK, s.taps, 0, stream); if (st) return st;
 
     TcArgs a;

@@ -202,11 +202,21 @@ class SynthesisLayer(nn.Module):
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
         styles = self.affine(w)
-        if self.residual:
-            x = self.norm(x)
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         fused = getattr(self.ops, 'fused_layer', None)
-        if fused is not None and not torch.is_grad_enabled() and self.activation in ('linear', 'lrelu'):
+        can_fuse = fused is not None and not torch.is_grad_enabled() and self.activation in ('linear', 'lrelu')
+        if can_fuse and self.residual:
+            # inference, residual layer: GroupNorm32 -> conv + noise + bias_act -> layer-scaled residual with ONE statistics pass
+            # over x; the normalisation itself is folded into the conv's operand pre-pass and epilogue
+            y = fused(x, self.weight, styles, self.bias, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
+                      flip_weight=True, act=self.activation, gain=self.act_gain * gain, clamp=act_clamp, residual=x, gamma=self.gamma,
+                      res_scale=float(np.sqrt(2)),
+                      group_norm=dict(weight=self.norm.weight, bias=self.norm.bias, num_groups=self.norm.num_groups, eps=self.norm.eps))
+            if y is not None:
+                return y
+        if self.residual:
+            x = self.norm(x)
+        if can_fuse:
             # inference: conv + noise + bias_act (+ layer-scaled residual) in one kernel epilogue
             y = fused(x, self.weight, styles, self.bias, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
                       flip_weight=(self.up == 1), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp,

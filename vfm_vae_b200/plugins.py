@@ -306,8 +306,32 @@ class _ModconvPlugin:
         return bool(_lib.load().vfm_modconv_uses_tensor_cores(C.byref(d)))
 
     @staticmethod
-    def forward(x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight, force_generic=False, epilogue=None):
+    def group_norm_affine(x, weight, bias, num_groups, eps=1e-5):
+        """GroupNorm statistics of x [N,C,H,W] as the per-(sample, channel) affine map (scale, shift), both fp32 [N,C]:
+        group_norm(x) == x * scale[:, :, None, None] + shift[:, :, None, None]  (nn.GroupNorm evaluated in fp32)."""
+        _check(x.is_cuda and x.dim() == 4 and x.is_contiguous(), 'x must be a contiguous NCHW CUDA tensor')
+        n, c = x.shape[0], x.shape[1]
+        _check(c % int(num_groups) == 0, 'channels must be divisible by num_groups')
+        gam = weight.detach().to(torch.float32).contiguous() if weight is not None else None
+        bet = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+        scale = torch.empty([n, c], dtype=torch.float32, device=x.device)
+        shift = torch.empty([n, c], dtype=torch.float32, device=x.device)
+        p = _lib.GroupNormAffineParams()
+        p.x, p.gamma, p.beta, p.scale, p.shift = _ptr(x), _ptr(gam), _ptr(bet), _ptr(scale), _ptr(shift)
+        p.dtype = _dtype_code(x, 'group_norm_affine')
+        p.batch, p.channels, p.groups, p.hw, p.eps = n, c, int(num_groups), x.shape[2] * x.shape[3], float(eps)
+        with torch.cuda.device(x.device):
+            st = _lib.load().vfm_group_norm_affine(C.byref(p), _stream(x))
+        _lib.check(st, 'group_norm_affine')
+        return scale, shift
+
+    @staticmethod
+    def forward(x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight, force_generic=False, epilogue=None,
+                x_affine=None):
         """-> (y [N,O,Hout,Wout] in x.dtype, dcoefs [N,O] fp32).
+
+        ``x_affine`` (inference only): (scale, shift) fp32 [N,I] from ``group_norm_affine``: the conv sees x*scale+shift; with
+        ``epilogue['residual_affine']`` the same map is applied to the epilogue's residual (which then is the raw x).
 
         ``epilogue`` (inference only): dict(act='linear'|'lrelu', alpha, gain, clamp, bias, residual, gamma, res_scale) fused into the
         kernel that writes y; returns None instead of a tuple if no kernel can fuse it for this call (caller composes)."""
@@ -342,10 +366,17 @@ class _ModconvPlugin:
             p.ep_clamp = float(clamp) if clamp is not None else -1.0
             p.ep_bias, p.ep_residual, p.ep_gamma = _ptr(bias), _ptr(res), _ptr(gamma)
             p.ep_res_scale = float(epilogue.get('res_scale', 1.0))
+            p.ep_res_affine = int(bool(epilogue.get('residual_affine', False)))
+        if x_affine is not None:
+            xs, xb = x_affine
+            _check(all(t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (d.batch, d.in_channels) and t.device == x.device
+                       for t in (xs, xb)), 'x_affine must be two contiguous fp32 [N,I] tensors')
+            keep += [xs, xb]
+            p.x_scale, p.x_shift = _ptr(xs), _ptr(xb)
         with torch.cuda.device(x.device):
             st = lib.vfm_modconv_forward(C.byref(p), _stream(x))
         del keep
-        if epilogue is not None and st == _lib.VFM_ERR_NO_KERNEL:
+        if (epilogue is not None or x_affine is not None) and st == _lib.VFM_ERR_NO_KERNEL:
             return None
         _lib.check(st, 'modulated_conv2d')
         return y, dcoefs

@@ -112,20 +112,26 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
 
 
 def fused_modconv_bias_act(x, weight, styles, bias, noise=None, up=1, padding=0, resample_filter=None, demodulate=True,
-                           flip_weight=True, act='lrelu', alpha=0.2, gain=1.0, clamp=None, residual=None, gamma=None, res_scale=1.0):
+                           flip_weight=True, act='lrelu', alpha=0.2, gain=1.0, clamp=None, residual=None, gamma=None, res_scale=1.0,
+                           group_norm=None):
     """Inference-only fusion of one legacy synthesis layer:
 
+        x = GroupNorm32(x)        (group_norm=dict(weight, bias, num_groups, eps); residual layers)  networks/generator.py:261-263
         y = modulated_conv2d(x, weight, styles, noise, up, ...)                      networks/generator.py:264-265
         y = bias_act(y, bias, act=act, gain=gain, clamp=clamp)                       networks/generator.py:268-270
         y = (gamma * y + residual) * res_scale            (residual layers only)     networks/generator.py:272-274
 
     in the kernel that writes y (conv epilogue for up=1, blur epilogue for up=2, streaming kernel for ToRGB).  No autograd.
+    With ``group_norm`` the normalisation costs one statistics pass over x: it becomes a per-(sample, channel) affine map that the
+    conv's operand pre-pass applies to x and its epilogue applies to the residual; ``residual`` must then be ``x`` itself (raw).
     Returns None when no kernel can fuse this call; the caller then composes the unfused ops exactly as the reference does.
     """
     assert act in ('linear', 'lrelu')
     if x.device.type != 'cuda' or torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or styles.requires_grad):
         return None
     if residual is not None and up != 1:
+        return None
+    if group_norm is not None and (up != 1 or (residual is not None and residual is not x)):
         return None
     _init()
     n = x.shape[0]
@@ -141,5 +147,14 @@ def fused_modconv_bias_act(x, weight, styles, bias, noise=None, up=1, padding=0,
     n32 = _noise_canon(noise.detach() if noise is not None else None, n, oh, ow)
     ep = dict(act=act, alpha=alpha, gain=gain, clamp=clamp, bias=bias.detach().to(x.dtype).contiguous() if bias is not None else None,
               residual=residual.detach().contiguous() if residual is not None else None, gamma=gamma, res_scale=res_scale)
-    out = _plugin.forward(xc, w32, s32, n32, int(up), int(padding), f32, bool(demodulate), bool(flip_weight), force_generic, epilogue=ep)
+    x_affine = None
+    if group_norm is not None:
+        if not _plugin.uses_tensor_cores(xc, w32, up=up, padding=padding, demodulate=demodulate, flip_weight=flip_weight, noise=n32, resample_filter=f32):
+            return None
+        x_affine = _plugin.group_norm_affine(xc, group_norm.get('weight'), group_norm.get('bias'), group_norm['num_groups'], group_norm.get('eps', 1e-5))
+        if residual is not None:
+            ep['residual'] = xc
+            ep['residual_affine'] = True
+    out = _plugin.forward(xc, w32, s32, n32, int(up), int(padding), f32, bool(demodulate), bool(flip_weight), force_generic, epilogue=ep,
+                          x_affine=x_affine)
     return None if out is None else out[0]

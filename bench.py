@@ -125,7 +125,7 @@ def run_reference_arm(args):
     value = batch * args.steps / dt
     sample = (f'oracle port (torch CPU fp32, oracle/ref_ops.py) of the same decoder, {batch} images per step, '
               f'{args.steps} timed steps after {args.warmup} warm-ups')
-    print(json.dumps({
+    _emit(json.dumps({
         'impl': 'reference', 'metric': f'images/sec ({args.mode})', 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -378,13 +378,24 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(args)
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints to fd 1 while the bench runs (NCCL's version
+    banner, for instance) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (line + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == '__main__':
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == 'reference':
         run_reference_arm(a)
     else:

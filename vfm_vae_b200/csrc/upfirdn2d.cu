@@ -248,12 +248,35 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
 // Requires 16-byte aligned rows on both sides; everything else goes to the tiled / generic kernels.
 struct BlurTaps { float f[4][4]; float fx[4], fy[4]; };
 
-template <class T, int PX, bool SEP>
+// 128- / 256-bit streaming accesses of NB bytes (16, 32 or 64)
+template <int NB> __device__ __forceinline__ void ldg_words(const void* p, uint32_t* w) {
+    if (NB == 16) { const uint4 u = ldg_stream(p); w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; }
+    else {
+#pragma unroll
+        for (int q = 0; q < NB / 32; q++)
+            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[8 * q]), "=r"(w[8 * q + 1]), "=r"(w[8 * q + 2]), "=r"(w[8 * q + 3]), "=r"(w[8 * q + 4]), "=r"(w[8 * q + 5]), "=r"(w[8 * q + 6]), "=r"(w[8 * q + 7])
+                         : "l"((const char*)p + 32 * q));
+    }
+}
+template <int NB> __device__ __forceinline__ void stg_words(void* p, const uint32_t* w) {
+    if (NB == 16) stg_stream(p, make_uint4(w[0], w[1], w[2], w[3]));
+    else {
+#pragma unroll
+        for (int q = 0; q < NB / 32; q++)
+            asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         :: "l"((char*)p + 32 * q), "r"(w[8 * q]), "r"(w[8 * q + 1]), "r"(w[8 * q + 2]), "r"(w[8 * q + 3]), "r"(w[8 * q + 4]), "r"(w[8 * q + 5]), "r"(w[8 * q + 6]), "r"(w[8 * q + 7]) : "memory");
+    }
+}
+
+// NC = output columns per thread (8, or 16 for fp16 rows aligned to 32 bytes: one 256-bit load / store per row)
+template <class T, int PX, bool SEP, int NC>
 __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& k, int cg_log2, int strips, int strip_rows) {
     constexpr int NL = PX;                 // halo columns on the left
     constexpr int NR = 3 - PX;             // halo columns on the right
     constexpr int EW = (int)(4 / sizeof(T));   // elements per 32-bit word (2 for fp16, 1 for fp32)
-    constexpr int NW = 8 / EW;             // words of the thread's own 8 columns
+    constexpr int NW = NC / EW;            // words of the thread's own NC columns
+    constexpr int NBYTES = NC * (int)sizeof(T);
     constexpr int WL = (NL + EW - 1) / EW, WR = (NR + EW - 1) / EW;    // halo words needed on each side
     constexpr int NE = WL + WR;            // halo words an edge lane fetches itself
     const int CG = 1 << cg_log2;           // column groups per row (power of two; groups past the row end idle)
@@ -268,7 +291,7 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     const int lmask = (CG < 32 ? CG : 32) - 1;
     const bool edge_l = (lane & lmask) == 0, edge_r = (lane & lmask) == lmask;
 
-    const int ox0 = cgi * 8;
+    const int ox0 = cgi * NC;
     const int oy_begin = strip * strip_rows;
     const int oy_end = min(oy_begin + strip_rows, p.out_h);
     const bool active = alive && ox0 < p.out_w && oy_begin < oy_end;      // produces outputs
@@ -283,11 +306,11 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     const bool lrelu = p.ep_enable && p.ep_act == 3;
     const float alpha = p.ep_alpha;
 
-    float acc[4][8];
+    float acc[4][NC];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 8; b++) acc[a][b] = acc_init;
+        for (int b = 0; b < NC; b++) acc[a][b] = acc_init;
 
     // input rows iy = oy - pady0 + ty  ->  rows [oy_begin - pady0, oy_end - 1 - pady0 + 3]
     const int nrows = feeds ? (oy_end - oy_begin + 3) : 0;
@@ -309,13 +332,17 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
 #pragma unroll
         for (int i = 0; i < WL; i++) keep[NW + i] = word_mask(ox0 - (WL - i) * EW);
 #pragma unroll
-        for (int i = 0; i < WR; i++) keep[NW + WL + i] = word_mask(ox0 + 8 + i * EW);
+        for (int i = 0; i < WR; i++) keep[NW + WL + i] = word_mask(ox0 + NC + i * EW);
 #pragma unroll
         for (int i = 0; i < NW + NE; i++) partial = partial || (keep[i] != 0xffffffffu);
     }
     // rows this thread may load: inside the image and not beyond the last row its strip needs
     const unsigned in_h_eff = feeds ? (unsigned)max(0, min(p.in_h, oy_end - p.pady0 + 3)) : 0u;
-    const bool own_ok = ox0 < p.in_w, own_hi_ok = ox0 + 4 < p.in_w;
+    // the aligned vector(s) of the own columns that contain at least one valid element
+    bool own_ok[NBYTES / 16 >= 2 && NBYTES == 16 * 2 && sizeof(T) == 4 ? 2 : 1];
+    constexpr int NSEG = (sizeof(T) == 4 && NBYTES == 32) ? 2 : 1;          // fp32 rows are only 16-byte aligned: two 128-bit loads
+    own_ok[0] = ox0 < p.in_w;
+    if (NSEG == 2) own_ok[NSEG - 1] = ox0 + 4 < p.in_w;
     bool el_ok[WL > 0 ? WL : 1], er_ok[WR > 0 ? WR : 1];
 #pragma unroll
     for (int i = 0; i < WL; i++) el_ok[i] = edge_l && keep[NW + i] != 0u;
@@ -328,19 +355,20 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
 #pragma unroll
         for (int i = 0; i < NW + NE; i++) w[i] = 0u;
         const bool ok = (unsigned)iy_f < in_h_eff;
-        if (ok && own_ok) {
-            const uint4 u0 = ldg_stream(rp_f);
-            w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w;
+        if (NSEG == 1) {
+            if (ok && own_ok[0]) ldg_words<NBYTES>(rp_f, w);
+        } else {
+            if (ok && own_ok[0]) ldg_words<16>(rp_f, w);
+            if (ok && own_ok[NSEG - 1]) ldg_words<16>(rp_f + 4, w + 4);
         }
-        if (NW == 8 && ok && own_hi_ok) { const uint4 u1 = ldg_stream(rp_f + 4); w[NW - 4] = u1.x; w[NW - 3] = u1.y; w[NW - 2] = u1.z; w[NW - 1] = u1.w; }
 #pragma unroll
         for (int i = 0; i < WL; i++) if (ok && el_ok[i]) w[NW + i] = __ldg((const uint32_t*)(rp_f - (WL - i) * EW));
 #pragma unroll
-        for (int i = 0; i < WR; i++) if (ok && er_ok[i]) w[NW + WL + i] = __ldg((const uint32_t*)(rp_f + 8 + i * EW));
+        for (int i = 0; i < WR; i++) if (ok && er_ok[i]) w[NW + WL + i] = __ldg((const uint32_t*)(rp_f + NC + i * EW));
         rp_f += p.ish;
         iy_f++;
     };
-    // in[0..10] = input columns ox0 - PX .. ox0 - PX + 10, from the thread's own words and its neighbours'
+    // in[0 .. NC+2] = input columns ox0 - PX .. ox0 - PX + NC + 2, from the thread's own words and its neighbours'
     auto expand = [&](uint32_t* w, float* in) {
         if (partial) {          // thread-constant; lanes whose vectors lie wholly inside the row skip the masking
 #pragma unroll
@@ -351,7 +379,7 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
         for (int i = 0; i < WL; i++) { const uint32_t t = __shfl_up_sync(0xffffffffu, w[NW - WL + i], 1); hl[i] = edge_l ? w[NW + i] : t; }
 #pragma unroll
         for (int i = 0; i < WR; i++) { const uint32_t t = __shfl_down_sync(0xffffffffu, w[i], 1); hr[i] = edge_r ? w[NW + WL + i] : t; }
-        float own[8], left[WL * EW > 0 ? WL * EW : 1], right[WR * EW > 0 ? WR * EW : 1];
+        float own[NC], left[WL * EW > 0 ? WL * EW : 1], right[WR * EW > 0 ? WR * EW : 1];
         if (EW == 2) {
 #pragma unroll
             for (int i = 0; i < NW; i++) { const float2 t = __half22float2(*(const __half2*)&w[i]); own[2 * i] = t.x; own[2 * i + 1] = t.y; }
@@ -370,24 +398,24 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
 #pragma unroll
         for (int i = 0; i < NL; i++) in[i] = left[WL * EW - NL + i];
 #pragma unroll
-        for (int i = 0; i < 8; i++) in[NL + i] = own[i];
+        for (int i = 0; i < NC; i++) in[NL + i] = own[i];
 #pragma unroll
-        for (int i = 0; i < NR; i++) in[NL + 8 + i] = right[i];
+        for (int i = 0; i < NR; i++) in[NL + NC + i] = right[i];
     };
     // the fused addend (noise) of an output row, fetched two rows before it is needed (running cursor oy_a / ap)
     int oy_a = oy_begin;
     const float* ap = p.add ? p.add + (int64_t)n * p.add_sn + (int64_t)oy_begin * p.add_sh + ox0 : nullptr;
-    const bool full_store = ox0 + 8 <= p.out_w;
+    const bool full_store = ox0 + NC <= p.out_w;
     auto fetch_add = [&](float* a) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = 0.f;
+        for (int i = 0; i < NC; i++) a[i] = 0.f;
         if (active && oy_a < oy_end) {
             if (add_vec && full_store) {
-                const float4 a0 = __ldg((const float4*)ap), a1 = __ldg((const float4*)ap + 1);
-                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+                for (int q = 0; q < NC / 4; q++) { const float4 t = __ldg((const float4*)ap + q); a[4 * q] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w; }
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) a[i] = __ldg(ap + i);
+                for (int i = 0; i < NC; i++) if (ox0 + i < p.out_w) a[i] = __ldg(ap + i);
             }
         }
         ap += p.add_sh;
@@ -401,29 +429,30 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
         if ((unsigned)orow < emit_rows) {
             if (p.add) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = fmaf(addv[i], eg, o[i]);
+                for (int i = 0; i < NC; i++) o[i] = fmaf(addv[i], eg, o[i]);
             }
             if (lrelu) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = fmaxf(o[i], o[i] * alpha);
+                for (int i = 0; i < NC; i++) o[i] = fmaxf(o[i], o[i] * alpha);
             }
             if (has_clamp) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) o[i] = fminf(fmaxf(o[i], -p.ep_clamp), p.ep_clamp);
+                for (int i = 0; i < NC; i++) o[i] = fminf(fmaxf(o[i], -p.ep_clamp), p.ep_clamp);
             }
             if (full_store) {
+                uint32_t w[NW];
                 if (EW == 2) {
-                    union { uint4 u; __half2 h[4]; } t;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) t.h[i] = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
-                    stg_stream(op, t.u);
+                    for (int i = 0; i < NW; i++) { const __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]); w[i] = *(const uint32_t*)&h; }
                 } else {
-                    stg_stream(op, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
-                    stg_stream(op + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+#pragma unroll
+                    for (int i = 0; i < NW; i++) w[i] = __float_as_uint(o[i]);
                 }
+                if (NSEG == 1) stg_words<NBYTES>(op, w);
+                else { stg_words<16>(op, w); stg_words<16>(op + 4, w + 4); }
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; i++) if (ox0 + i < p.out_w) op[i] = from_acc<T, float>(o[i]);
+                for (int i = 0; i < NC; i++) if (ox0 + i < p.out_w) op[i] = from_acc<T, float>(o[i]);
             }
         }
         op += p.osh;
@@ -434,7 +463,7 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     // A ring of four row vectors is kept in flight (a slot is refilled with row r + 4 as soon as row r has been unpacked)
     // and the addend of an output row is fetched two rows before it is needed.
     uint32_t wq[4][NW + NE];
-    float addq[2][8];
+    float addq[2][NC];
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) fetch(wq[rr]);
     if (p.add) { fetch_add(addq[1]); fetch_add(addq[0]); }
@@ -442,39 +471,37 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     for (int r0 = 0; r0 < nrows_warp; r0 += 4) {
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
-            float in[11];
+            float in[NC + 3];
             expand(wq[rr], in);
             fetch(wq[rr]);
             if (SEP) {
-                float h[8];
+                float h[NC];
 #pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = k.fx[0] * in[i] + k.fx[1] * in[i + 1] + k.fx[2] * in[i + 2] + k.fx[3] * in[i + 3];
+                for (int i = 0; i < NC; i++) h[i] = k.fx[0] * in[i] + k.fx[1] * in[i + 1] + k.fx[2] * in[i + 2] + k.fx[3] * in[i + 3];
 #pragma unroll
                 for (int ty = 0; ty < 4; ty++)
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(k.fy[ty], h[i], acc[(rr - ty) & 3][i]);
+                    for (int i = 0; i < NC; i++) acc[(rr - ty) & 3][i] = fmaf(k.fy[ty], h[i], acc[(rr - ty) & 3][i]);
             } else {
 #pragma unroll
                 for (int ty = 0; ty < 4; ty++)
 #pragma unroll
                     for (int tx = 0; tx < 4; tx++)
 #pragma unroll
-                        for (int i = 0; i < 8; i++) acc[(rr - ty) & 3][i] = fmaf(k.f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
+                        for (int i = 0; i < NC; i++) acc[(rr - ty) & 3][i] = fmaf(k.f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
             }
             // output row (r - 3) used accumulator slot (rr - 3) & 3 == (rr + 1) & 3
             const bool emitted = orow >= 0;
             emit(acc[(rr + 1) & 3], addq[rr & 1]);
             if (p.add && emitted) fetch_add(addq[rr & 1]);
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[(rr + 1) & 3][i] = acc_init;
+            for (int i = 0; i < NC; i++) acc[(rr + 1) & 3][i] = acc_init;
         }
     }
 }
 
-template <class T, int PX>
-__global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+__device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps& k) {
     // correlation taps with the gain folded in (fp32 product, like the reference's scaled filter tensor); missing taps = 0
-    BlurTaps k;
 #pragma unroll
     for (int ty = 0; ty < 4; ty++)
 #pragma unroll
@@ -488,38 +515,56 @@ __global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg_l
             k.f[ty][tx] = v;
         }
     // rank-1 test: f == fy (x) fx with fx = pivot row / pivot, fy = pivot column
-    bool sep;
-    {
-        int pi = 0, pj = 0; float best = -1.f;
+    int pi = 0, pj = 0; float best = -1.f;
 #pragma unroll
-        for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < 4; ty++)
 #pragma unroll
-            for (int tx = 0; tx < 4; tx++) if (fabsf(k.f[ty][tx]) > best) { best = fabsf(k.f[ty][tx]); pi = ty; pj = tx; }
-        float piv = 1.f, prow[4], pcol[4];
+        for (int tx = 0; tx < 4; tx++) if (fabsf(k.f[ty][tx]) > best) { best = fabsf(k.f[ty][tx]); pi = ty; pj = tx; }
+    float piv = 1.f, prow[4], pcol[4];
 #pragma unroll
-        for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < 4; ty++)
 #pragma unroll
-            for (int tx = 0; tx < 4; tx++) {
-                if (ty == pi && tx == pj) piv = k.f[ty][tx];
-                if (ty == pi) prow[tx] = k.f[ty][tx];
-                if (tx == pj) pcol[ty] = k.f[ty][tx];
-            }
-        const float inv = (best > 0.f) ? 1.f / piv : 0.f;
-        sep = best > 0.f;
+        for (int tx = 0; tx < 4; tx++) {
+            if (ty == pi && tx == pj) piv = k.f[ty][tx];
+            if (ty == pi) prow[tx] = k.f[ty][tx];
+            if (tx == pj) pcol[ty] = k.f[ty][tx];
+        }
+    const float inv = (best > 0.f) ? 1.f / piv : 0.f;
+    bool sep = best > 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { k.fx[i] = prow[i] * inv; k.fy[i] = pcol[i]; }
+    for (int i = 0; i < 4; i++) { k.fx[i] = prow[i] * inv; k.fy[i] = pcol[i]; }
 #pragma unroll
-        for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < 4; ty++)
 #pragma unroll
-            for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(k.f[ty][tx] - k.fy[ty] * k.fx[tx]) <= 1e-6f * best);
-    }
-    if (sep) blur_body<T, PX, true>(p, k, cg_log2, strips, strip_rows);
-    else blur_body<T, PX, false>(p, k, cg_log2, strips, strip_rows);
+        for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(k.f[ty][tx] - k.fy[ty] * k.fx[tx]) <= 1e-6f * best);
+    return sep;
+}
+
+template <class T, int PX>
+__global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+    BlurTaps k;
+    if (blur_taps(p, k)) blur_body<T, PX, true, 8>(p, k, cg_log2, strips, strip_rows);
+    else blur_body<T, PX, false, 8>(p, k, cg_log2, strips, strip_rows);
+}
+// 16 columns per thread (fp16 rows aligned to 32 bytes): half the per-row bookkeeping per output
+template <int PX>
+__global__ void __launch_bounds__(128, 3) upfirdn2d_blur16(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+    BlurTaps k;
+    if (blur_taps(p, k)) blur_body<__half, PX, true, 16>(p, k, cg_log2, strips, strip_rows);
+    else blur_body<__half, PX, false, 16>(p, k, cg_log2, strips, strip_rows);
 }
 
 template <class T>
 int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
-    const int groups = ceil_div(a.out_w, 8);
+    // 16 columns per thread when the rows are fp16, 32-byte aligned and wide enough to keep a warp busy
+    bool wide = false;
+    if (sizeof(T) == 2) {
+        auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+        wide = al32(a.x) && al32(a.y) && (a.ish % 16) == 0 && (a.isc % 16) == 0 && (a.isn % 16) == 0 &&
+               (a.osh % 16) == 0 && (a.osc % 16) == 0 && (a.osn % 16) == 0 && a.out_w >= 256;   // measured: pays off only for full-warp rows
+    }
+    const int nc = wide ? 16 : 8;
+    const int groups = ceil_div(a.out_w, nc);
     int cg_log2 = 0;
     while ((1 << cg_log2) < groups) cg_log2++;
     // strips: enough threads to fill the machine, few enough that the 3-row halo stays cheap
@@ -533,6 +578,15 @@ int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     KernelTimer timer("upfirdn2d_blur", stream, 0.0,
                       ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T) + (double)a.fw * a.fh * 4,
                       "w%dc%d", a.out_w, a.channels);
+    if (wide) {
+        switch (a.padx0) {
+            case 0: upfirdn2d_blur16<0><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+            case 1: upfirdn2d_blur16<1><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+            case 2: upfirdn2d_blur16<2><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+            default: upfirdn2d_blur16<3><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+        }
+        return launch_status("upfirdn2d_blur16");
+    }
     switch (a.padx0) {
         case 0: upfirdn2d_blur<T, 0><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
         case 1: upfirdn2d_blur<T, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;

@@ -130,7 +130,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int BN = 128, BK = 64, STAGES = 3;   // wgrad tile (M = 128 out channels, N = in channels)
+constexpr int BK = 64;
 constexpr float kLoScale = 2048.f;     // the lo term of the fp16 split is stored scaled by 2^11
 
 // ------------------------------------------------------------------------------------------------ conv / data gradient
@@ -673,33 +673,56 @@ constexpr int WBOX_BYTES = WK * 128;        // one [64 px][64 ch] box = 8 KB
 constexpr int WOP_BYTES = 2 * WBOX_BYTES;   // 128 channels
 
 struct WgTcArgs {
-    int tw, th, tn;              // pixel tile (tw*th*tn == 64) in the x grid
+    int tw, th, tn;              // pixel tile (tw*th*tn == 64)
     int tiles_w, tiles_h, tiles_n;
     int ksplit, ntaps;
     int tap_ay[9], tap_ax[9];    // dz coordinate = q*sd + tap_a
     int tap_widx[9];
     int sd;
     int O, I, KK;
+    int ib;                      // I / 128
+    int jobs_per_o;              // column-block pairs per 128 output channels
     float* dw;                   // [O][I][KK] fp32, accumulated with atomics
     const float* rowscale;       // a[o]
     const float* gscale;         // device scalar multiplied into the result, or NULL
 };
 
+// A CTA accumulates D[128 out-ch][up to 256 columns] over its share of the pixel tiles (split-K).  The 256 columns are two
+// "column blocks" (tap, 128 input channels):
+//   sd == 1: the tap shift is applied to the x operand (B), the dz tile (A) is the same for every tap, so the two blocks may
+//            belong to different taps -- also 128-channel layers get N = 256 (shared-memory and L2 traffic per MMA drop by 25%);
+//   sd == 2: the shift / stride 2 sits on the dz operand, both blocks share the tap and cover 256 input channels.
 template <bool SPLIT>
-__global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                       const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, WgTcArgs p) {
-    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * 2 * WOP_BYTES;
-    constexpr int TMEM_COLS = SPLIT ? 2 * BN : BN;
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                          const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, WgTcArgs p) {
+    constexpr int A_OP = WOP_BYTES, B_OP = 2 * WOP_BYTES;                    // 16 KB + 32 KB
+    constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_OP + B_OP);
+    constexpr int NST = (192 * 1024) / STAGE_BYTES;                          // 4 (fp16) / 2 (split)
+    constexpr int TMEM_COLS = SPLIT ? 512 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
+    uint64_t* full_bar = (uint64_t*)(smem + NST * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* accum_bar = empty_bar + NST;
     uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o0 = blockIdx.x * 128, i0 = blockIdx.y * 128;
-    const int tap = blockIdx.z / p.ksplit, ks = blockIdx.z - tap * p.ksplit;
+    // job -> output-channel block and column blocks
+    const int o0 = (blockIdx.x / p.jobs_per_o) * 128;
+    const int jc = blockIdx.x % p.jobs_per_o;
+    const int ks = blockIdx.y;
+    int btap[2], bi0[2], nb;
+    if (p.sd == 1) {
+        const int cb0 = 2 * jc, ncb = p.ntaps * p.ib;
+        nb = (cb0 + 1 < ncb) ? 2 : 1;
+        for (int j = 0; j < 2; j++) { const int cb = (cb0 + j < ncb) ? cb0 + j : cb0; btap[j] = cb / p.ib; bi0[j] = (cb % p.ib) * 128; }
+    } else {
+        const int pairs = (p.ib + 1) / 2;
+        const int tap = jc / pairs, pr = jc % pairs;
+        nb = (2 * pr + 1 < p.ib) ? 2 : 1;
+        btap[0] = btap[1] = tap;
+        bi0[0] = 2 * pr * 128; bi0[1] = (nb == 2) ? bi0[0] + 128 : bi0[0];
+    }
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     const int t_begin = (int)((long long)total_tiles * ks / p.ksplit), t_end = (int)((long long)total_tiles * (ks + 1) / p.ksplit);
     const int iters = t_end - t_begin;
@@ -708,7 +731,7 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NST; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
@@ -723,51 +746,58 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
 
     if (warp == 0) {
         if (lane == 0) {
+            const uint32_t tx_bytes = (SPLIT ? 2 : 1) * (A_OP + nb * WOP_BYTES);
             for (int it = 0; it < iters; it++) {
-                const int s = it % STAGES;
-                const uint32_t phs = (it / STAGES) & 1;
+                const int s = it % NST;
+                const uint32_t phs = (it / NST) & 1;
                 mbar_wait(&empty_bar[s], phs ^ 1);
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                mbar_expect_tx(&full_bar[s], tx_bytes);
                 int t = t_begin + it;
                 const int tile_w = t % p.tiles_w; t /= p.tiles_w;
                 const int tile_h = t % p.tiles_h; t /= p.tiles_h;
                 const int n0 = t * p.tn, h0 = tile_h * p.th, w0 = tile_w * p.tw;
-                const int aw = w0 * p.sd + p.tap_ax[tap], ah = h0 * p.sd + p.tap_ay[tap];
+                // sd == 1: tiles walk the dz grid, x is read at (z - tap_a);  sd == 2: tiles walk the x grid, dz at (q*2 + tap_a)
+                const int aw = (p.sd == 1) ? w0 : w0 * p.sd + p.tap_ax[btap[0]], ah = (p.sd == 1) ? h0 : h0 * p.sd + p.tap_ay[btap[0]];
                 uint8_t* sa = smem + s * STAGE_BYTES;
                 tma_load_4d(sa, &tmA, &full_bar[s], o0, aw, ah, n0);
                 tma_load_4d(sa + WBOX_BYTES, &tmA, &full_bar[s], o0 + 64, aw, ah, n0);
-                tma_load_4d(sa + WOP_BYTES, &tmB, &full_bar[s], i0, w0, h0, n0);
-                tma_load_4d(sa + WOP_BYTES + WBOX_BYTES, &tmB, &full_bar[s], i0 + 64, w0, h0, n0);
                 if (SPLIT) {
-                    uint8_t* sl = sa + 2 * WOP_BYTES;
-                    tma_load_4d(sl, &tmAlo, &full_bar[s], o0, aw, ah, n0);
-                    tma_load_4d(sl + WBOX_BYTES, &tmAlo, &full_bar[s], o0 + 64, aw, ah, n0);
-                    tma_load_4d(sl + WOP_BYTES, &tmBlo, &full_bar[s], i0, w0, h0, n0);
-                    tma_load_4d(sl + WOP_BYTES + WBOX_BYTES, &tmBlo, &full_bar[s], i0 + 64, w0, h0, n0);
+                    tma_load_4d(sa + A_OP + B_OP, &tmAlo, &full_bar[s], o0, aw, ah, n0);
+                    tma_load_4d(sa + A_OP + B_OP + WBOX_BYTES, &tmAlo, &full_bar[s], o0 + 64, aw, ah, n0);
+                }
+                for (int j = 0; j < nb; j++) {
+                    const int bw = (p.sd == 1) ? w0 - p.tap_ax[btap[j]] : w0, bh = (p.sd == 1) ? h0 - p.tap_ay[btap[j]] : h0;
+                    uint8_t* sb = sa + A_OP + j * WOP_BYTES;
+                    tma_load_4d(sb, &tmB, &full_bar[s], bi0[j], bw, bh, n0);
+                    tma_load_4d(sb + WBOX_BYTES, &tmB, &full_bar[s], bi0[j] + 64, bw, bh, n0);
+                    if (SPLIT) {
+                        tma_load_4d(sb + A_OP + B_OP, &tmBlo, &full_bar[s], bi0[j], bw, bh, n0);
+                        tma_load_4d(sb + A_OP + B_OP + WBOX_BYTES, &tmBlo, &full_bar[s], bi0[j] + 64, bw, bh, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_mnmajor(128, 128);
+            const uint32_t idesc = make_idesc_f16_mnmajor(128, 128 * nb);
             for (int it = 0; it < iters; it++) {
-                const int s = it % STAGES;
-                const uint32_t phs = (it / STAGES) & 1;
+                const int s = it % NST;
+                const uint32_t phs = (it / NST) & 1;
                 mbar_wait(&full_bar[s], phs);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t adesc = make_mnmajor_sw128_desc(sa, WBOX_BYTES);
-                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + WOP_BYTES, WBOX_BYTES);
-                const uint64_t adesc_lo = make_mnmajor_sw128_desc(sa + 2 * WOP_BYTES, WBOX_BYTES);
-                const uint64_t bdesc_lo = make_mnmajor_sw128_desc(sa + 3 * WOP_BYTES, WBOX_BYTES);
+                const uint64_t bdesc = make_mnmajor_sw128_desc(sa + A_OP, WBOX_BYTES);
+                const uint64_t adesc_lo = make_mnmajor_sw128_desc(sa + A_OP + B_OP, WBOX_BYTES);
+                const uint64_t bdesc_lo = make_mnmajor_sw128_desc(sa + 2 * A_OP + B_OP, WBOX_BYTES);
 #pragma unroll
                 for (int k = 0; k < WK / 16; k++) {
                     const uint64_t ko = (uint64_t)((k * 16 * 128) >> 4);     // 16 pixel rows of 128 bytes
                     const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
                     umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, first);
                     if (SPLIT) {
-                        umma_f16(tmem_base + BN, adesc + ko, bdesc_lo + ko, idesc, first);
-                        umma_f16(tmem_base + BN, adesc_lo + ko, bdesc + ko, idesc, 1u);
+                        umma_f16(tmem_base + 256, adesc + ko, bdesc_lo + ko, idesc, first);
+                        umma_f16(tmem_base + 256, adesc_lo + ko, bdesc + ko, idesc, 1u);
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -778,21 +808,23 @@ __global__ void __launch_bounds__(192) wgrad_tc_kernel(const __grid_constant__ C
         const int lg = warp & 3;
         const int o = o0 + lg * 32 + lane;
         const float rs = p.rowscale[o] * (p.gscale ? *p.gscale : 1.f);
-        float* dst = p.dw + ((size_t)o * p.I + i0) * p.KK + p.tap_widx[tap];
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        for (int j = 0; j < nb; j++) {
+            float* dst = p.dw + ((size_t)o * p.I + bi0[j]) * p.KK + p.tap_widx[btap[j]];
 #pragma unroll 1
-        for (int j = 0; j < BN / 16; j++) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 16), v);
-            if (SPLIT) {
-                float v1[16];
-                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + j * 16), v1);
+            for (int q = 0; q < 128 / 16; q++) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 128 + q * 16), v);
+                if (SPLIT) {
+                    float v1[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + j * 128 + q * 16), v1);
 #pragma unroll
-                for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
+                    for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
+                }
+#pragma unroll
+                for (int c = 0; c < 16; c++) atomicAdd(dst + (size_t)(q * 16 + c) * p.KK, v[c] * rs);
             }
-#pragma unroll
-            for (int c = 0; c < 16; c++) atomicAdd(dst + (size_t)(j * 16 + c) * p.KK, v[c] * rs);
         }
         tc_fence_before();
     }
@@ -1126,15 +1158,19 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
                  float* dweight, cudaStream_t stream) {
     const int N = d.batch, I = d.in_channels, O = d.out_channels;
     WgTcArgs a;
-    pick_wtile(d.in_h, d.in_w, a.tw, a.th, a.tn);
-    a.tiles_w = ceil_div(d.in_w, a.tw); a.tiles_h = ceil_div(d.in_h, a.th); a.tiles_n = ceil_div(N, a.tn);
     a.ntaps = s.taps.ntaps; a.sd = s.sd;
     for (int t = 0; t < a.ntaps; t++) { a.tap_ay[t] = -s.taps.off_y[t]; a.tap_ax[t] = -s.taps.off_x[t]; a.tap_widx[t] = s.taps.widx[t]; }
     a.O = O; a.I = I; a.KK = d.kh * d.kw;
     a.dw = dweight; a.rowscale = rowscale; a.gscale = gscale;
+    // sd == 1: the pixel tiles walk the dz grid (== x grid for the padded stride-1 conv) and the shift is on x
+    const int gw = (s.sd == 1) ? s.zw : d.in_w, gh = (s.sd == 1) ? s.zh : d.in_h;
+    pick_wtile(gh, gw, a.tw, a.th, a.tn);
+    a.tiles_w = ceil_div(gw, a.tw); a.tiles_h = ceil_div(gh, a.th); a.tiles_n = ceil_div(N, a.tn);
     const int tiles = a.tiles_w * a.tiles_h * a.tiles_n;
-    const int base = (O / 128) * (I / 128) * a.ntaps;
-    a.ksplit = max(1, min(tiles, ceil_div(2 * kNumSMs, base)));
+    a.ib = I / 128;
+    a.jobs_per_o = (s.sd == 1) ? ceil_div(a.ntaps * a.ib, 2) : a.ntaps * ceil_div(a.ib, 2);
+    const int jobs = (O / 128) * a.jobs_per_o;
+    a.ksplit = max(1, min(tiles, (2 * kNumSMs + jobs / 2) / jobs));
     CUtensorMap maps[4];
     uint64_t adims[4] = {(uint64_t)O, (uint64_t)s.zw, (uint64_t)s.zh, (uint64_t)N};
     uint32_t abox[4] = {64u, (uint32_t)(a.tw * s.sd), (uint32_t)(a.th * s.sd), (uint32_t)a.tn};
@@ -1145,9 +1181,9 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     st = encode_map(&maps[1], w.xt, 4, bdims, bbox, nullptr); if (st) return st;
     st = encode_map(&maps[2], f32 ? w.act_lo : w.act, 4, adims, abox, astr); if (st) return st;
     st = encode_map(&maps[3], f32 ? w.xt_lo : w.xt, 4, bdims, bbox, nullptr); if (st) return st;
-    dim3 grid(O / 128, I / 128, a.ntaps * a.ksplit);
-    if (grid.z > 65535) { set_error("tcgen05 wgrad: grid too large"); return VFM_ERR_INVALID; }
-    const size_t smem = (size_t)STAGES * (f32 ? 2 : 1) * 2 * WOP_BYTES + 1024 + 256;
+    dim3 grid(jobs, a.ksplit, 1);
+    if (grid.y > 65535) { set_error("tcgen05 wgrad: grid too large"); return VFM_ERR_INVALID; }
+    const size_t smem = (size_t)192 * 1024 + 1024 + 256;
     const double flops = 2.0 * N * d.in_h * d.in_w * (double)O * I * a.ntaps;
     KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0, "i%do%dh%ds%d", I, O, d.in_h, s.sd);
     if (f32) {

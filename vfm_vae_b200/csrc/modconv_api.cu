@@ -14,6 +14,8 @@ int run_conv(int dtype, const ConvArgs& a, cudaStream_t stream);
 int run_wgrad(int dtype, WgradArgs a, cudaStream_t stream);
 int run_gsum(int dtype, const void* dy, const void* y, const float* noise, int64_t noise_sn, const float* dcoefs, int planes, int O, int HW, float* g, cudaStream_t stream);
 int run_dnoise(int dtype, const void* dy, int N, int O, int HW, int per_sample, float* dnoise, cudaStream_t stream);
+int run_gsum_dnoise(int dtype, const void* dy, const void* y, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
+                    float* g, float* dnoise, int dnoise_per_sample, cudaStream_t stream);
 int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream);
 int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, const float* dcoefs, const float* iscale, const float* wsq, int N, int O, int I, int demod, cudaStream_t stream);
 
@@ -25,7 +27,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
                       const float* noise, int64_t noise_sn, const Epilogue& ep, const float* x_scale, const float* x_shift,
                       void* ws, size_t ws_bytes, cudaStream_t stream);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
-int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
+int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
                        void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 static int validate(const vfm_modconv_desc& d) {
@@ -50,8 +52,9 @@ static int validate(const vfm_modconv_desc& d) {
 
 static int call_upfirdn(int dtype, const void* in, void* out, const float* f, int fw, int fh, int up, int down, int px0, int py0, int flip, float gain,
                         int N, int C, int ih, int iw, int oh, int ow, const float* add, int64_t add_sn, cudaStream_t stream, int in_pitch = 0,
-                        const Epilogue* ep = nullptr) {
+                        const Epilogue* ep = nullptr, int out_pitch = 0) {
     if (in_pitch == 0) in_pitch = iw;
+    if (out_pitch == 0) out_pitch = ow;
     vfm_upfirdn2d_params u;
     u.x = in; u.f = f; u.y = out; u.dtype = dtype;
     u.upx = u.upy = up; u.downx = u.downy = down; u.padx0 = px0; u.pady0 = py0; u.flip = flip; u.gain = gain;
@@ -59,7 +62,7 @@ static int call_upfirdn(int dtype, const void* in, void* out, const float* f, in
     u.in_stride_w = 1; u.in_stride_h = in_pitch; u.in_stride_c = (int64_t)ih * in_pitch; u.in_stride_n = (int64_t)C * ih * in_pitch;
     u.fw = fw; u.fh = fh; u.f_stride_w = 1; u.f_stride_h = fw;
     u.out_w = ow; u.out_h = oh;
-    u.out_stride_w = 1; u.out_stride_h = ow; u.out_stride_c = (int64_t)oh * ow; u.out_stride_n = (int64_t)C * oh * ow;
+    u.out_stride_w = 1; u.out_stride_h = out_pitch; u.out_stride_c = (int64_t)oh * out_pitch; u.out_stride_n = (int64_t)C * oh * out_pitch;
     u.add = add; u.add_stride_h = ow; u.add_stride_n = add_sn;
     u.ep_enable = 0; u.ep_act = 1; u.ep_alpha = 0; u.ep_gain = 1; u.ep_clamp = -1; u.ep_bias = nullptr;
     if (ep && ep->enable) { u.ep_enable = 1; u.ep_act = ep->act; u.ep_alpha = ep->alpha; u.ep_gain = ep->gain; u.ep_clamp = ep->clamp; u.ep_bias = ep->bias; }
@@ -185,20 +188,28 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     k.d = p->dcoefs;
     Stage1 s = make_stage1(d);
     void* dz = nullptr;
-    if (d.up == 2) dz = cv.take<char>((size_t)N * O * s.zh * s.zw * esize(d.dtype));
+    // tensor-core path: rows of the blur-backward output are padded to 32 bytes so that the streaming blur kernel writes it
+    const int dz_pitch = (d.up == 2 && use_tc(d)) ? ((s.zw + 15) & ~15) : s.zw;
+    if (d.up == 2) dz = cv.take<char>((size_t)N * O * s.zh * (size_t)((s.zw + 15) & ~15) * esize(d.dtype));
     float* g = cv.take<float>((size_t)N * O);
     float* dsum = cv.take<float>((size_t)N * I);
     st = compute_coefs(d, p->weight, p->styles, k, nullptr, p->dcoefs, stream); if (st) return st;
 
     const int HWo = d.out_h * d.out_w;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)HWo : 0;
-    if (d.demodulate && (p->dweight || p->dstyles)) {
-        st = run_gsum(d.dtype, p->dy, p->y, p->noise, noise_sn, p->dcoefs, N * O, O, HWo, g, stream); if (st) return st;
-    }
-    if (p->dnoise) {
-        int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
-        VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
-        st = run_dnoise(d.dtype, p->dy, N, O, HWo, per_sample, p->dnoise, stream); if (st) return st;
+    {
+        const bool need_g = d.demodulate && (p->dweight || p->dstyles);
+        const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
+        if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
+        // one pass over dy for both reductions where the tensors allow it
+        st = (need_g || p->dnoise) ? run_gsum_dnoise(d.dtype, p->dy, p->y, p->noise, noise_sn, p->dcoefs, N, O, HWo, need_g ? g : nullptr, p->dnoise, per_sample, stream)
+                                   : VFM_OK;
+        if (st == VFM_ERR_NO_KERNEL) {
+            st = VFM_OK;
+            if (need_g) { st = run_gsum(d.dtype, p->dy, p->y, p->noise, noise_sn, p->dcoefs, N * O, O, HWo, g, stream); if (st) return st; }
+            if (p->dnoise) { st = run_dnoise(d.dtype, p->dy, N, O, HWo, per_sample, p->dnoise, stream); if (st) return st; }
+        }
+        if (st) return st;
     }
 
     // gradient w.r.t. the stage-1 output
@@ -206,7 +217,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     if (d.up == 2) {
         // backward of upfirdn2d (torch_utils/ops/upfirdn2d.py:251-269): swap up/down, flip the filter, same gain
         st = call_upfirdn(d.dtype, p->dy, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
-                          N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream);
+                          N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream, 0, nullptr, dz_pitch);
         if (st) return st;
         dzp = dz;
     }
@@ -220,7 +231,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
         if (st) return st;
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
-        st = tc_stage1_backward(d, s, dzp, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
+        st = tc_stage1_backward(d, s, dzp, d.up == 2 ? dz_pitch : 0, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
                                 (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
         if (st) return st;
     } else {

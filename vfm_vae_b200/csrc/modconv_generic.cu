@@ -354,6 +354,68 @@ __global__ void __launch_bounds__(256) dnoise_kernel(const T* __restrict__ dy, i
     atomicAdd(&dnoise[(per_sample ? (size_t)blockIdx.z * HW : 0) + pix], (float)s);
 }
 
+// Both reductions of the backward that read the whole dy in ONE pass (16-byte loads, 8 vectors in flight per thread):
+//   g[n,o] += (1/d[n,o]) * sum_p dy*(y - noise)          dnoise[(n,)p] += sum_o dy
+// A CTA owns one sample and a chunk of 1024 pixels and walks over the channels: a thread keeps its 8 pixels' dnoise sums
+// in registers, the per-channel partials of g are reduced by warp shuffles into a shared-memory array and leave as
+// one atomic per (CTA, channel).  Requires HW % 8 == 0 and 16-byte aligned tensors; otherwise the two simple kernels above run.
+template <class T>
+__global__ void __launch_bounds__(128) gsum_dnoise_kernel(const T* __restrict__ dy, const T* __restrict__ y, const float* __restrict__ noise, int64_t noise_sn,
+                                                          const float* __restrict__ dcoefs, int O, int HW, float* g, float* dnoise, int64_t dnoise_sn) {
+    constexpr int V = 16 / (int)sizeof(T);              // elements per vector: a thread covers 8 pixels = 8/V vectors
+    constexpr int NV = 8 / V;
+    extern __shared__ float s_g[];                       // [O]
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * 1024 + threadIdx.x * 8;
+    const bool live = p0 < HW;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) s_g[o] = 0.f;
+    __syncthreads();
+    float nz[8], dn[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { nz[i] = (noise && live) ? noise[(size_t)n * noise_sn + p0 + i] : 0.f; dn[i] = 0.f; }
+    const T* dyp = dy + (size_t)n * O * HW + p0;
+    const T* yp = y ? y + (size_t)n * O * HW + p0 : nullptr;
+    const int lane = threadIdx.x & 31;
+    for (int o0 = 0; o0 < O; o0 += 4) {
+        uint4 a[4][NV], b[4][NV];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const bool ok = live && o0 + k < O;
+                a[k][q] = ok ? ldg_stream(dyp + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+                b[k][q] = (ok && yp) ? ldg_stream(yp + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float part = 0.f;
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const T* av = (const T*)&a[k][q];
+                const T* bv = (const T*)&b[k][q];
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    const float d = to_acc(av[e]);
+                    dn[q * V + e] += d;
+                    part = fmaf(d, to_acc(bv[e]) - nz[q * V + e], part);
+                }
+            }
+            if (g) {
+                part = warp_sum(part);
+                if (lane == 0 && o0 + k < O) atomicAdd(&s_g[o0 + k], part);
+            }
+        }
+    }
+    if (dnoise && live) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) atomicAdd(&dnoise[(size_t)n * dnoise_sn + p0 + i], dn[i]);
+    }
+    if (g) {
+        __syncthreads();
+        for (int o = threadIdx.x; o < O; o += blockDim.x) atomicAdd(&g[(size_t)n * O + o], s_g[o] / dcoefs[(size_t)n * O + o]);
+    }
+}
+
 // dW[o,i,k] = M[o,i,k] - a[o]^2 W[o,i,k] sum_n h[n,o] s'[n,i]^2,  h = g d^3          (thread per (o,i))
 __global__ void dw_fix_kernel(float* dw, const float* __restrict__ w, const float* __restrict__ a, const float* __restrict__ g,
                               const float* __restrict__ dcoefs, const float* __restrict__ iscale, int N, int O, int I, int KK) {
@@ -407,6 +469,22 @@ int run_dnoise(int dtype, const void* dy, int N, int O, int HW, int per_sample, 
         default:      dnoise_kernel<double><<<grid, 256, 0, stream>>>((const double*)dy, N, O, HW, per_sample, pps, dnoise); break;
     }
     return launch_status("modconv dnoise_kernel");
+}
+// g (zero-initialised by this function) and/or dnoise (zero-initialised by the caller) in one pass over dy; returns
+// VFM_ERR_NO_KERNEL when the tensors do not allow the vector kernel (the caller then uses run_gsum / run_dnoise)
+int run_gsum_dnoise(int dtype, const void* dy, const void* y, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
+                    float* g, float* dnoise, int dnoise_per_sample, cudaStream_t stream) {
+    if ((dtype != VFM_F16 && dtype != VFM_F32) || HW % 8 != 0 || HW < 2048 || !aligned16(dy) || (y && !aligned16(y)) || (size_t)O * sizeof(float) > 48 * 1024) return VFM_ERR_NO_KERNEL;
+    if (g) VFM_CUDA_OK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)N * O, stream));
+    dim3 grid(ceil_div(HW, 1024), N);
+    const double es = dtype == VFM_F16 ? 2.0 : 4.0;
+    KernelTimer timer("modconv_gsum_dnoise", stream, 0.0, (double)N * O * HW * es * (g ? 2.0 : 1.0), "o%dhw%d", O, HW);
+    const int64_t dsn = dnoise_per_sample ? HW : 0;
+    if (dtype == VFM_F16)
+        gsum_dnoise_kernel<__half><<<grid, 128, O * sizeof(float), stream>>>((const __half*)dy, g ? (const __half*)y : nullptr, g ? noise : nullptr, noise_sn, dcoefs, O, HW, g, dnoise, dsn);
+    else
+        gsum_dnoise_kernel<float><<<grid, 128, O * sizeof(float), stream>>>((const float*)dy, g ? (const float*)y : nullptr, g ? noise : nullptr, noise_sn, dcoefs, O, HW, g, dnoise, dsn);
+    return launch_status("modconv gsum_dnoise_kernel");
 }
 int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream) {
     dw_fix_kernel<<<ceil_div(O * I, 256), 256, 0, stream>>>(dw, w, a, g, dcoefs, iscale, N, O, I, KK);

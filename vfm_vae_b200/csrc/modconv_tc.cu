@@ -860,7 +860,8 @@ __global__ void wgrad_scalars_kernel(const float* __restrict__ iscale, int n_el,
 // along pixels, coalesced 16-byte writes along channels.
 template <class TIn, bool SPLIT>
 __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           const float* __restrict__ gscale, __half* __restrict__ xt, __half* __restrict__ xt_lo, int C, int HW) {
+                                                           const float* __restrict__ gscale, __half* __restrict__ xt, __half* __restrict__ xt_lo, int C, int HW,
+                                                           int W, int in_pitch) {
     __shared__ __half s[SPLIT ? 2 : 1][64][66];     // [pixel][channel], 33-word pitch: conflict-free transposed stores
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
@@ -868,13 +869,16 @@ __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict
     {
         const int pl = tid & 63, cg = tid >> 6;      // 4 channel groups x 64 pixels
         const int pidx = p0 + pl;
+        // input rows may be pitched (the blur backward writes 32-byte aligned rows): pixel -> offset inside the plane
+        const size_t plane_sz = (in_pitch == W) ? (size_t)HW : (size_t)(HW / W) * in_pitch;
+        const size_t poff = (in_pitch == W) ? (size_t)pidx : (size_t)(pidx / W) * in_pitch + (pidx % W);
 #pragma unroll 4
         for (int i = 0; i < 16; i++) {
             const int cl = cg + i * 4;
             const int c = c0 + cl;
             float v = 0.f;
             if (pidx < HW && c < C) {
-                v = to_acc(x[((size_t)n * C + c) * HW + pidx]) * (scale[(size_t)n * C + c] * gs);
+                v = to_acc(x[((size_t)n * C + c) * plane_sz + poff]) * (scale[(size_t)n * C + c] * gs);
                 if (shift) v += shift[(size_t)n * C + c] * gs;
             }
             const __half hi = __float2half_rn(v);
@@ -953,11 +957,14 @@ __global__ void scale_prep_kernel(const float* __restrict__ in_scale, const floa
 
 // amax over |x * scale[n,c]| (bit pattern of a non-negative float is monotone -> atomicMax on uint)
 template <class TIn>
-__global__ void __launch_bounds__(256) amax_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, int C, int HW, size_t total, unsigned int* amax_bits) {
+__global__ void __launch_bounds__(256) amax_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, int C, int HW, size_t total, unsigned int* amax_bits,
+                                                   int W, int pitch) {
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t plane = i / HW;
-        m = fmaxf(m, fabsf(to_acc(x[i]) * scale[plane]));
+        size_t off = i;
+        if (pitch != W) { const int rem = (int)(i - plane * HW); off = plane * (size_t)(HW / W) * pitch + (size_t)(rem / W) * pitch + (rem % W); }   // pitched rows
+        m = fmaxf(m, fabsf(to_acc(x[off]) * scale[plane]));
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
@@ -1090,13 +1097,14 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
 }
 
 int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream,
-                const float* shift = nullptr) {
+                const float* shift = nullptr, int W = 0, int in_pitch = 0) {
+    if (W <= 0 || in_pitch <= 0) { W = HW; in_pitch = HW; }         // dense planes
     dim3 grid(ceil_div(HW, 64), ceil_div(C, 64), N);
     if (grid.z > 65535 || grid.y > 65535) { set_error("tcgen05 path: batch too large"); return VFM_ERR_INVALID; }
     KernelTimer timer("modconv_nhwc_prepass", stream, 0.0, (double)N * C * HW * ((dtype == VFM_F16 ? 2 : 4) + (split ? 4 : 2)), "c%dhw%d", C, HW);
-    if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, shift, gscale, xt, xt_lo, C, HW);
-    else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW);
-    else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW);
+    if (dtype == VFM_F16) nhwc_prepass_kernel<__half, false><<<grid, 256, 0, stream>>>((const __half*)x, scale, shift, gscale, xt, xt_lo, C, HW, W, in_pitch);
+    else if (split) nhwc_prepass_kernel<float, true><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW, W, in_pitch);
+    else nhwc_prepass_kernel<float, false><<<grid, 256, 0, stream>>>((const float*)x, scale, shift, gscale, xt, xt_lo, C, HW, W, in_pitch);
     return launch_status("modconv nhwc_prepass_kernel");
 }
 
@@ -1261,7 +1269,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     return run_tc_conv(f32, false, op, a, nph, stream);
 }
 
-int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, const void* x, const float* weight, const Coefs& k,
+int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
                        void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
@@ -1278,13 +1286,13 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         VFM_CUDA_OK(cudaMemsetAsync(w.amax, 0, sizeof(unsigned int), stream));
         size_t want_blocks = (zel + 255) / 256;
         int blocks = (int)(want_blocks < (size_t)kNumSMs * 8 ? want_blocks : (size_t)kNumSMs * 8);
-        amax_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dz, k.d, O, s.zh * s.zw, zel, w.amax);
+        amax_kernel<float><<<blocks, 256, 0, stream>>>((const float*)dz, k.d, O, s.zh * s.zw, zel, w.amax, s.zw, dz_pitch > 0 ? dz_pitch : s.zw);
         st = launch_status("modconv amax_kernel"); if (st) return st;
         gscale_kernel<<<1, 1, 0, stream>>>(w.amax, w.gs);
         st = launch_status("modconv gscale_kernel"); if (st) return st;
         gs = w.gs;
     }
-    st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream); if (st) return st;
+    st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream, nullptr, s.zw, dz_pitch > 0 ? dz_pitch : s.zw); if (st) return st;
     if (dx) {
         // dxpre[n,i,p] = sum_{o,t} (a*W)[o,i,widx(t)] * (d*dz)[n,o,z(p,t)];  dx = s' * dxpre;  dsum = sum_p x * dxpre
         TapTable dt; int sn, sd;

@@ -271,7 +271,7 @@ template <int NB> __device__ __forceinline__ void stg_words(void* p, const uint3
 
 // NC = output columns per thread (8, or 16 for fp16 rows aligned to 32 bytes: one 256-bit load / store per row)
 template <class T, int PX, bool SEP, int NC>
-__device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& k, int cg_log2, int strips, int strip_rows) {
+__device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& k, int CG, int strips, int strip_rows) {
     constexpr int NL = PX;                 // halo columns on the left
     constexpr int NR = 3 - PX;             // halo columns on the right
     constexpr int EW = (int)(4 / sizeof(T));   // elements per 32-bit word (2 for fp16, 1 for fp32)
@@ -279,17 +279,17 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     constexpr int NBYTES = NC * (int)sizeof(T);
     constexpr int WL = (NL + EW - 1) / EW, WR = (NR + EW - 1) / EW;    // halo words needed on each side
     constexpr int NE = WL + WR;            // halo words an edge lane fetches itself
-    const int CG = 1 << cg_log2;           // column groups per row (power of two; groups past the row end idle)
+    // CG = column groups per row (any number: a warp may straddle two strips, see the edge flags below)
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cgi = (int)(gid & (CG - 1));
-    int64_t rest = gid >> cg_log2;
+    const int cgi = (int)(gid % CG);
+    int64_t rest = gid / CG;
     const int strip = (int)(rest % strips);
     const int64_t plane = rest / strips;
     const bool alive = plane < (int64_t)p.channels * p.batch;
     const int c = alive ? (int)(plane % p.channels) : 0, n = alive ? (int)(plane / p.channels) : 0;
     const int lane = threadIdx.x & 31;
-    const int lmask = (CG < 32 ? CG : 32) - 1;
-    const bool edge_l = (lane & lmask) == 0, edge_r = (lane & lmask) == lmask;
+    // a lane's shuffle neighbour is its column neighbour unless the lane sits at the end of the warp or of the row
+    const bool edge_l = lane == 0 || cgi == 0, edge_r = lane == 31 || cgi == CG - 1;
 
     const int ox0 = cgi * NC;
     const int oy_begin = strip * strip_rows;
@@ -541,17 +541,17 @@ __device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps& k) {
 }
 
 template <class T, int PX>
-__global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+__global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg, int strips, int strip_rows) {
     BlurTaps k;
-    if (blur_taps(p, k)) blur_body<T, PX, true, 8>(p, k, cg_log2, strips, strip_rows);
-    else blur_body<T, PX, false, 8>(p, k, cg_log2, strips, strip_rows);
+    if (blur_taps(p, k)) blur_body<T, PX, true, 8>(p, k, cg, strips, strip_rows);
+    else blur_body<T, PX, false, 8>(p, k, cg, strips, strip_rows);
 }
 // 16 columns per thread (fp16 rows aligned to 32 bytes): half the per-row bookkeeping per output
 template <int PX>
-__global__ void __launch_bounds__(128, 3) upfirdn2d_blur16(UpfirdnArgs p, int cg_log2, int strips, int strip_rows) {
+__global__ void __launch_bounds__(128, 3) upfirdn2d_blur16(UpfirdnArgs p, int cg, int strips, int strip_rows) {
     BlurTaps k;
-    if (blur_taps(p, k)) blur_body<__half, PX, true, 16>(p, k, cg_log2, strips, strip_rows);
-    else blur_body<__half, PX, false, 16>(p, k, cg_log2, strips, strip_rows);
+    if (blur_taps(p, k)) blur_body<__half, PX, true, 16>(p, k, cg, strips, strip_rows);
+    else blur_body<__half, PX, false, 16>(p, k, cg, strips, strip_rows);
 }
 
 template <class T>
@@ -565,14 +565,12 @@ int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     }
     const int nc = wide ? 16 : 8;
     const int groups = ceil_div(a.out_w, nc);
-    int cg_log2 = 0;
-    while ((1 << cg_log2) < groups) cg_log2++;
     // strips: enough threads to fill the machine, few enough that the 3-row halo stays cheap
     const int64_t planes = (int64_t)a.channels * a.batch;
     int strip_rows = 64;
-    while (strip_rows > 8 && planes * ceil_div(a.out_h, strip_rows) * (1 << cg_log2) < (int64_t)kNumSMs * 2048) strip_rows >>= 1;
+    while (strip_rows > 8 && planes * ceil_div(a.out_h, strip_rows) * groups < (int64_t)kNumSMs * 2048) strip_rows >>= 1;
     const int strips = ceil_div(a.out_h, strip_rows);
-    const int64_t threads = planes * strips * (1 << cg_log2);
+    const int64_t threads = planes * strips * groups;
     const int64_t blocks = ceil_div64(threads, 128);
     if (blocks > 0x7fffffffLL) { set_error("upfirdn2d: grid too large"); return VFM_ERR_INVALID; }
     KernelTimer timer("upfirdn2d_blur", stream, 0.0,
@@ -580,18 +578,18 @@ int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
                       "w%dc%d", a.out_w, a.channels);
     if (wide) {
         switch (a.padx0) {
-            case 0: upfirdn2d_blur16<0><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-            case 1: upfirdn2d_blur16<1><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-            case 2: upfirdn2d_blur16<2><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-            default: upfirdn2d_blur16<3><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+            case 0: upfirdn2d_blur16<0><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+            case 1: upfirdn2d_blur16<1><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+            case 2: upfirdn2d_blur16<2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+            default: upfirdn2d_blur16<3><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
         }
         return launch_status("upfirdn2d_blur16");
     }
     switch (a.padx0) {
-        case 0: upfirdn2d_blur<T, 0><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-        case 1: upfirdn2d_blur<T, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-        case 2: upfirdn2d_blur<T, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
-        default: upfirdn2d_blur<T, 3><<<(unsigned)blocks, 128, 0, stream>>>(a, cg_log2, strips, strip_rows); break;
+        case 0: upfirdn2d_blur<T, 0><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+        case 1: upfirdn2d_blur<T, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+        case 2: upfirdn2d_blur<T, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
+        default: upfirdn2d_blur<T, 3><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
     }
     return launch_status("upfirdn2d_blur");
 }

@@ -391,6 +391,10 @@ def _modconv_vs_oracle(N, I, O_, H, W, k, up, demod, dtype, noise_kind, generic,
     dict(N=2, I=256, O_=128, H=12, W=64, k=3, up=1, demod=True, noise_kind='random'),
     dict(N=1, I=128, O_=128, H=6, W=128, k=3, up=1, demod=True, noise_kind='const'),      # partial tile rows
     dict(N=2, I=128, O_=256, H=8, W=64, k=1, up=1, demod=False, noise_kind=None),
+    # >= 2048 output pixels with noise: the backward's one-pass gsum + dnoise kernel, both noise layouts
+    dict(N=2, I=128, O_=128, H=64, W=64, k=3, up=1, demod=True, noise_kind='const'),
+    dict(N=2, I=128, O_=128, H=32, W=64, k=3, up=1, demod=True, noise_kind='random'),
+    dict(N=1, I=128, O_=128, H=32, W=32, k=3, up=2, demod=True, noise_kind='const'),      # 64x64 output through the pitched blur backward
 ], ids=lambda c: f"N{c['N']}I{c['I']}O{c['O_']}H{c['H']}k{c['k']}up{c['up']}")
 def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
     _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)

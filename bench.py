@@ -41,14 +41,16 @@ def parse():
     ap.add_argument('--res', type=int, default=256, choices=[256, 512])
     ap.add_argument('--fp16-res', type=int, default=3, help='num_fp16_res (3 = training configs, 0 = the inference tools)')
     ap.add_argument('--cpu-batch', type=int, default=4, help='sample size of the CPU legs')
+    ap.add_argument('--variant', choices=['legacy', 'convnext'], default='legacy',
+                    help="decoder variant: 'legacy' = use_convnext=False (the path north_star names, default), 'convnext' = the shipped YAMLs' layers")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cudnn-benchmark', action='store_true', help='leave torch.backends.cudnn.benchmark off for the glue layers')
     return ap.parse_args()
 
 
 def decoder_kwargs(args):
-    from vfm_vae_b200.decoder import F16D32_LEGACY_KWARGS
-    kw = dict(F16D32_LEGACY_KWARGS)
+    from vfm_vae_b200.decoder import F16D32_LEGACY_KWARGS, F16D32_CONVNEXT_KWARGS
+    kw = dict(F16D32_CONVNEXT_KWARGS if args.variant == 'convnext' else F16D32_LEGACY_KWARGS)
     kw['img_resolution'] = args.res
     kw['z_resolution'] = args.res // 16
     kw['num_fp16_res'] = args.fp16_res
@@ -63,7 +65,8 @@ def make_inputs(kw, batch, num_ws, seed):
 
 
 def workload_name(args):
-    return (f'f16d32 D-legacy pixel decoder (SynthesisNetwork use_convnext=False) {args.mode}, {args.res}x{args.res}, '
+    variant = 'D-legacy pixel decoder (SynthesisNetwork use_convnext=False)' if args.variant == 'legacy' else 'D-convnext pixel decoder (SynthesisNetwork use_convnext=True)'
+    return (f'f16d32 {variant} {args.mode}, {args.res}x{args.res}, '
             f'batch {args.batch}/GPU, num_fp16_res={args.fp16_res}, random-init weights, synthetic latents '
             f'(BASELINE configs[1] restricted to the hot path; SigLIP2 encoder out of scope)')
 
@@ -80,7 +83,7 @@ def oracle_ops():
         return O.modulated_conv2d(x, weight, styles, noise=noise, up=up, down=down, padding=padding, resample_filter=resample_filter,
                                   demodulate=demodulate, flip_weight=flip_weight)
     return SimpleNamespace(bias_act=O.bias_act, def_gain=lambda a: O.ACTIVATIONS[a][1], setup_filter=O.setup_filter,
-                           upsample2d=O.upsample2d, modulated_conv2d=modconv)
+                           upsample2d=O.upsample2d, modulated_conv2d=modconv, modulated_pointwise_conv2d=O.modulated_pointwise_conv2d)
 
 
 def cpu_step_fn(args, batch):
@@ -368,7 +371,7 @@ def run_ours(args):
             'dtype': 'f16' if args.fp16_res > 0 else 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(args), 'global_batch': args.batch * world, 'parallelism': f'batch-sharded x{world}' + (' (replicas, no collective)' if args.mode == 'decode' else ' + gradient all-mean (NCCL)'),
                        'l2': 'explicit 256 MiB flush write between timed iterations; per-step activations (GBs) exceed the 126 MB L2 anyway',
-                       'decoder_variant': 'D-legacy (use_convnext=False)', 'cudnn_benchmark': bool(torch.backends.cudnn.benchmark)},
+                       'decoder_variant': 'D-legacy (use_convnext=False)' if args.variant == 'legacy' else 'D-convnext (use_convnext=True)', 'cudnn_benchmark': bool(torch.backends.cudnn.benchmark)},
             'e2e': {'value': total_imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
                     'h2d_bytes_per_step': (z_h.numel() + ws_h.numel()) * 4, 'd2h_bytes_per_step': out_h.numel() * 4},
             'gpu_launches': int(launches),

@@ -206,6 +206,7 @@ VFM_API int vfm_filtered_lrelu_act(const vfm_filtered_lrelu_act_params* p, void*
  * x, y: NCHW contiguous, `dtype`.  weight fp32 [O,I,kh,kw] contiguous; styles fp32 [N,I]; noise fp32.
  * dcoefs: fp32 [N,O] written by forward (ones if !demodulate) and consumed by backward.
  */
+#define VFM_EP_ACT_GELU 10
 enum vfm_noise_mode { VFM_NOISE_NONE = 0, VFM_NOISE_HW = 1 /* [Hout,Wout] */, VFM_NOISE_N1HW = 2 /* [N,1,Hout,Wout] */ };
 
 typedef struct {
@@ -235,7 +236,8 @@ typedef struct {
     /* Optional fused layer epilogue (inference).  When ep_enable != 0 the kernel that produces y also
      * applies what networks/generator.py:268-274 does after the conv:
      *     y = clamp(act(y + bias[o]) * ep_gain, +-ep_clamp);   if (ep_residual) y = (ep_gamma[o] * y + ep_residual) * ep_res_scale
-     * ep_act is 1 (linear) or 3 (lrelu, slope ep_alpha).  Returns VFM_ERR_NO_KERNEL if the path chosen for this descriptor
+     * ep_act is 1 (linear), 3 (lrelu, slope ep_alpha) or VFM_EP_ACT_GELU (exact erf gelu: the ConvNeXt layers'
+     * pwconv1 -> GELU, networks/utils/convnext_utils.py:140-142).  Returns VFM_ERR_NO_KERNEL if the path chosen for this descriptor
      * cannot fuse it; the caller then composes bias_act (+ residual arithmetic) itself, as the reference does. */
     int32_t      ep_enable;
     int32_t      ep_act;

@@ -383,6 +383,15 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     return y
 
 
+def modulated_pointwise_conv2d(x, weight, style, bias=None, demodulate=True):
+    """networks/utils/convnext_utils.py:36-57: 1x1 modulated / demodulated conv + broadcast bias (fp32/fp64 semantics; the
+    fp16-only pre-normalisation of the reference cancels under demodulation)."""
+    y = modulated_conv2d(x, weight, style, noise=None, up=1, padding=0, demodulate=demodulate, flip_weight=True)
+    if bias is not None:
+        y = y + bias
+    return y
+
+
 # ---------------------------------------------------------------------------
 # one legacy synthesis layer (networks/generator.py:240-276) -- used by the decoder-level tests/bench
 

@@ -17,16 +17,16 @@ def oracle_ops():
         return O.modulated_conv2d(x, weight, styles, noise=noise, up=up, down=down, padding=padding, resample_filter=resample_filter,
                                   demodulate=demodulate, flip_weight=flip_weight)
     return SimpleNamespace(bias_act=O.bias_act, def_gain=lambda a: O.ACTIVATIONS[a][1], setup_filter=O.setup_filter,
-                           upsample2d=O.upsample2d, modulated_conv2d=modconv)
+                           upsample2d=O.upsample2d, modulated_conv2d=modconv, modulated_pointwise_conv2d=O.modulated_pointwise_conv2d)
 
 
-def build(ops, device='cpu'):
+def build(ops, device='cpu', name='decoder_legacy'):
     from vfm_vae_b200.decoder import SynthesisNetwork
     # the reference trains and evaluates with TF32 off (training/training_loop.py:504-505); the out-of-scope glue layers
     # (z-convs, attention) run on cuDNN/cuBLAS and would otherwise lose 1e-3 of precision
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    G = golden('decoder_legacy')
+    G = golden(name)
     kw = dict(G.meta['kwargs'])
     net = SynthesisNetwork(ops=ops, **kw)
     sd = {k[4:]: G.t(k) for k in G.keys() if k.startswith('sd::')}
@@ -110,3 +110,51 @@ def test_decoder_cuda_inference_fused_matches_unfused():
     assert rel_err(img_b, img_a) <= 2e-5
     for a, b in zip(multi_a, multi_b):
         assert rel_err(b, a) <= 2e-5
+
+
+# ------------------------------------------------------------------ ConvNeXt variant (use_convnext=True)
+
+def test_convnext_decoder_host_logic_cpu():
+    """The mirror of the ConvNeXt-variant decoder (what the shipped YAMLs run) against the reference's own output and gradients."""
+    net, G = build(oracle_ops(), name='decoder_convnext')
+    check(net, G, 'cpu', 2e-5)
+
+
+def test_convnext_state_dict_names_match_reference():
+    from vfm_vae_b200.decoder import SynthesisNetwork
+    G = golden('decoder_convnext')
+    net = SynthesisNetwork(ops=oracle_ops(), **G.meta['kwargs'])
+    ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k[4:]: tuple(G.z[k].shape) for k in G.keys() if k.startswith('sd::')}
+    assert ours == ref
+
+
+@pytest.mark.gpu
+def test_convnext_decoder_cuda_fp32():
+    from vfm_vae_b200.decoder import default_ops
+    net, G = build(default_ops(), 'cuda', name='decoder_convnext')
+    z, ws = G.t('z', 'cuda'), G.t('ws', 'cuda')
+    img, multi = net(z, ws, None, None, force_fp32=True)
+    assert rel_err(img, G.t('img')) <= 2e-5
+    for i, m in enumerate(multi):
+        assert rel_err(m, G.t(f'multi{i}')) <= 2e-5
+    loss = img.square().mean() + sum(m.square().mean() for m in multi)
+    params = dict(net.named_parameters())
+    names = G.meta['grad_names']
+    grads = torch.autograd.grad(loss, [params[n] for n in names])
+    for n, g in zip(names, grads):
+        assert rel_err(g, G.t('grad::' + n)) <= 2e-4, n
+    with torch.no_grad():                                              # inference route (fused where the shapes allow)
+        img_b, _ = net(z, ws, None, None, force_fp32=True)
+    assert rel_err(img_b, G.t('img')) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_convnext_decoder_cuda_fp16_blocks():
+    from vfm_vae_b200.decoder import default_ops
+    net, G = build(default_ops(), 'cuda', name='decoder_convnext')
+    img, multi = net(G.t('z', 'cuda'), G.t('ws', 'cuda'), None, None)
+    assert img.dtype == torch.float32
+    assert rel_err(img, G.t('img')) <= 4e-3
+    for i, m in enumerate(multi):
+        assert rel_err(m, G.t(f'multi{i}')) <= 4e-3

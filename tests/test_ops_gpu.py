@@ -536,6 +536,58 @@ def test_fused_residual_layer_with_group_norm(cfg, dtype):
     assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [dict(N=2, C=128, H=16, demod=True), dict(N=3, C=32, H=8, demod=True), dict(N=2, C=128, H=8, demod=False)],
+                         ids=lambda c: f"C{c['C']}H{c['H']}{'' if c['demod'] else 'nodemod'}")
+def test_modulated_pointwise_conv2d_vs_oracle(cfg, dtype):
+    """networks/utils/convnext_utils.py:36 drop-in: 1x1 modulated conv C -> 4C + bias, forward and gradients."""
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import modulated_pointwise_conv2d
+    g = torch.Generator().manual_seed(40)
+    N, Cc, H = cfg['N'], cfg['C'], cfg['H']
+    xq = torch.randn(N, Cc, H, H, generator=g).to(dtype).float()
+    w = torch.randn(4 * Cc, Cc, 1, 1, generator=g) * 0.2
+    s = torch.randn(N, Cc, generator=g) + 1
+    b = torch.randn(1, 4 * Cc, 1, 1, generator=g) * 0.1
+    ref_in = [t.clone().requires_grad_(True) for t in (xq, w, s, b)]
+    yr = O.modulated_pointwise_conv2d(*ref_in, demodulate=cfg['demod'])
+    dy = torch.randn(yr.shape, generator=g)
+    gr = torch.autograd.grad(yr, ref_in, dy)
+    dev_in = [xq.to(DEV, dtype).requires_grad_(True)] + [t.to(DEV).requires_grad_(True) for t in (w, s, b)]
+    y = modulated_pointwise_conv2d(*dev_in, demodulate=cfg['demod'])
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert rel_err(y, yr) <= tol
+    gg = torch.autograd.grad(y, dev_in, dy.to(DEV, y.dtype))
+    for name, a, r in zip(['dx', 'dw', 'ds', 'db'], gg, gr):
+        assert rel_err(a, r) <= 2 * tol, name
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [dict(N=2, C=128, H=16), dict(N=1, C=128, H=64), dict(N=3, C=256, H=8)], ids=lambda c: f"C{c['C']}H{c['H']}")
+def test_fused_convnext_mlp(cfg, dtype):
+    """GroupNorm32 -> pwconv1 (modulated, +bias) -> GELU -> pwconv2 (+bias) -> gamma*y + x_in (convnext_utils.py:138-147) as one
+    statistics pass + two tensor-core 1x1 convs, against the chain composed from torch / oracle ops in fp32."""
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_convnext_mlp
+    g = torch.Generator().manual_seed(41)
+    N, Cc, H = cfg['N'], cfg['C'], cfg['H']
+    xq = (torch.randn(N, Cc, H, H, generator=g) * 2 + torch.randn(N, Cc, 1, 1, generator=g)).to(dtype).float()
+    x_in = torch.randn(N, Cc, H, H, generator=g).to(dtype).float()
+    w1 = torch.randn(4 * Cc, Cc, 1, 1, generator=g) * 0.2
+    b1 = torch.randn(1, 4 * Cc, 1, 1, generator=g) * 0.1
+    w2 = torch.randn(Cc, 4 * Cc, 1, 1, generator=g) * 0.05
+    b2 = torch.randn(Cc, generator=g) * 0.1
+    s = torch.randn(N, Cc, generator=g) + 1
+    gn_w, gn_b = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.3
+    gamma = torch.rand(1, Cc, 1, 1, generator=g) + 0.5
+    xn = torch.nn.functional.group_norm(xq, 32, gn_w, gn_b, eps=1e-5)
+    h = torch.nn.functional.gelu(O.modulated_pointwise_conv2d(xn, w1, s, b1))
+    yr = gamma * torch.nn.functional.conv2d(h, w2, b2) + x_in
+    with torch.no_grad():
+        y = fused_convnext_mlp(xq.to(DEV, dtype), x_in.to(DEV, dtype), gn_w.to(DEV), gn_b.to(DEV), 32, 1e-5, w1.to(DEV), b1.to(DEV), s.to(DEV),
+                               w2.to(DEV), b2.to(DEV), gamma.to(DEV))
+    assert y is not None and y.dtype == dtype
+    assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
+
+
 def test_fused_layer_declines_what_it_cannot_do():
     from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
     x = torch.randn(2, 40, 9, 13, device=DEV)            # ragged channels -> generic SIMT path, which does not fuse

@@ -315,6 +315,41 @@ def gen_decoder():
     save('decoder_legacy', arrays, dict(kwargs=DECODER_KW, num_ws=net.num_ws, grad_names=names, loss=float(loss)))
 
 
+def gen_decoder_convnext():
+    """Tiny ConvNeXt-variant SynthesisNetwork (use_convnext=True, what the shipped configs run)."""
+    kw = dict(DECODER_KW, use_convnext=True, add_additional_convnext=True, legacy=True, use_gaussian_blur=True)
+    torch.manual_seed(8)
+    net = ref_gen.SynthesisNetwork(**kw)
+    g = rng(9)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith('noise_strength'):
+                p.fill_(0.1)
+            elif name.endswith('gamma') and p.ndim == 4:
+                p.fill_(0.3)
+            elif (name.endswith('.bias') and 'affine' not in name and 'norm' not in name) or name.endswith('pwconv1.bias'):
+                p.copy_(randn(g, *p.shape, dtype=torch.float32) * 0.1)
+            elif name.endswith('pwconv1.weight') or name.endswith('pwconv2.weight') or name.endswith('dwconv.weight'):
+                p.copy_(randn(g, *p.shape, dtype=torch.float32) * 0.2)
+            elif name.endswith('to_out.weight') or (name.endswith('.3.weight') and '.ff.' in name):
+                p.copy_(randn(g, *p.shape, dtype=torch.float32) * 0.05)
+    z = randn(g, 2, 16, 8, 8, dtype=torch.float32)
+    ws = randn(g, 2, net.num_ws, 32, dtype=torch.float32)
+    img, multi = net(z, ws, None, None)
+    loss = img.square().mean() + sum(m.square().mean() for m in multi)
+    names = ['blocks.3.convs1.3.pwconv1.weight', 'blocks.3.convs1.3.pwconv1.bias', 'blocks.2.conv0.dwconv.weight', 'blocks.0.convs1.1.gamma',
+             'blocks.3.conv0.noise_strength', 'blocks.1.torgb.weight', 'blocks.3.conv0.affine_pw1.proj.weight', 'blocks.2.seperate_upsample_conv.pointwise.weight']
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(loss, [params[n] for n in names])
+    arrays = {'sd::' + k: v for k, v in net.state_dict().items()}
+    arrays['z'], arrays['ws'], arrays['img'] = z, ws, img
+    for i, m in enumerate(multi):
+        arrays[f'multi{i}'] = m
+    for n, gr in zip(names, grads):
+        arrays['grad::' + n] = gr
+    save('decoder_convnext', arrays, dict(kwargs=kw, num_ws=net.num_ws, grad_names=names, loss=float(loss)))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -324,3 +359,4 @@ if __name__ == '__main__':
     gen_modconv()
     gen_conv2d_resample()
     gen_decoder()
+    gen_decoder_convnext()

@@ -131,7 +131,10 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     // optional fused layer epilogue: goes into the stage-1 kernel for up=1 and into the blur for up=2
     Epilogue ep = no_epilogue();
     if (p->ep_enable) {
-        VFM_CHECK_ARG(p->ep_act == 1 || p->ep_act == 3, "modulated_conv2d: the fused epilogue supports linear and lrelu only");
+        VFM_CHECK_ARG(p->ep_act == 1 || p->ep_act == 3 || p->ep_act == VFM_EP_ACT_GELU, "modulated_conv2d: the fused epilogue supports linear, lrelu and gelu only");
+        if (p->ep_act == VFM_EP_ACT_GELU && !(use_tc(d) && d.up == 1 && !(use_pw(d) && aligned16(p->x) && aligned16(p->y)))) {
+            set_error("modulated_conv2d: the gelu epilogue is only implemented in the tcgen05 kernel (up = 1)"); return VFM_ERR_NO_KERNEL;
+        }
         VFM_CHECK_ARG(!p->ep_residual || p->ep_gamma, "modulated_conv2d: ep_residual needs ep_gamma");
         const bool fusable = (use_pw(d) && aligned16(p->x) && aligned16(p->y)) || (use_tc(d) && (d.up == 1 || !p->ep_residual));
         if (!fusable) { set_error("modulated_conv2d: no kernel fuses the epilogue for this descriptor"); return VFM_ERR_NO_KERNEL; }

@@ -485,6 +485,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         const float gp = p.ep.gain, gn = p.ep.gain * p.ep.alpha;
 #pragma unroll
                         for (int i = 0; i < NV; i++) o[i] *= (o[i] > 0.f) ? gp : gn;
+                    } else if (p.ep.act == VFM_EP_ACT_GELU) {
+                        const float hg = 0.5f * p.ep.gain;
+#pragma unroll
+                        for (int i = 0; i < NV; i++) o[i] = hg * o[i] * (1.f + erff(o[i] * 0.70710678118654752f));
                     } else if (p.ep.gain != 1.f) {
 #pragma unroll
                         for (int i = 0; i < NV; i++) o[i] *= p.ep.gain;

@@ -16,6 +16,7 @@ benchmark box.
 to check this file's host logic against the golden vectors without a GPU; the product default never touches the oracle.
 """
 import math
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -26,10 +27,11 @@ import torch.nn.functional as F
 
 def default_ops():
     from .torch_utils.ops import bias_act, upfirdn2d
-    from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act
+    from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act, modulated_pointwise_conv2d, fused_convnext_mlp
     return SimpleNamespace(fused_layer=fused_modconv_bias_act, bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
                            setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d,
-                           modulated_conv2d=modulated_conv2d)
+                           modulated_conv2d=modulated_conv2d, modulated_pointwise_conv2d=modulated_pointwise_conv2d,
+                           fused_convnext_mlp=None if os.environ.get('VFM_NO_FUSED_CONVNEXT') else fused_convnext_mlp)
 
 
 # ------------------------------------------------------------------------------------------- small shared layers
@@ -255,13 +257,97 @@ class ToRGBLayer(nn.Module):
         return self.ops.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 
 
+# ------------------------------------------------------------------------------------------- ConvNeXt-variant layers
+# (use_convnext=True: what the shipped YAMLs run; SURVEY.md 8f row 1.  networks/utils/convnext_utils.py:60-187)
+
+class ModulatedPointwiseConv2DLayer(nn.Module):
+    def __init__(self, in_channels, out_channels, demodulate=True, ops=None):
+        super().__init__()
+        self.ops, self.demodulate = ops, demodulate
+        self.weight = nn.Parameter(torch.empty([out_channels, in_channels, 1, 1]))
+        self.bias = nn.Parameter(torch.zeros(1, out_channels, 1, 1))
+        nn.init.trunc_normal_(self.weight, std=0.02)
+
+    def forward(self, x, style):
+        return self.ops.modulated_pointwise_conv2d(x, self.weight, style, self.bias, self.demodulate)
+
+
+class ConvNeXtSynthesisLayer(nn.Module):
+    """dw kxk conv (+bilinearly resized const noise) -> GroupNorm32 -> modulated 1x1 conv C->4C -> GELU -> 1x1 conv 4C->C -> gamma*y + x"""
+
+    def __init__(self, channels, w_dim, kernel_size, layer_scale_init=1e-5, demodulate=True, block_index=0, legacy=False, ops=None):
+        super().__init__()
+        self.ops, self.legacy, self.channels, self.kernel_size = ops, legacy, channels, kernel_size
+        self.affine_pw1 = StyleSplit(w_dim, channels, bias_init=1)
+        self.dwconv = nn.Conv2d(channels, channels, kernel_size=kernel_size, padding=kernel_size // 2, groups=channels)
+        nn.init.trunc_normal_(self.dwconv.weight, std=0.02)
+        nn.init.constant_(self.dwconv.bias, 0)
+        if legacy:
+            resolution = 8 * 2 ** block_index
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = nn.Parameter(torch.zeros([]))
+        self.pwconv1 = ModulatedPointwiseConv2DLayer(channels, 4 * channels, demodulate, ops=ops)
+        self.pwconv2 = nn.Conv2d(4 * channels, channels, kernel_size=1)
+        nn.init.trunc_normal_(self.pwconv2.weight, std=0.02)
+        nn.init.zeros_(self.pwconv2.bias)
+        self.norm = GroupNorm32(min(32, channels // 4), channels)
+        self.act = nn.GELU()
+        self.gamma = nn.Parameter(layer_scale_init * torch.ones([1, channels, 1, 1])) if layer_scale_init > 0 else None
+
+    def forward(self, x, w):
+        dtype = x.dtype
+        x_in = x
+        style = self.affine_pw1(w)
+        x = self.dwconv(x)
+        if self.legacy:
+            noise = self.noise_const[None, None] * self.noise_strength
+            noise = F.interpolate(noise, size=x.shape[2:], mode='bilinear', align_corners=False)
+        fused = getattr(self.ops, 'fused_convnext_mlp', None)
+        if fused is not None and not torch.is_grad_enabled():
+            # inference: one GroupNorm statistics pass + two tensor-core 1x1 convs with everything else in their epilogues
+            xd = torch.add(x, noise.to(x.dtype)) if self.legacy else x
+            y = fused(xd.to(dtype), x_in, self.norm.weight, self.norm.bias, self.norm.num_groups, self.norm.eps, self.pwconv1.weight,
+                      self.pwconv1.bias, style, self.pwconv2.weight, self.pwconv2.bias, self.gamma, self.pwconv1.demodulate)
+            if y is not None:
+                return y
+        if self.legacy:
+            x = x + noise
+        x = self.norm(x)
+        x = self.pwconv1(x, style)
+        x = self.act(x)
+        x = self.pwconv2(x)
+        if self.gamma is not None:
+            x = self.gamma * x
+        return (x + x_in).to(dtype)
+
+
+class ConvNeXtToRGBLayer(nn.Module):
+    """1x1 modulated conv without demodulation + broadcast bias   (convnext_utils.py:145-187)"""
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, ops=None):
+        super().__init__()
+        self.ops, self.in_channels, self.out_channels, self.kernel_size = ops, in_channels, out_channels, kernel_size
+        self.weight = nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size) * 0.1)
+        self.bias = nn.Parameter(torch.zeros(1, out_channels, 1, 1))
+        self.affine = StyleSplit(w_dim, in_channels, bias_init=1)
+        self.weight_gain = 1 / np.sqrt(in_channels * kernel_size ** 2)
+
+    def forward(self, x, w):
+        style = self.affine(w) * self.weight_gain
+        if torch.is_autocast_enabled() and x.is_cuda:
+            x = x.to(torch.get_autocast_gpu_dtype())
+        y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=style, demodulate=False)
+        return y + self.bias
+
+
 class SynthesisBlock(nn.Module):
     """conv0 (up 2) + 2*num_res_blocks convs (plain, residual alternating, gain sqrt(1/2)) + optional self-attention +
     multi-scale ToRGB on the running feature sum   (generator.py:320-576, legacy branch)"""
 
     def __init__(self, block_index, in_channels, out_channels, last_out_channels, w_dim, resolution, img_channels, is_last,
                  num_res_blocks=1, use_multiscale_output=False, architecture='skip', resample_filter=(1, 3, 3, 1), conv_clamp=None,
-                 use_fp16=False, attn_depth=0, attn_heads=8, attn_ff_mult=4, use_gaussian_blur=True, ops=None, **layer_kwargs):
+                 use_fp16=False, attn_depth=0, attn_heads=8, attn_ff_mult=4, use_gaussian_blur=True, use_convnext=False,
+                 add_additional_convnext=False, legacy=False, is_first=False, ops=None, **layer_kwargs):
         super().__init__()
         assert architecture in ('orig', 'skip')
         assert architecture == 'skip' or not use_multiscale_output
@@ -271,19 +357,31 @@ class SynthesisBlock(nn.Module):
         self.in_channels, self.out_channels, self.last_out_channels = in_channels, out_channels, last_out_channels
         self.w_dim, self.resolution, self.img_channels, self.is_last = w_dim, resolution, img_channels, is_last
         self.architecture, self.use_fp16, self.use_multiscale_output = architecture, use_fp16, use_multiscale_output
-        self.register_buffer('resample_filter', ops.setup_filter(list(resample_filter)))
+        if not use_convnext:                       # the reference registers the buffer only for the legacy layers (generator.py:378-380)
+            self.register_buffer('resample_filter', ops.setup_filter(list(resample_filter)))
         blur_kernel = '3x3' if block_index <= 2 else '5x5'
-        self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2, resample_filter=resample_filter,
-                                    conv_clamp=conv_clamp, ops=ops, **layer_kwargs)
+        self.use_convnext = use_convnext
+        kernel_size = 5 if block_index <= 1 else 7
         convs = []
-        for _ in range(num_res_blocks):
-            convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, ops=ops, **layer_kwargs))
-            convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, residual=True, ops=ops, **layer_kwargs))
+        if use_convnext:
+            self.seperate_upsample_conv = SeparableUpsampleWithFixedBlur(in_channels, out_channels, upscale_factor=2, pre_normalize=not is_first,
+                                                                         use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel)
+            self.conv0 = ConvNeXtSynthesisLayer(out_channels, w_dim=w_dim, kernel_size=kernel_size, block_index=block_index, legacy=legacy, ops=ops)
+            for _ in range(num_res_blocks):
+                for _ in range(3 if block_index <= 3 and add_additional_convnext else 2):
+                    convs.append(ConvNeXtSynthesisLayer(out_channels, w_dim=w_dim, kernel_size=kernel_size, block_index=block_index, legacy=legacy, ops=ops))
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2, resample_filter=resample_filter,
+                                        conv_clamp=conv_clamp, ops=ops, **layer_kwargs)
+            for _ in range(num_res_blocks):
+                convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, ops=ops, **layer_kwargs))
+                convs.append(SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp, residual=True, ops=ops, **layer_kwargs))
         self.convs1 = nn.ModuleList(convs)
         self.num_conv = 1 + len(convs)
         self.num_torgb = 0
         if is_last or architecture == 'skip':
-            self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, ops=ops)
+            self.torgb = (ConvNeXtToRGBLayer(out_channels, img_channels, w_dim=w_dim, ops=ops) if use_convnext else
+                          ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, ops=ops))
             self.num_torgb = 1
         if use_multiscale_output and last_out_channels is not None:
             self.last_upsample_conv = SeparableUpsampleWithFixedBlur(last_out_channels, out_channels, upscale_factor=2,
@@ -298,9 +396,16 @@ class SynthesisBlock(nn.Module):
         dtype = torch.float16 if fp16 else torch.float32
         amp = dict(device_type='cuda', enabled=fp16, dtype=torch.float16)
         x = x.to(dtype=dtype)
-        x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-        for conv in self.convs1:
-            x = conv(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
+        if self.use_convnext:
+            with torch.amp.autocast(**amp):
+                x = self.seperate_upsample_conv(x)
+                x = self.conv0(x, next(w_iter))
+                for conv in self.convs1:
+                    x = conv(x, next(w_iter))
+        else:
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            for conv in self.convs1:
+                x = conv(x, next(w_iter), fused_modconv=fused_modconv, gain=np.sqrt(0.5), **layer_kwargs)
         if self.self_attns is not None:
             with torch.amp.autocast(**amp):
                 for attn in self.self_attns:
@@ -329,10 +434,8 @@ class SynthesisNetwork(nn.Module):
                  num_blocks=6, num_res_blocks=3, z_resolution=16, z_dim=8, concat_z_block_indices=(), concat_z_mapped_dims=(),
                  how_to_process_concat_z='unshuffle', activation_for_concat_z='gelu', use_multiscale_output=False,
                  attn_block_indices=(), attn_depths=(), use_self_attn=False, use_cross_attn=False, use_convnext=False,
-                 use_gaussian_blur=True, c_dim=0, ops=None, **block_kwargs):
+                 use_gaussian_blur=True, c_dim=0, add_additional_convnext=False, legacy=False, ops=None, **block_kwargs):
         super().__init__()
-        if use_convnext:
-            raise NotImplementedError('the ConvNeXt decoder variant calls none of the hot-path ops (SURVEY.md 0.2); it is a "next" row')
         if use_cross_attn:
             raise NotImplementedError('cross-attention is unused by the f16d32 configs (conditional: False)')
         assert how_to_process_concat_z == 'unshuffle', 'only the unshuffle z-processing of the shipped configs is mirrored'
@@ -380,6 +483,7 @@ class SynthesisNetwork(nn.Module):
                                    resolution=self.block_resolutions[idx], img_channels=img_channels, is_last=(idx == num_blocks - 1),
                                    use_fp16=(idx >= fp16_idx), conv_clamp=conv_clamp, num_res_blocks=num_res_blocks,
                                    use_multiscale_output=use_multiscale_output, use_gaussian_blur=use_gaussian_blur,
+                                   use_convnext=use_convnext, add_additional_convnext=add_additional_convnext, legacy=legacy, is_first=(idx == 0),
                                    attn_depth=depth, ops=ops, **block_kwargs)
             self.num_ws += block.num_conv + block.num_torgb
             self.blocks[str(idx)] = block
@@ -422,3 +526,6 @@ F16D32_LEGACY_KWARGS = dict(
     activation_for_concat_z='lrelu', attn_block_indices=[0, 1, 2], attn_depths=[2, 2, 2], use_self_attn=True, use_cross_attn=False,
     use_convnext=False, use_multiscale_output=True, num_blocks=6, num_fp16_res=3, conv_clamp=256, channel_base=32768,
     channel_max=512, num_res_blocks=2, architecture='skip')
+
+#: the same with the ConvNeXt layers of the shipped configs (use_convnext: True, add_additional_convnext: True, legacy noise)
+F16D32_CONVNEXT_KWARGS = dict(F16D32_LEGACY_KWARGS, use_convnext=True, add_additional_convnext=True, legacy=True, use_gaussian_blur=True)

@@ -333,7 +333,7 @@ class _ModconvPlugin:
         ``x_affine`` (inference only): (scale, shift) fp32 [N,I] from ``group_norm_affine``: the conv sees x*scale+shift; with
         ``epilogue['residual_affine']`` the same map is applied to the epilogue's residual (which then is the raw x).
 
-        ``epilogue`` (inference only): dict(act='linear'|'lrelu', alpha, gain, clamp, bias, residual, gamma, res_scale) fused into the
+        ``epilogue`` (inference only): dict(act='linear'|'lrelu'|'gelu', alpha, gain, clamp, bias, residual, gamma, res_scale) fused into the
         kernel that writes y; returns None instead of a tuple if no kernel can fuse it for this call (caller composes)."""
         _ModconvPlugin._common_checks(x, weight, styles, noise, up, resample_filter)
         d = _ModconvPlugin._desc(x, weight, up, padding, demodulate, flip_weight, noise, resample_filter, force_generic)
@@ -359,7 +359,7 @@ class _ModconvPlugin:
                 _check(gamma.numel() == d.out_channels, 'epilogue gamma must have O elements')
             keep = [bias, res, gamma]
             p.ep_enable = 1
-            p.ep_act = {'linear': 1, 'lrelu': 3}[epilogue.get('act', 'linear')]
+            p.ep_act = {'linear': 1, 'lrelu': 3, 'gelu': 10}[epilogue.get('act', 'linear')]
             p.ep_alpha = float(epilogue.get('alpha', 0.2))
             p.ep_gain = float(epilogue.get('gain', 1.0))
             clamp = epilogue.get('clamp')

@@ -126,7 +126,7 @@ def fused_modconv_bias_act(x, weight, styles, bias, noise=None, up=1, padding=0,
     conv's operand pre-pass applies to x and its epilogue applies to the residual; ``residual`` must then be ``x`` itself (raw).
     Returns None when no kernel can fuse this call; the caller then composes the unfused ops exactly as the reference does.
     """
-    assert act in ('linear', 'lrelu')
+    assert act in ('linear', 'lrelu', 'gelu')
     if x.device.type != 'cuda' or torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or styles.requires_grad):
         return None
     if residual is not None and up != 1:
@@ -157,4 +157,52 @@ def fused_modconv_bias_act(x, weight, styles, bias, noise=None, up=1, padding=0,
             ep['residual_affine'] = True
     out = _plugin.forward(xc, w32, s32, n32, int(up), int(padding), f32, bool(demodulate), bool(flip_weight), force_generic, epilogue=ep,
                           x_affine=x_affine)
+    return None if out is None else out[0]
+
+
+def modulated_pointwise_conv2d(x, weight, style, bias=None, demodulate=True):
+    """Drop-in for networks/utils/convnext_utils.py:36 (the ConvNeXt layers' 1x1 modulated conv): the same function as
+    ``modulated_conv2d`` with a 1x1 kernel (its fp16 pre-normalisation ``(1/I)**0.5 / max|w|`` is generator.py:66-68 with kh = kw = 1),
+    plus the broadcast bias.  Runs on the tcgen05 kernel when the channel counts are multiples of 128; autograd as modulated_conv2d.
+    Like the reference under autocast, the contraction runs in the autocast dtype."""
+    if torch.is_autocast_enabled() and x.is_cuda:
+        x = x.to(torch.get_autocast_gpu_dtype())
+    y = modulated_conv2d(x, weight, style, noise=None, up=1, padding=0, demodulate=demodulate, flip_weight=True)
+    if bias is not None:
+        y = y + bias          # [1,O,1,1] fp32 parameter: promotes like the reference does
+    return y
+
+
+def fused_convnext_mlp(x, x_in, norm_weight, norm_bias, num_groups, eps, w1, b1, style, w2, b2, gamma, demodulate=True):
+    """Inference-only fusion of the pointwise half of a ConvNeXt synthesis layer (networks/utils/convnext_utils.py:138-147):
+
+        h = gelu(modulated_pointwise_conv2d(GroupNorm32(x), w1, style, b1));   y = gamma * (conv1x1(h, w2) + b2) + x_in
+
+    as: one GroupNorm statistics pass (vfm_group_norm_affine) + two tcgen05 1x1 convs, the first with the normalisation folded
+    into its operand pre-pass and bias + GELU in its epilogue, the second with bias, layer scale and the residual in its
+    epilogue.  x: the depthwise-conv output (+noise), x_in: the layer input; both [N,C,H,W] in the same fp16/fp32 dtype.
+    Returns None when the shapes do not map onto the tensor-core kernel (the caller composes the reference ops)."""
+    if x.device.type != 'cuda' or torch.is_grad_enabled() and (x.requires_grad or w1.requires_grad or w2.requires_grad or style.requires_grad):
+        return None
+    _init()
+    c, c4 = w1.shape[1], w1.shape[0]
+    if c % 128 != 0 or c4 % 128 != 0 or x.dtype not in (torch.float16, torch.float32) or x_in.dtype != x.dtype:
+        return None
+    xc = x.contiguous()
+    w1f = w1.detach().to(torch.float32).contiguous()
+    s32 = style.detach().to(torch.float32).contiguous()
+    if not _plugin.uses_tensor_cores(xc, w1f, up=1, padding=0, demodulate=demodulate):
+        return None
+    aff = _plugin.group_norm_affine(xc, norm_weight, norm_bias, num_groups, eps)
+    ep1 = dict(act='gelu', gain=1.0, clamp=None, bias=b1.detach().reshape(-1).to(x.dtype).contiguous() if b1 is not None else None)
+    out = _plugin.forward(xc, w1f, s32, None, 1, 0, None, bool(demodulate), True, force_generic, epilogue=ep1, x_affine=aff)
+    if out is None:
+        return None
+    h = out[0]
+    w2f = w2.detach().to(torch.float32).contiguous()
+    ones = torch.ones([x.shape[0], c4], dtype=torch.float32, device=x.device)
+    g = gamma if gamma is not None else torch.ones([c], dtype=torch.float32, device=x.device)
+    ep2 = dict(act='linear', gain=1.0, clamp=None, bias=b2.detach().reshape(-1).to(x.dtype).contiguous() if b2 is not None else None,
+               residual=x_in.detach().contiguous(), gamma=g, res_scale=1.0)
+    out = _plugin.forward(h, w2f, ones, None, 1, 0, None, False, True, force_generic, epilogue=ep2)
     return None if out is None else out[0]

@@ -49,9 +49,15 @@ def test_install_patches_loader_and_modconv(ref_on_path):
         assert torch.equal(ref_gen.modulated_conv2d(x, w, s, padding=1), orig_modconv(x, w, s, padding=1))
         assert torch.equal(ref_bias_act.bias_act(x, torch.zeros(4), act='lrelu'), torch.nn.functional.leaky_relu(x, 0.2) * (2 ** 0.5))
         assert ref_gen.modulated_conv2d is not orig_modconv
+        import networks.utils.convnext_utils as ref_cnx
+        wp, bp = torch.randn(8, 4, 1, 1), torch.randn(1, 8, 1, 1)
+        assert hasattr(ref_cnx.modulated_pointwise_conv2d, '__wrapped__')
+        assert torch.equal(ref_cnx.modulated_pointwise_conv2d(x, wp, s, bp), ref_cnx.modulated_pointwise_conv2d.__wrapped__(x, wp, s, bp))
     finally:
         integ.uninstall()
     assert ref_custom_ops.get_plugin is orig_loader and ref_gen.modulated_conv2d is orig_modconv
+    import networks.utils.convnext_utils as ref_cnx
+    assert not hasattr(ref_cnx.modulated_pointwise_conv2d, '__wrapped__')
 
 
 def test_plugin_signatures_match_reference_pybind():

@@ -16,7 +16,10 @@ What it patches (and nothing else):
    for CUDA tensors; CPU tensors keep going to the reference function (its pure-PyTorch body *is* its reference path).
    ``SynthesisLayer``/``ToRGBLayer`` look the name up in module globals at call time, so they need no change.
 
-``uninstall()`` restores both.  Nothing here imports ``oracle/``.
+3. ``networks.utils.convnext_utils.modulated_pointwise_conv2d`` (reference convnext_utils.py:36, the 1x1 modulated conv of the
+   ConvNeXt layers every shipped config runs) -> ``vfm_vae_b200.modulated_pointwise_conv2d`` for CUDA tensors, same rule.
+
+``uninstall()`` restores all three.  Nothing here imports ``oracle/``.
 """
 import importlib
 
@@ -49,6 +52,20 @@ def install(patch_modconv=True):
 
         modulated_conv2d.__wrapped__ = ref_fn
         gen.modulated_conv2d = modulated_conv2d
+
+        cnx = importlib.import_module('networks.utils.convnext_utils')
+        from .torch_utils.ops.modulated_conv2d import modulated_pointwise_conv2d as ours_pw
+        if 'modulated_pointwise_conv2d' not in _saved:
+            _saved['modulated_pointwise_conv2d'] = cnx.modulated_pointwise_conv2d
+        ref_pw = _saved['modulated_pointwise_conv2d']
+
+        def modulated_pointwise_conv2d(x, weight, style, bias=None, demodulate=True):
+            if x.device.type == 'cuda':
+                return ours_pw(x, weight, style, bias, demodulate)
+            return ref_pw(x, weight, style, bias, demodulate)
+
+        modulated_pointwise_conv2d.__wrapped__ = ref_pw
+        cnx.modulated_pointwise_conv2d = modulated_pointwise_conv2d
     return True
 
 
@@ -59,3 +76,5 @@ def uninstall():
             importlib.import_module(f'torch_utils.ops.{name}')._plugin = None
     if 'modulated_conv2d' in _saved:
         importlib.import_module('networks.generator').modulated_conv2d = _saved.pop('modulated_conv2d')
+    if 'modulated_pointwise_conv2d' in _saved:
+        importlib.import_module('networks.utils.convnext_utils').modulated_pointwise_conv2d = _saved.pop('modulated_pointwise_conv2d')

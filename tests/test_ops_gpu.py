@@ -537,7 +537,8 @@ def test_fused_residual_layer_with_group_norm(cfg, dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
-@pytest.mark.parametrize('cfg', [dict(N=2, C=128, H=16, demod=True), dict(N=3, C=32, H=8, demod=True), dict(N=2, C=128, H=8, demod=False)],
+@pytest.mark.parametrize('cfg', [dict(N=2, C=128, H=16, demod=True), dict(N=3, C=32, H=8, demod=True), dict(N=2, C=128, H=8, demod=False),
+                                 dict(N=2, C=128, H=64, demod=True)],      # 64-pixel rows: the forward reads x straight from NCHW
                          ids=lambda c: f"C{c['C']}H{c['H']}{'' if c['demod'] else 'nodemod'}")
 def test_modulated_pointwise_conv2d_vs_oracle(cfg, dtype):
     """networks/utils/convnext_utils.py:36 drop-in: 1x1 modulated conv C -> 4C + bias, forward and gradients."""

@@ -20,6 +20,8 @@ ap.add_argument('--cin', type=int, default=128)
 ap.add_argument('--cout', type=int, default=128)
 ap.add_argument('--res', type=int, default=256, help='input resolution')
 ap.add_argument('--up', type=int, default=1)
+ap.add_argument('--k', type=int, default=3)
+ap.add_argument('--act', default='lrelu')
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--mode', default='fwd')
 ap.add_argument('--dtype', default='f16')
@@ -29,15 +31,15 @@ dev = 'cuda'
 dt = torch.float16 if a.dtype == 'f16' else torch.float32
 torch.manual_seed(0)
 x = torch.randn(a.batch, a.cin, a.res, a.res, device=dev, dtype=dt)
-w = torch.randn(a.cout, a.cin, 3, 3, device=dev)
+w = torch.randn(a.cout, a.cin, a.k, a.k, device=dev)
 s = torch.randn(a.batch, a.cin, device=dev) + 1
 b = torch.randn(a.cout, device=dev, dtype=dt)
 ro = a.res * a.up
-noise = torch.randn(ro, ro, device=dev)
+noise = torch.randn(ro, ro, device=dev) if a.k == 3 else None
 gamma = torch.full([1, a.cout, 1, 1], 1e-5, device=dev)
 f4 = U.setup_filter([1, 3, 3, 1]).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-kw = dict(noise=noise, up=a.up, padding=1, resample_filter=f4, flip_weight=(a.up == 1))
+kw = dict(noise=noise, up=a.up, padding=a.k // 2, resample_filter=f4, flip_weight=(a.up == 1))
 
 
 def run():
@@ -47,7 +49,7 @@ def run():
     if a.mode in ('fused', 'fused_res'):
         with torch.no_grad():
             res = x if (a.mode == 'fused_res' and a.cin == a.cout and a.up == 1) else None
-            return fused_modconv_bias_act(x, w, s, b, act='lrelu', gain=1.0, clamp=181.0, residual=res, gamma=gamma if res is not None else None,
+            return fused_modconv_bias_act(x, w, s, b, act=a.act, gain=1.0, clamp=181.0 if a.act == 'lrelu' else None, residual=res, gamma=gamma if res is not None else None,
                                           res_scale=math.sqrt(2), **kw)
     xg = x.detach().requires_grad_(True)
     wg = w.detach().requires_grad_(True)

@@ -130,6 +130,21 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// MN-major operand tiles (rows of 64 MN-elements = 128 bytes, K = row index): used by the weight gradient (both operands) and by
+// the 1x1 convs that read their pixel operand straight from the NCHW tensor
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;      // leading byte offset: next 64-channel block
+    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next group of 8 K rows
+    d |= (uint64_t)1 << 46;                                // version
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_mnmajor(int M, int N) {
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 constexpr int BK = 64;
 constexpr float kLoScale = 2048.f;     // the lo term of the fp16 split is stored scaled by 2^11
 
@@ -171,6 +186,7 @@ struct TcArgs {
     float* aux_sum;            // dgrad: [N, Nout] += sum_p aux * acc
     Epilogue ep;               // forward: optional fused bias/activation/residual
     int vec_out, vec_side, vec_add;   // 16-byte vector access allowed on out / (aux | residual) / noise
+    const float* bias_nc;             // forward: optional per-(sample, channel) bias added before the activation (folded input shift)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -253,7 +269,11 @@ template <> __device__ __forceinline__ void store16<float>(float* p, const float
 // PAIR (transposed conv, stride 2): an item computes the two horizontal sub-pixel phases (px = 0, 1) of one row parity
 // into two accumulators and the epilogue interleaves them, so the stores to the 2x-resolution output are contiguous.
 // SPLIT (fp32 tensors): two accumulators per phase (hi*hi and the cross terms), recombined in the epilogue.
-template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX>
+// MNP (1x1 convs, fp16): the pixel operand is read straight from the NCHW tensor as MN-major tiles (one TMA box [64 pixels of a
+// row, 64 channels] per image row of the tile) and the weight operand is a per-sample weight [n][Cout][Cin] that carries the
+// modulation (and a folded input affine map) -- no pre-pass over the activations at all.  Only possible without tap shifts: TMA
+// needs the innermost box start 16-byte aligned, which a +-1 pixel shift of an NCHW row is not.
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmP,
                                                                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPlo, TcArgs p) {
     constexpr int P_BYTES = NPIX * BK * 2;
@@ -326,8 +346,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         const int tap = k / p.kchunks, kc = k - tap * p.kchunks;
                         uint8_t* sw = smem + s * STAGE_BYTES;
                         const int cw = w0 * p.a_s + ph.dx[tap], chh = h0 * p.a_s + ph.dy[tap];
-                        tma_load_3d(sw, &tmW, &full_bar[s], kc * BK, c0, ph.tb[tap]);
-                        tma_load_4d(sw + W_BYTES, &tmP, &full_bar[s], kc * BK, cw, chh, n0);
+                        if (MNP) {
+                            tma_load_4d(sw, &tmW, &full_bar[s], kc * BK, c0, ph.tb[tap], n0);
+#pragma unroll
+                            for (int r = 0; r < NPIX / 64; r++)      // 64-pixel box r of the tile (row-major over th x tw)
+                                tma_load_4d(sw + W_BYTES + r * 8192, &tmP, &full_bar[s], cw + ((64 * r) & (p.tw - 1)), chh + ((64 * r) >> p.tw_sh), kc * BK, n0);
+                        } else {
+                            tma_load_3d(sw, &tmW, &full_bar[s], kc * BK, c0, ph.tb[tap]);
+                            tma_load_4d(sw + W_BYTES, &tmP, &full_bar[s], kc * BK, cw, chh, n0);
+                        }
                         if (SPLIT) {
                             tma_load_3d(sw + W_BYTES + P_BYTES, &tmWlo, &full_bar[s], kc * BK, c0, ph.tb[tap]);
                             tma_load_4d(sw + 2 * W_BYTES + P_BYTES, &tmPlo, &full_bar[s], kc * BK, cw, chh, n0);
@@ -339,7 +366,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(CH, NPIX);
+            constexpr uint32_t idesc = make_idesc_f16(CH, NPIX) | (MNP ? (1u << 16) : 0u);      // bit 16: B operand MN-major
             uint32_t it = 0, icount = 0;
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 int grp, n0, h0, w0, c0;
@@ -358,15 +385,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         tc_fence_after();
                         const uint32_t sw = smem_u32(smem + s * STAGE_BYTES);
                         const uint64_t wdesc = make_kmajor_sw128_desc(sw);
-                        const uint64_t pdesc = make_kmajor_sw128_desc(sw + W_BYTES);
+                        const uint64_t pdesc = MNP ? make_mnmajor_sw128_desc(sw + W_BYTES, 8192) : make_kmajor_sw128_desc(sw + W_BYTES);
                         const uint64_t wdesc_lo = make_kmajor_sw128_desc(sw + W_BYTES + P_BYTES);
                         const uint64_t pdesc_lo = make_kmajor_sw128_desc(sw + 2 * W_BYTES + P_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; kk++) {
                             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (>>4) address field
                             const uint64_t ko = (uint64_t)(2 * kk);
+                            const uint64_t pko = MNP ? (uint64_t)(kk * 128) : ko;                 // MN-major: 16 K rows of 128 bytes
                             const uint32_t accum = (k > 0 || kk > 0) ? 1u : 0u;
-                            umma_f16(acc, wdesc + ko, pdesc + ko, idesc, accum);
+                            umma_f16(acc, wdesc + ko, pdesc + pko, idesc, accum);
                             if (SPLIT) {
                                 umma_f16(acc + NPIX, wdesc + ko, pdesc_lo + ko, idesc, accum);
                                 umma_f16(acc + NPIX, wdesc_lo + ko, pdesc + ko, idesc, 1u);
@@ -433,19 +461,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 if (p.ep.bias) bias = to_acc(((const TOut*)p.ep.bias)[ch]);
                 if (has_res) gam = p.ep.gamma[ch] * p.ep.res_scale;
             }
+            const float bias0 = bias;
+            // can the whole item go through the vectorised fast path?  (complete 16-pixel chunks, 32-byte aligned tensors)
+            const bool wide_item = wide && p.vec_out && (!side_base || p.vec_side) && (PAIR || p.out_s == 1) &&
+                                   (PAIR ? (2 * (w0 + p.tw) <= p.out_W) : (w0 + p.tw <= ph0.Wg && w0 + p.tw + ph0.ox <= p.out_W));
             // side input (x of the dstyles reduction / residual of the fused layer): this thread's 16-pixel chunks, prefetched
             uint32_t pre[PRE ? NIT * RW : 1];
-            uint32_t pre_ok = 0;
-            if (PRE && side_base && wide && p.vec_side) {
+            if (PRE && side_base && wide_item) {
 #pragma unroll
                 for (int c = 0; c < NIT; c++) {
                     int n, gh, gw;
                     locate(chalf * (NPIX / 2) + c * 16, n0, h0, w0, n, gh, gw);
-                    const bool ok = n < p.N && gh < ph0.Hg && gw + 16 <= ph0.Wg && gw + 16 <= p.out_W && gh < p.out_H;
-                    if (ok) {
+                    if (n < p.N && gh < ph0.Hg && gh < p.out_H)
                         raw16_load<TOut>(side_base + ((size_t)n * p.Nout + ch) * side_plane + (size_t)gh * side_pitch + gw, &pre[c * RW]);
-                        pre_ok |= 1u << c;
-                    }
                 }
             }
             if (has_add) asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -459,6 +487,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 ds_acc = 0.f;
                 cur_n = n;
                 scale = (n >= 0 && n < p.N) ? p.oscale[(size_t)n * p.Nout + ch] * gsv : 0.f;
+                if (!DGRAD && p.bias_nc && n >= 0 && n < p.N) bias = bias0 + p.bias_nc[(size_t)n * p.Nout + ch];
                 if (!DGRAD && has_res && p.ep.res_a && n >= 0 && n < p.N) {
                     res_a = p.ep.res_a[(size_t)n * p.Nout + ch] * p.ep.res_scale;
                     res_b = p.ep.res_b[(size_t)n * p.Nout + ch] * p.ep.res_scale;
@@ -487,8 +516,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         for (int i = 0; i < NV; i++) o[i] *= (o[i] > 0.f) ? gp : gn;
                     } else if (p.ep.act == VFM_EP_ACT_GELU) {
                         const float hg = 0.5f * p.ep.gain;
+                        if (sizeof(TOut) == 2) {
+                            // fp16 output: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 + the fast exp / reciprocal, far below
+                            // half precision) -- 14 instead of ~30 instructions per element; the 4C-wide GELU epilogue is issue-bound
 #pragma unroll
-                        for (int i = 0; i < NV; i++) o[i] = hg * o[i] * (1.f + erff(o[i] * 0.70710678118654752f));
+                            for (int i = 0; i < NV; i++) {
+                                const float z = fabsf(o[i]) * 0.70710678118654752f;
+                                const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+                                float q = fmaf(1.061405429f, t, -1.453152027f);
+                                q = fmaf(q, t, 1.421413741f);
+                                q = fmaf(q, t, -0.284496736f);
+                                q = fmaf(q, t, 0.254829592f);
+                                const float e = 1.f - q * t * __expf(-z * z);           // erf(|x| / sqrt2)
+                                o[i] = hg * (o[i] + fabsf(o[i]) * e);                    // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < NV; i++) o[i] = hg * o[i] * (1.f + erff(o[i] * 0.70710678118654752f));
+                        }
                     } else if (p.ep.gain != 1.f) {
 #pragma unroll
                         for (int i = 0; i < NV; i++) o[i] *= p.ep.gain;
@@ -504,7 +549,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 }
             };
 
-            if (wide) {
+            if (wide_item) {
+                // fast path: every 16-pixel chunk of the item is complete and 32-byte aligned (all tiles of the decoder's layers);
+                // ragged or unaligned items take the compact element-wise path below, which keeps this unrolled code small enough
+                // for the instruction cache (a 1x1 conv's epilogue is not hidden behind MMAs)
                 uint32_t raw[2][NLD][16];
                 auto issue = [&](int step, int slot) {
 #pragma unroll
@@ -541,36 +589,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                             float o[32];
 #pragma unroll
                             for (int i = 0; i < 16; i++) { o[2 * i] = v[0][i] * scale; o[2 * i + 1] = v[NSUB - 1][i] * scale; }
-                            const int ox0 = gw0 * 2;
-                            int nv = p.out_W - ox0; nv = nv > 32 ? 32 : nv;
-                            const int nw = (ph0.Wg - gw0) * 2;             // columns this tile may write (its px = 0 grid)
-                            nv = nv > nw ? nw : nv;
-                            if (nv <= 0) break;
-                            TOut* outp = (TOut*)p.out + plane * HW + (size_t)oy * p.out_pitch + ox0;
-                            store16<TOut>(outp, o, nv > 16 ? 16 : nv, p.vec_out);
-                            if (nv > 16) store16<TOut>(outp + 16, o + 16, nv - 16, p.vec_out);
+                            TOut* outp = (TOut*)p.out + plane * HW + (size_t)oy * p.out_pitch + gw0 * 2;
+                            store16<TOut>(outp, o, 16, true);
+                            store16<TOut>(outp + 16, o + 16, 16, true);
                             break;
                         }
-                        int nv = ph0.Wg - gw0; nv = nv > 16 ? 16 : nv;
-                        const int ox0 = gw0 * p.out_s + ph0.ox;
-                        if (p.out_s != 1) {
-                            // strided output without pairing (not used by the decoder): scalar stores
-#pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                const int ox = ox0 + i * p.out_s;
-                                if (i < nv && ox < p.out_W) ((TOut*)p.out)[plane * HW + (size_t)oy * p.out_pitch + ox] = from_acc<TOut, float>(v[0][i] * scale);
-                            }
-                            break;
-                        }
-                        { const int lim = p.out_W - ox0; nv = nv > lim ? lim : nv; }
-                        if (nv <= 0) break;
+                        const int ox0 = gw0 + ph0.ox;
                         const size_t off = plane * HW + (size_t)oy * p.out_pitch + ox0;
                         float* o = v[0];
                         float sd[16];
-                        if (PRE && side_base) {
-                            if (pre_ok & (1u << step)) raw16_unpack<TOut>(&pre[step * RW], sd);
-                            else load16<TOut>(side_base + plane * side_plane + (size_t)oy * side_pitch + ox0, sd, nv, false);
-                        }
+                        if (PRE && side_base) raw16_unpack<TOut>(&pre[step * RW], sd);
                         if (DGRAD) {
                             if (do_ds) {
 #pragma unroll
@@ -589,7 +617,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                             }
                             finish_fwd(o, nz, sd, std::integral_constant<int, 16>());
                         }
-                        store16<TOut>((TOut*)p.out + off, o, nv, p.vec_out);
+                        store16<TOut>((TOut*)p.out + off, o, 16, true);
                     } while (0);
                     if (step + 1 < NIT) tmem_ld_wait();
                 }
@@ -659,19 +687,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 // MN-major tile (channels contiguous, K = pixel rows) in the 128-byte-swizzled layout; two boxes side by side make the
 // 128-wide M (resp. N) extent.  The tap shift (and the stride 2 of the transposed conv) is the coordinate / element
 // stride of the dz box, zero padding is TMA out-of-bounds fill.  Split-K over pixel tiles, fp32 red.add into dweight.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;      // leading byte offset: next 64-channel block
-    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset: next group of 8 K rows
-    d |= (uint64_t)1 << 46;                                // version
-    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
-    return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_f16_mnmajor(int M, int N) {
-    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 constexpr int WK = 64;                      // pixels per K block
 constexpr int WBOX_BYTES = WK * 128;        // one [64 px][64 ch] box = 8 KB
 constexpr int WOP_BYTES = 2 * WBOX_BYTES;   // 128 channels
@@ -930,6 +945,28 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, const float* __r
     }
 }
 
+// 1x1 direct-NCHW path: per-sample weights  wt[n][o][i] = W[o,i] * a[o] * s'[n,i] * (xa[n,i] or 1)   (fp16)  and the folded
+// input shift  pb[n,o] = d[n,o] * sum_i W[o,i] * a[o] * s'[n,i] * xb[n,i]   (fp32, added by the epilogue before the activation).
+// One warp per (n, o): coalesced along i, the bias sum by warp shuffle.
+__global__ void __launch_bounds__(256) weight_prep_mod1x1_kernel(const float* __restrict__ w, const float* __restrict__ a, const float* __restrict__ iscale,
+                                                                 const float* __restrict__ xa, const float* __restrict__ xb, const float* __restrict__ d,
+                                                                 __half* __restrict__ wt, float* __restrict__ pb, int N, int O, int I) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N * O) return;
+    const int n = warp / O, o = warp - n * O;
+    const float ao = a[o];
+    float acc = 0.f;
+    for (int i = lane; i < I; i += 32) {
+        const float base = w[(size_t)o * I + i] * ao * iscale[(size_t)n * I + i];
+        wt[((size_t)n * O + o) * I + i] = __float2half_rn(xa ? base * xa[(size_t)n * I + i] : base);
+        if (xb) acc = fmaf(base, xb[(size_t)n * I + i], acc);
+    }
+    if (pb) {
+        acc = warp_sum(acc);
+        if (lane == 0) pb[(size_t)n * O + o] = acc * d[(size_t)n * O + o];
+    }
+}
+
 // per-sample power-of-two normalisation of the activation scale so that |x * scale| stays far from the fp16 limit:
 //   a_scale[n,i] = in_scale[n,i] * c2[n],  o_scale[n,o] = out_scale[n,o] / c2[n],  c2 = 2^-ceil(log2(max_i |in_scale|)) if that max > 1
 //   with an input affine map x -> x * xa + xb:  a_scale *= xa,  a_shift[n,i] = in_scale * c2 * xb
@@ -1036,13 +1073,13 @@ int ilog2(int v) { int r = 0; while ((1 << r) < v) r++; return r; }
 
 size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 256 + 2 * 256 * sizeof(float); }
 
-template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX>
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP = false>
 int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PAIR, NPIX>;
+    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PAIR, NPIX, MNP>;
     size_t smem = smem_bytes();
     VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0,
-                      "i%do%dh%d%s%s%s", a.kchunks * BK, a.Nout, a.out_H, PAIR ? "p" : "", (!DGRAD && a.ep.enable) ? "e" : "",
+                      "i%do%dh%d%s%s%s%s", a.kchunks * BK, a.Nout, a.out_H, MNP ? "m" : "", PAIR ? "p" : "", (!DGRAD && a.ep.enable) ? "e" : "",
                       (DGRAD ? a.aux_sum != nullptr : (a.ep.enable && a.ep.residual)) ? "r" : "");
     kern<<<grid, kConvThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     return launch_status("modconv conv_tc_kernel");
@@ -1056,8 +1093,10 @@ struct TcOperands {
 
 // One implicit-GEMM conv.  `args` must have ph[], out*, a_s, scales, add/aux already filled in; this sets the tiling.
 // nphases == 4: the phases are the sub-pixel phases of a stride-2 transposed conv in the order 2*py + px (PAIR kernel).
-int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream) {
+// mnp: op.act is the NCHW fp16 tensor itself and op.wt the per-sample weights [N][ntaps][Nout][Cin] (1x1 convs only, see conv_tc_kernel).
+int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream, bool mnp = false) {
     const bool pair = (nphases == 4);
+    if (mnp && (f32 || pair || dgrad || a.a_s != 1 || op.ntaps != 1)) { set_error("tcgen05 conv: direct NCHW operands need an fp16 1x1 forward conv"); return VFM_ERR_INVALID; }
     if (nphases != 1 && nphases != 4) { set_error("tcgen05 conv: unsupported phase structure"); return VFM_ERR_INVALID; }
     if (pair && (dgrad || a.ep.enable || a.add)) { set_error("tcgen05 conv: the paired-phase kernel has no fused epilogue"); return VFM_ERR_INVALID; }
     const int npix = (!f32 && !pair) ? 256 : 128;
@@ -1065,6 +1104,10 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     double taps_px = 0;
     for (int i = 0; i < nphases; i++) { Hg = max(Hg, a.ph[i].Hg); Wg = max(Wg, a.ph[i].Wg); taps_px += (double)a.ph[i].ntaps * a.ph[i].Hg * a.ph[i].Wg; }
     pick_tile(Hg, Wg, npix, a.a_s, a.tw, a.th, a.tn);
+    if (mnp) {                                                // 64-pixel TMA boxes; the widest rows that divide W keep the DRAM accesses long
+        a.tw = (op.Wa % 256 == 0) ? 256 : (op.Wa % 128 == 0 ? 128 : 64);
+        a.th = npix / a.tw; a.tn = 1;
+    }
     a.tw_sh = ilog2(a.tw); a.th_sh = ilog2(a.th);
     a.tiles_w = ceil_div(Wg, a.tw); a.tiles_h = ceil_div(Hg, a.th);
     a.kchunks = op.Cin / BK;
@@ -1083,7 +1126,20 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     uint32_t pstr[4] = {1u, (uint32_t)a.a_s, (uint32_t)a.a_s, 1u};
     uint64_t wdims[3] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps};
     uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)CH, 1u};
-    int st = encode_map(&maps[0], op.wt, 3, wdims, wbox, nullptr); if (st) return st;
+    int st;
+    if (mnp) {
+        uint64_t wdims4[4] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps, (uint64_t)op.N};
+        uint32_t wbox4[4] = {(uint32_t)BK, (uint32_t)CH, 1u, 1u};
+        uint64_t xdims[4] = {(uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.Cin, (uint64_t)op.N};
+        uint32_t xbox[4] = {64u, 1u, (uint32_t)BK, 1u};
+        st = encode_map(&maps[0], op.wt, 4, wdims4, wbox4, nullptr); if (st) return st;
+        st = encode_map(&maps[1], op.act, 4, xdims, xbox, nullptr); if (st) return st;
+        maps[2] = maps[0]; maps[3] = maps[1];
+        const long long items = (long long)a.tiles_w * a.tiles_h * op.N * (op.Nout / CH);
+        dim3 g((unsigned)(items < kNumSMs ? items : kNumSMs), 1, 1);
+        return launch_tc<__half, false, false, false, 256, true>(maps, a, g, 2.0 * op.N * taps_px * (double)op.Nout * op.Cin, stream);
+    }
+    st = encode_map(&maps[0], op.wt, 3, wdims, wbox, nullptr); if (st) return st;
     st = encode_map(&maps[1], op.act, 4, pdims, pbox, pstr); if (st) return st;
     st = encode_map(&maps[2], f32 ? op.wt_lo : op.wt, 3, wdims, wbox, nullptr); if (st) return st;
     st = encode_map(&maps[3], f32 ? op.act_lo : op.act, 4, pdims, pbox, pstr); if (st) return st;
@@ -1127,9 +1183,15 @@ bool is_f32(const vfm_modconv_desc& d) { return d.dtype == VFM_F32; }
 struct TcWorkspace {
     __half *act, *act_lo, *wt, *wt_lo;       // NHWC activation operand (x in forward, d*dz in backward), re-laid-out weights
     __half *xt, *xt_lo;                      // backward only: x*s' NHWC for the weight gradient
+    __half* wt_mod; float* pb;               // forward, 1x1 direct-NCHW path: per-sample weights [N][O][I] and folded-shift bias [N][O]
     float *a_scale, *a_shift, *o_scale, *gs; // gs: [0] gk, [1] 1/gk, [2] c2g, [3] 1/(gk*c2g)
     unsigned int* amax;
 };
+
+// forward 1x1 convs that can read x straight from NCHW (conv_tc_kernel MNP): fp16, rows that split into 64-pixel boxes
+bool mnp_candidate(const vfm_modconv_desc& d) {
+    return d.dtype == VFM_F16 && d.kh == 1 && d.kw == 1 && d.up == 1 && d.in_w % 64 == 0 && d.in_channels % 64 == 0;
+}
 
 void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direction, TcWorkspace& w) {
     const bool f32 = is_f32(d);
@@ -1141,6 +1203,8 @@ void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direct
     w.wt = cv.take<__half>(wel);
     w.wt_lo = f32 ? cv.take<__half>(wel) : nullptr;
     w.xt = w.xt_lo = nullptr;
+    w.wt_mod = nullptr; w.pb = nullptr;
+    if (direction == 0 && mnp_candidate(d)) { w.wt_mod = cv.take<__half>(wel * d.batch); w.pb = cv.take<float>((size_t)d.batch * d.out_channels); }
     if (direction == 1) {
         w.xt = cv.take<__half>(x_el);
         w.xt_lo = f32 ? cv.take<__half>(x_el) : nullptr;
@@ -1236,6 +1300,24 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     TcWorkspace w;
     carve_tc(cv, d, s, 0, w);
     if (!cv.ok()) { set_error("modulated_conv2d: tcgen05 workspace too small"); return VFM_ERR_WORKSPACE; }
+    if (w.wt_mod && aligned16(x)) {
+        // 1x1 direct path: A = x as it lies in memory (NCHW), B = per-sample W * a * s' (* input scale), epilogue scale = d,
+        // the input shift becomes a per-(n,o) bias
+        {
+            KernelTimer timer("modconv_weight_mod1x1", stream, 0.0, (double)N * O * I * 2.0, "i%do%d", I, O);
+            weight_prep_mod1x1_kernel<<<ceil_div(N * O * 32, 256), 256, 0, stream>>>(weight, k.a, k.iscale, x_scale, x_shift, k.d, w.wt_mod, x_shift ? w.pb : nullptr, N, O, I);
+        }
+        int st0 = launch_status("modconv weight_prep_mod1x1_kernel"); if (st0) return st0;
+        TcArgs a;
+        TcPhase& ph = a.ph[0];
+        ph.ntaps = 1; ph.dy[0] = 0; ph.dx[0] = 0; ph.tb[0] = 0;
+        ph.oy = ph.ox = 0; ph.Hg = s.zh; ph.Wg = s.zw;
+        a.out_s = 1; a.out_H = s.zh; a.out_W = s.zw; a.out_pitch = zpitch; a.a_s = 1;
+        a.out = z; a.oscale = k.d; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr; a.ep = ep;
+        a.bias_nc = x_shift ? w.pb : nullptr;
+        TcOperands op{(__half*)x, nullptr, w.wt_mod, nullptr, N, d.in_h, d.in_w, I, O, 1};
+        return run_tc_conv(false, false, op, a, 1, stream, true);
+    }
     // A = x * s' * c2, B = W * a, epilogue scale = d / c2
     scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O, x_scale, x_shift, x_scale ? w.a_shift : nullptr);
     int st = launch_status("modconv scale_prep_kernel"); if (st) return st;
@@ -1269,6 +1351,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     }
     a.out_H = s.zh; a.out_W = s.zw; a.out_pitch = zpitch; a.a_s = 1;
     a.out = z; a.oscale = w.o_scale; a.gscale_inv = nullptr; a.add = noise; a.add_sn = noise_sn; a.aux = nullptr; a.aux_sum = nullptr; a.ep = ep;
+    a.bias_nc = nullptr;
     TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, d.in_h, d.in_w, I, O, s.taps.ntaps};
     return run_tc_conv(f32, false, op, a, nph, stream);
 }
@@ -1309,7 +1392,7 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         ph.oy = ph.ox = 0; ph.Hg = d.in_h; ph.Wg = d.in_w;
         a.out_s = 1; a.out_H = d.in_h; a.out_W = d.in_w; a.out_pitch = d.in_w; a.a_s = sn;
         a.out = dx; a.oscale = k.iscale; a.gscale_inv = gs ? gs + 1 : nullptr; a.add = nullptr; a.add_sn = 0;
-        a.aux = dsum ? x : nullptr; a.aux_sum = dsum; a.ep = no_epilogue();
+        a.aux = dsum ? x : nullptr; a.aux_sum = dsum; a.ep = no_epilogue(); a.bias_nc = nullptr;
         TcOperands op{w.act, w.act_lo, w.wt, w.wt_lo, N, s.zh, s.zw, O, I, dt.ntaps};
         st = run_tc_conv(f32, true, op, a, 1, stream); if (st) return st;
     }

@@ -137,6 +137,10 @@ typedef struct {
     int32_t      ep_act;
     double       ep_alpha, ep_gain, ep_clamp;
     const void*  ep_bias;     /* [channels], dtype of x, or NULL */
+    /* 0 = zero padding (the reference op); 1 = replicate (clamp-to-edge) padding for same-size blurs with up = down = 1 and
+     * <= 5x5 taps: F.pad(x, mode='replicate') + depthwise conv with a fixed kernel, the blur behind the pixel-shuffle upsampler
+     * (networks/utils/convnext_utils.py:250-255).  Returns VFM_ERR_NO_KERNEL where the streaming kernel does not apply. */
+    int32_t      pad_mode;
 } vfm_upfirdn2d_params;
 
 VFM_API int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream);

@@ -206,6 +206,31 @@ def test_upfirdn2d_streaming_blur(dtype, cfg):
     assert rel_err(ys, O.upfirdn2d(xq[..., :cfg['shape'][3] - 3], f, **kw)) <= tol
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('cfg', [dict(shape=(2, 5, 16, 32), taps=[1, 2, 1]), dict(shape=(2, 3, 24, 64), taps=[1, 4, 6, 4, 1]),
+                                 dict(shape=(1, 4, 9, 8), taps=[1, 4, 6, 4, 1]), dict(shape=(1, 2, 40, 512), taps=[1, 4, 6, 4, 1]),
+                                 dict(shape=(2, 2, 12, 24), taps='rand5')], ids=lambda c: f"{c['shape'][2]}x{c['shape'][3]}-{c['taps']}")
+def test_blur2d_replicate(cfg, dtype):
+    """replicate-pad + fixed-kernel depthwise blur of the pixel-shuffle upsampler (convnext_utils.py:250-255) in one kernel."""
+    V = _ops()
+    g = torch.Generator().manual_seed(13)
+    if cfg['taps'] == 'rand5':
+        k2 = torch.randn(5, 5, generator=g)
+    else:
+        k = torch.tensor(cfg['taps'], dtype=torch.float32)
+        k2 = torch.outer(k, k)
+        k2 = k2 / k2.sum()
+    kh, kw = k2.shape
+    pad = ((kw - 1) // 2, (kw - 1) // 2 + int(kw % 2 == 0), (kh - 1) // 2, (kh - 1) // 2 + int(kh % 2 == 0))
+    xq = torch.randn(cfg['shape'], generator=g).to(dtype).float()
+    Cc = cfg['shape'][1]
+    yr = torch.nn.functional.conv2d(torch.nn.functional.pad(xq, pad, mode='replicate'), k2[None, None].repeat(Cc, 1, 1, 1), groups=Cc)
+    with torch.no_grad():
+        y = V.upfirdn2d.blur2d_replicate(xq.to(DEV, dtype), k2.to(DEV), pad)
+    assert y is not None and y.shape == yr.shape and y.dtype == dtype
+    assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

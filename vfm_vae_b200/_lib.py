@@ -32,7 +32,8 @@ class Upfirdn2dParams(C.Structure):
                 ('out_w', _i32), ('out_h', _i32),
                 ('out_stride_w', _i64), ('out_stride_h', _i64), ('out_stride_c', _i64), ('out_stride_n', _i64),
                 ('add', _vp), ('add_stride_h', _i64), ('add_stride_n', _i64),
-                ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64), ('ep_bias', _vp)]
+                ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64), ('ep_bias', _vp),
+                ('pad_mode', _i32)]
 
 
 class FilteredLreluParams(C.Structure):

@@ -32,6 +32,7 @@ struct UpfirdnArgs {
     int xstart, ystart, tiles_x, tiles_y;
     int vec_ok;   // input rows can be staged with 16-byte loads
     int ep_enable, ep_act; float ep_alpha, ep_gain, ep_clamp; const void* ep_bias;
+    int pad_mode;    // 0 = zero padding, 1 = replicate (clamp to edge; streaming blur kernel only)
 };
 
 template <class T, class S> __device__ __forceinline__ S ep_apply(const UpfirdnArgs& p, S v, int c) {
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(UpfirdnArgs p) {
 // converted once and every output row leaves as one aligned vector store.  A rank-1 filter (the decoder's
 // [1,3,3,1] x [1,3,3,1]) is detected in the kernel and evaluated separably (8 instead of 16 FMAs per output).
 // Requires 16-byte aligned rows on both sides; everything else goes to the tiled / generic kernels.
-struct BlurTaps { float f[4][4]; float fx[4], fy[4]; };
+template <int FT> struct BlurTaps { float f[FT][FT]; float fx[FT], fy[FT]; };
 
 // 128- / 256-bit streaming accesses of NB bytes (16, 32 or 64)
 template <int NB> __device__ __forceinline__ void ldg_words(const void* p, uint32_t* w) {
@@ -270,10 +271,11 @@ template <int NB> __device__ __forceinline__ void stg_words(void* p, const uint3
 }
 
 // NC = output columns per thread (8, or 16 for fp16 rows aligned to 32 bytes: one 256-bit load / store per row)
-template <class T, int PX, bool SEP, int NC>
-__device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& k, int CG, int strips, int strip_rows) {
+// FT = taps per dimension (4, or 5 for the pixel-shuffle upsampler's [1,4,6,4,1] blur); REPL = replicate (clamp-to-edge) padding
+template <class T, int PX, bool SEP, int NC, int FT, bool REPL>
+__device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps<FT>& k, int CG, int strips, int strip_rows) {
     constexpr int NL = PX;                 // halo columns on the left
-    constexpr int NR = 3 - PX;             // halo columns on the right
+    constexpr int NR = FT - 1 - PX;        // halo columns on the right
     constexpr int EW = (int)(4 / sizeof(T));   // elements per 32-bit word (2 for fp16, 1 for fp32)
     constexpr int NW = NC / EW;            // words of the thread's own NC columns
     constexpr int NBYTES = NC * (int)sizeof(T);
@@ -306,14 +308,14 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     const bool lrelu = p.ep_enable && p.ep_act == 3;
     const float alpha = p.ep_alpha;
 
-    float acc[4][NC];
+    float acc[FT][NC];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < FT; a++)
 #pragma unroll
         for (int b = 0; b < NC; b++) acc[a][b] = acc_init;
 
-    // input rows iy = oy - pady0 + ty  ->  rows [oy_begin - pady0, oy_end - 1 - pady0 + 3]
-    const int nrows = feeds ? (oy_end - oy_begin + 3) : 0;
+    // input rows iy = oy - pady0 + ty  ->  rows [oy_begin - pady0, oy_end - 1 - pady0 + FT - 1]
+    const int nrows = feeds ? (oy_end - oy_begin + FT - 1) : 0;
     const int nrows_warp = __reduce_max_sync(0xffffffffu, nrows);      // shuffles need the whole warp in the loop
 
     // Loads never wait for their data inside fetch(): a vector / word that straddles the row end is loaded whole (it is
@@ -337,7 +339,8 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
         for (int i = 0; i < NW + NE; i++) partial = partial || (keep[i] != 0xffffffffu);
     }
     // rows this thread may load: inside the image and not beyond the last row its strip needs
-    const unsigned in_h_eff = feeds ? (unsigned)max(0, min(p.in_h, oy_end - p.pady0 + 3)) : 0u;
+    const unsigned in_h_eff = feeds ? (unsigned)max(0, min(p.in_h, oy_end - p.pady0 + FT - 1)) : 0u;
+    const int iy_last = oy_end - 1 - p.pady0 + FT - 1;                     // last input row the strip needs (REPL: rows beyond are not fetched)
     // the aligned vector(s) of the own columns that contain at least one valid element
     bool own_ok[NBYTES / 16 >= 2 && NBYTES == 16 * 2 && sizeof(T) == 4 ? 2 : 1];
     constexpr int NSEG = (sizeof(T) == 4 && NBYTES == 32) ? 2 : 1;          // fp32 rows are only 16-byte aligned: two 128-bit loads
@@ -354,21 +357,24 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     auto fetch = [&](uint32_t* w) {
 #pragma unroll
         for (int i = 0; i < NW + NE; i++) w[i] = 0u;
-        const bool ok = (unsigned)iy_f < in_h_eff;
+        // zero padding: rows outside the image stay zero;  replicate: they are the clamped row
+        const bool ok = REPL ? (feeds && iy_f <= iy_last) : ((unsigned)iy_f < in_h_eff);
+        const T* rp = REPL ? xp + ox0 + (int64_t)min(max(iy_f, 0), p.in_h - 1) * p.ish : rp_f;
         if (NSEG == 1) {
-            if (ok && own_ok[0]) ldg_words<NBYTES>(rp_f, w);
+            if (ok && own_ok[0]) ldg_words<NBYTES>(rp, w);
         } else {
-            if (ok && own_ok[0]) ldg_words<16>(rp_f, w);
-            if (ok && own_ok[NSEG - 1]) ldg_words<16>(rp_f + 4, w + 4);
+            if (ok && own_ok[0]) ldg_words<16>(rp, w);
+            if (ok && own_ok[NSEG - 1]) ldg_words<16>(rp + 4, w + 4);
         }
 #pragma unroll
-        for (int i = 0; i < WL; i++) if (ok && el_ok[i]) w[NW + i] = __ldg((const uint32_t*)(rp_f - (WL - i) * EW));
+        for (int i = 0; i < WL; i++) if (ok && el_ok[i]) w[NW + i] = __ldg((const uint32_t*)(rp - (WL - i) * EW));
 #pragma unroll
-        for (int i = 0; i < WR; i++) if (ok && er_ok[i]) w[NW + WL + i] = __ldg((const uint32_t*)(rp_f + NC + i * EW));
+        for (int i = 0; i < WR; i++) if (ok && er_ok[i]) w[NW + WL + i] = __ldg((const uint32_t*)(rp + NC + i * EW));
         rp_f += p.ish;
         iy_f++;
     };
-    // in[0 .. NC+2] = input columns ox0 - PX .. ox0 - PX + NC + 2, from the thread's own words and its neighbours'
+    const bool row_end = ox0 + NC >= p.in_w;               // REPL (in_w is a multiple of NC there): the thread owns the last columns
+    // in[0 .. NC+FT-2] = input columns ox0 - PX .. ox0 - PX + NC + FT - 2, from the thread's own words and its neighbours'
     auto expand = [&](uint32_t* w, float* in) {
         if (partial) {          // thread-constant; lanes whose vectors lie wholly inside the row skip the masking
 #pragma unroll
@@ -396,11 +402,11 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
             for (int i = 0; i < WR; i++) right[i] = __uint_as_float(hr[i]);
         }
 #pragma unroll
-        for (int i = 0; i < NL; i++) in[i] = left[WL * EW - NL + i];
+        for (int i = 0; i < NL; i++) in[i] = (REPL && cgi == 0) ? own[0] : left[WL * EW - NL + i];
 #pragma unroll
         for (int i = 0; i < NC; i++) in[NL + i] = own[i];
 #pragma unroll
-        for (int i = 0; i < NR; i++) in[NL + NC + i] = right[i];
+        for (int i = 0; i < NR; i++) in[NL + NC + i] = (REPL && row_end) ? own[NC - 1] : right[i];
     };
     // the fused addend (noise) of an output row, fetched two rows before it is needed (running cursor oy_a / ap)
     int oy_a = oy_begin;
@@ -423,11 +429,11 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
     };
     const bool has_clamp = p.ep_enable && p.ep_clamp >= 0.f;
     const unsigned emit_rows = active ? (unsigned)(oy_end - oy_begin) : 0u;      // output rows this thread stores
-    int orow = -3;                                                                // output row (strip-relative) completed by the current input row
-    T* op = yp + ox0 + (int64_t)(oy_begin - 3) * p.osh;                           // its address (dereferenced only for 0 <= orow < emit_rows)
+    int orow = -(FT - 1);                                                         // output row (strip-relative) completed by the current input row
+    T* op = yp + ox0 + (int64_t)(oy_begin - (FT - 1)) * p.osh;                           // its address (dereferenced only for 0 <= orow < emit_rows)
     auto emit = [&](float* o, const float* addv) {
         if ((unsigned)orow < emit_rows) {
-            if (p.add) {
+            if (FT == 4 && p.add) {
 #pragma unroll
                 for (int i = 0; i < NC; i++) o[i] = fmaf(addv[i], eg, o[i]);
             }
@@ -459,53 +465,60 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps& 
         orow++;
     };
 
-    // input row r (0-based inside the strip) feeds output rows r - ty (ty = 0..3); output row r - 3 is complete after it.
-    // A ring of four row vectors is kept in flight (a slot is refilled with row r + 4 as soon as row r has been unpacked)
-    // and the addend of an output row is fetched two rows before it is needed.
-    uint32_t wq[4][NW + NE];
+    // input row r (0-based inside the strip) feeds output rows r - ty (ty < FT); output row r - (FT-1) is complete after it.
+    // A ring of FT row vectors is kept in flight (a slot is refilled with row r + FT as soon as row r has been unpacked)
+    // and the addend of an output row is fetched two rows before it is needed (FT == 4 only).
+    uint32_t wq[FT][NW + NE];
     float addq[2][NC];
+    const bool use_add = (FT == 4) && p.add != nullptr;
 #pragma unroll
-    for (int rr = 0; rr < 4; rr++) fetch(wq[rr]);
-    if (p.add) { fetch_add(addq[1]); fetch_add(addq[0]); }
+    for (int rr = 0; rr < FT; rr++) fetch(wq[rr]);
+    if (use_add) { fetch_add(addq[1]); fetch_add(addq[0]); }
 #pragma unroll 1
-    for (int r0 = 0; r0 < nrows_warp; r0 += 4) {
+    for (int r0 = 0; r0 < nrows_warp; r0 += FT) {
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-            float in[NC + 3];
+        for (int rr = 0; rr < FT; rr++) {
+            float in[NC + FT - 1];
             expand(wq[rr], in);
             fetch(wq[rr]);
             if (SEP) {
                 float h[NC];
 #pragma unroll
-                for (int i = 0; i < NC; i++) h[i] = k.fx[0] * in[i] + k.fx[1] * in[i + 1] + k.fx[2] * in[i + 2] + k.fx[3] * in[i + 3];
+                for (int i = 0; i < NC; i++) {
+                    float t = k.fx[0] * in[i];
 #pragma unroll
-                for (int ty = 0; ty < 4; ty++)
+                    for (int tx = 1; tx < FT; tx++) t = fmaf(k.fx[tx], in[i + tx], t);
+                    h[i] = t;
+                }
 #pragma unroll
-                    for (int i = 0; i < NC; i++) acc[(rr - ty) & 3][i] = fmaf(k.fy[ty], h[i], acc[(rr - ty) & 3][i]);
+                for (int ty = 0; ty < FT; ty++)
+#pragma unroll
+                    for (int i = 0; i < NC; i++) acc[(rr - ty + FT) % FT][i] = fmaf(k.fy[ty], h[i], acc[(rr - ty + FT) % FT][i]);
             } else {
 #pragma unroll
-                for (int ty = 0; ty < 4; ty++)
+                for (int ty = 0; ty < FT; ty++)
 #pragma unroll
-                    for (int tx = 0; tx < 4; tx++)
+                    for (int tx = 0; tx < FT; tx++)
 #pragma unroll
-                        for (int i = 0; i < NC; i++) acc[(rr - ty) & 3][i] = fmaf(k.f[ty][tx], in[i + tx], acc[(rr - ty) & 3][i]);
+                        for (int i = 0; i < NC; i++) acc[(rr - ty + FT) % FT][i] = fmaf(k.f[ty][tx], in[i + tx], acc[(rr - ty + FT) % FT][i]);
             }
-            // output row (r - 3) used accumulator slot (rr - 3) & 3 == (rr + 1) & 3
+            // output row r - (FT-1) used accumulator slot (rr + 1) % FT
             const bool emitted = orow >= 0;
-            emit(acc[(rr + 1) & 3], addq[rr & 1]);
-            if (p.add && emitted) fetch_add(addq[rr & 1]);
+            emit(acc[(rr + 1) % FT], addq[rr & 1]);
+            if (use_add && emitted) fetch_add(addq[rr & 1]);
 #pragma unroll
-            for (int i = 0; i < NC; i++) acc[(rr + 1) & 3][i] = acc_init;
+            for (int i = 0; i < NC; i++) acc[(rr + 1) % FT][i] = acc_init;
         }
     }
 }
 
-__device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps& k) {
+template <int FT>
+__device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps<FT>& k) {
     // correlation taps with the gain folded in (fp32 product, like the reference's scaled filter tensor); missing taps = 0
 #pragma unroll
-    for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < FT; ty++)
 #pragma unroll
-        for (int tx = 0; tx < 4; tx++) {
+        for (int tx = 0; tx < FT; tx++) {
             float v = 0.f;
             if (tx < p.fw && ty < p.fh) {
                 const int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
@@ -517,14 +530,14 @@ __device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps& k) {
     // rank-1 test: f == fy (x) fx with fx = pivot row / pivot, fy = pivot column
     int pi = 0, pj = 0; float best = -1.f;
 #pragma unroll
-    for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < FT; ty++)
 #pragma unroll
-        for (int tx = 0; tx < 4; tx++) if (fabsf(k.f[ty][tx]) > best) { best = fabsf(k.f[ty][tx]); pi = ty; pj = tx; }
-    float piv = 1.f, prow[4], pcol[4];
+        for (int tx = 0; tx < FT; tx++) if (fabsf(k.f[ty][tx]) > best) { best = fabsf(k.f[ty][tx]); pi = ty; pj = tx; }
+    float piv = 1.f, prow[FT], pcol[FT];
 #pragma unroll
-    for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < FT; ty++)
 #pragma unroll
-        for (int tx = 0; tx < 4; tx++) {
+        for (int tx = 0; tx < FT; tx++) {
             if (ty == pi && tx == pj) piv = k.f[ty][tx];
             if (ty == pi) prow[tx] = k.f[ty][tx];
             if (tx == pj) pcol[ty] = k.f[ty][tx];
@@ -532,33 +545,41 @@ __device__ __forceinline__ bool blur_taps(const UpfirdnArgs& p, BlurTaps& k) {
     const float inv = (best > 0.f) ? 1.f / piv : 0.f;
     bool sep = best > 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { k.fx[i] = prow[i] * inv; k.fy[i] = pcol[i]; }
+    for (int i = 0; i < FT; i++) { k.fx[i] = prow[i] * inv; k.fy[i] = pcol[i]; }
 #pragma unroll
-    for (int ty = 0; ty < 4; ty++)
+    for (int ty = 0; ty < FT; ty++)
 #pragma unroll
-        for (int tx = 0; tx < 4; tx++) sep = sep && (fabsf(k.f[ty][tx] - k.fy[ty] * k.fx[tx]) <= 1e-6f * best);
+        for (int tx = 0; tx < FT; tx++) sep = sep && (fabsf(k.f[ty][tx] - k.fy[ty] * k.fx[tx]) <= 1e-6f * best);
     return sep;
 }
 
 template <class T, int PX>
 __global__ void __launch_bounds__(128, 4) upfirdn2d_blur(UpfirdnArgs p, int cg, int strips, int strip_rows) {
-    BlurTaps k;
-    if (blur_taps(p, k)) blur_body<T, PX, true, 8>(p, k, cg, strips, strip_rows);
-    else blur_body<T, PX, false, 8>(p, k, cg, strips, strip_rows);
+    BlurTaps<4> k;
+    if (blur_taps<4>(p, k)) blur_body<T, PX, true, 8, 4, false>(p, k, cg, strips, strip_rows);
+    else blur_body<T, PX, false, 8, 4, false>(p, k, cg, strips, strip_rows);
 }
 // 16 columns per thread (fp16 rows aligned to 32 bytes): half the per-row bookkeeping per output
 template <int PX>
 __global__ void __launch_bounds__(128, 3) upfirdn2d_blur16(UpfirdnArgs p, int cg, int strips, int strip_rows) {
-    BlurTaps k;
-    if (blur_taps(p, k)) blur_body<__half, PX, true, 16>(p, k, cg, strips, strip_rows);
-    else blur_body<__half, PX, false, 16>(p, k, cg, strips, strip_rows);
+    BlurTaps<4> k;
+    if (blur_taps<4>(p, k)) blur_body<__half, PX, true, 16, 4, false>(p, k, cg, strips, strip_rows);
+    else blur_body<__half, PX, false, 16, 4, false>(p, k, cg, strips, strip_rows);
+}
+// replicate-padded blur (the fixed binomial blur behind the pixel-shuffle upsampler, networks/utils/convnext_utils.py:250-255):
+// <= 4 taps with left pad PX4 in the FT = 4 body, 5 taps (pad 2) in the FT = 5 body; separable filters only take the fast path
+template <class T, int FT, int PX>
+__global__ void __launch_bounds__(128, 3) upfirdn2d_blur_repl(UpfirdnArgs p, int cg, int strips, int strip_rows) {
+    BlurTaps<FT> k;
+    if (blur_taps<FT>(p, k)) blur_body<T, PX, true, 8, FT, true>(p, k, cg, strips, strip_rows);
+    else blur_body<T, PX, false, 8, FT, true>(p, k, cg, strips, strip_rows);
 }
 
 template <class T>
 int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     // 16 columns per thread when the rows are fp16, 32-byte aligned and wide enough to keep a warp busy
     bool wide = false;
-    if (sizeof(T) == 2) {
+    if (sizeof(T) == 2 && !a.pad_mode) {
         auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
         wide = al32(a.x) && al32(a.y) && (a.ish % 16) == 0 && (a.isc % 16) == 0 && (a.isn % 16) == 0 &&
                (a.osh % 16) == 0 && (a.osc % 16) == 0 && (a.osn % 16) == 0 && a.out_w >= 256;   // measured: pays off only for full-warp rows
@@ -573,9 +594,16 @@ int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     const int64_t threads = planes * strips * groups;
     const int64_t blocks = ceil_div64(threads, 128);
     if (blocks > 0x7fffffffLL) { set_error("upfirdn2d: grid too large"); return VFM_ERR_INVALID; }
-    KernelTimer timer("upfirdn2d_blur", stream, 0.0,
+    KernelTimer timer(a.pad_mode ? "upfirdn2d_blur_repl" : "upfirdn2d_blur", stream, 0.0,
                       ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T) + (double)a.fw * a.fh * 4,
                       "w%dc%d", a.out_w, a.channels);
+    if (a.pad_mode) {
+        const int ft = (a.fw > 4 || a.fh > 4) ? 5 : 4;
+        if (ft == 5 && a.padx0 == 2) upfirdn2d_blur_repl<T, 5, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+        else if (ft == 4 && a.padx0 == 1) upfirdn2d_blur_repl<T, 4, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+        else { set_error("upfirdn2d: replicate padding supports 3/4 taps with left pad 1 and 5 taps with left pad 2"); return VFM_ERR_NO_KERNEL; }
+        return launch_status("upfirdn2d_blur_repl");
+    }
     if (wide) {
         switch (a.padx0) {
             case 0: upfirdn2d_blur16<0><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows); break;
@@ -626,11 +654,20 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
         // streaming blur: up = down = 1, <= 4x4 taps, 16-byte aligned rows, and the left padding inside the halo it handles
         const int es = (int)sizeof(T);
         const bool rows16 = a.vec_ok && aligned16(a.y) && (a.osh * es) % 16 == 0 && (a.osc * es) % 16 == 0 && (a.osn * es) % 16 == 0;
+        if (a.pad_mode) {
+            // replicate padding: same-size output, rows of whole 8-column groups
+            if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw <= 5 && a.fh <= 5 && rows16 && !a.add && !a.ep_enable &&
+                a.out_w == a.in_w && a.out_h == a.in_h && a.in_w % 8 == 0)
+                return launch_blur<T>(a, stream);
+            set_error("upfirdn2d: replicate padding is only implemented for same-size blurs of 16-byte aligned rows");
+            return VFM_ERR_NO_KERNEL;
+        }
         if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw <= 4 && a.fh <= 4 && rows16 &&
             a.padx0 >= 0 && a.padx0 <= 3 && (!a.add || a.add_sh >= a.out_w) &&
             (!a.ep_enable || (a.ep_gain > 0.f && (a.ep_act != 3 || (a.ep_alpha >= 0.f && a.ep_alpha <= 1.f)))))
             return launch_blur<T>(a, stream);
     }
+    if (a.pad_mode) { set_error("upfirdn2d: replicate padding needs fp16/fp32"); return VFM_ERR_NO_KERNEL; }
     if (wcontig && sym && a.out_w >= 32 && a.out_h >= 8) {
         int up = a.upx, down = a.downx;
         if (up == 1 && down == 1 && a.fw <= 4 && a.fh <= 4) return launch_tiled<T, 1, 1, 4, 4>(a, stream);
@@ -676,6 +713,7 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
     a.add_sh = p->add_stride_h; a.add_sn = p->add_stride_n;
     a.ep_enable = p->ep_enable; a.ep_act = p->ep_act; a.ep_alpha = (float)p->ep_alpha; a.ep_gain = (float)p->ep_gain; a.ep_clamp = (float)p->ep_clamp; a.ep_bias = p->ep_bias;
     VFM_CHECK_ARG(!p->ep_enable || p->ep_act == 1 || p->ep_act == 3, "upfirdn2d: fused epilogue supports linear and lrelu only");
+    a.pad_mode = p->pad_mode;
     a.xstart = a.ystart = a.tiles_x = a.tiles_y = 0;
     {
         const int64_t es = (p->dtype == VFM_F16) ? 2 : (p->dtype == VFM_F32 ? 4 : 8);

@@ -29,7 +29,7 @@ def default_ops():
     from .torch_utils.ops import bias_act, upfirdn2d
     from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act, modulated_pointwise_conv2d, fused_convnext_mlp
     return SimpleNamespace(fused_layer=fused_modconv_bias_act, bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
-                           setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d,
+                           setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d, blur2d_replicate=upfirdn2d.blur2d_replicate,
                            modulated_conv2d=modulated_conv2d, modulated_pointwise_conv2d=modulated_pointwise_conv2d,
                            fused_convnext_mlp=None if os.environ.get('VFM_NO_FUSED_CONVNEXT') else fused_convnext_mlp)
 
@@ -138,8 +138,9 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
     """GN -> dw3x3 -> 1x1 -> PixelShuffle(2) -> replicate-pad -> fixed binomial blur
     (networks/utils/convnext_utils.py:197-257).  Used by the legacy path only for ``last_upsample_conv``."""
 
-    def __init__(self, in_channels, out_channels, upscale_factor=2, blur_kernel='3x3', pre_normalize=True, use_gaussian_blur=True):
+    def __init__(self, in_channels, out_channels, upscale_factor=2, blur_kernel='3x3', pre_normalize=True, use_gaussian_blur=True, ops=None):
         super().__init__()
+        self.ops = ops
         self.out_channels, self.pre_normalize, self.use_gaussian_blur = out_channels, pre_normalize, use_gaussian_blur
         nc = in_channels if pre_normalize else out_channels
         self.norm = nn.GroupNorm(min(32, nc // 4), nc)
@@ -161,6 +162,11 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
         else:
             x = self.norm(self.shuffle(self.pointwise(self.depthwise(x))))
         if self.use_gaussian_blur:
+            fused = getattr(self.ops, 'blur2d_replicate', None) if self.ops is not None else None
+            if fused is not None and not torch.is_grad_enabled():
+                y = fused(x, self.blur_weight[0, 0], self.pad)       # replicate pad + fixed blur in one pass
+                if y is not None:
+                    return y
             x = F.conv2d(F.pad(x, self.pad, mode='replicate'), self.blur_weight.to(x.dtype) if not torch.is_autocast_enabled() else self.blur_weight,
                          groups=self.out_channels)
         return x
@@ -365,7 +371,7 @@ class SynthesisBlock(nn.Module):
         convs = []
         if use_convnext:
             self.seperate_upsample_conv = SeparableUpsampleWithFixedBlur(in_channels, out_channels, upscale_factor=2, pre_normalize=not is_first,
-                                                                         use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel)
+                                                                         use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel, ops=ops)
             self.conv0 = ConvNeXtSynthesisLayer(out_channels, w_dim=w_dim, kernel_size=kernel_size, block_index=block_index, legacy=legacy, ops=ops)
             for _ in range(num_res_blocks):
                 for _ in range(3 if block_index <= 3 and add_additional_convnext else 2):
@@ -385,7 +391,7 @@ class SynthesisBlock(nn.Module):
             self.num_torgb = 1
         if use_multiscale_output and last_out_channels is not None:
             self.last_upsample_conv = SeparableUpsampleWithFixedBlur(last_out_channels, out_channels, upscale_factor=2,
-                                                                     use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel)
+                                                                     use_gaussian_blur=use_gaussian_blur, blur_kernel=blur_kernel, ops=ops)
         self.self_attns = nn.ModuleList([SelfAttentionBlock(out_channels, dim_head=out_channels // attn_heads, heads=attn_heads, ff_mult=attn_ff_mult)
                                          for _ in range(attn_depth)]) if attn_depth > 0 else None
 

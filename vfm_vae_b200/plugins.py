@@ -111,7 +111,8 @@ class _BiasActPlugin:
 
 class _Upfirdn2dPlugin:
     @staticmethod
-    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None):
+    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, pad_mode=0):
+        """``pad_mode=1`` (extension): replicate padding; returns None where no kernel implements it."""
         _check(x.is_cuda, 'x must reside on CUDA device')
         _check(f.device == x.device, 'f must reside on the same device as x')
         _check(f.dtype == torch.float32, 'f must be float32')
@@ -142,8 +143,12 @@ class _Upfirdn2dPlugin:
             _check(add.dtype == torch.float32 and add.is_contiguous() and add.shape[-2:] == (out_h, out_w), 'add must be fp32 [..,out_h,out_w]')
             p.add, p.add_stride_h = _ptr(add), out_w
             p.add_stride_n = out_h * out_w if add.numel() == x.size(0) * out_h * out_w and add.dim() > 2 and x.size(0) > 1 else 0
+        p.pad_mode = int(pad_mode)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().vfm_upfirdn2d(C.byref(p), _stream(x)), 'upfirdn2d')
+            st = _lib.load().vfm_upfirdn2d(C.byref(p), _stream(x))
+        if pad_mode and st == _lib.VFM_ERR_NO_KERNEL:
+            return None
+        _lib.check(st, 'upfirdn2d')
         return y
 
 

@@ -147,3 +147,19 @@ def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl='cuda'
     fw, fh = _get_filter_size(f)
     p = [padx0 + (fw - downx + 1) // 2, padx1 + (fw - downx) // 2, pady0 + (fh - downy + 1) // 2, pady1 + (fh - downy) // 2]
     return upfirdn2d(x, f, down=down, padding=p, flip_filter=flip_filter, gain=gain, impl=impl)
+
+
+def blur2d_replicate(x, f, padding):
+    """Inference-only: ``F.conv2d(F.pad(x, padding, mode='replicate'), f[None, None].repeat(C, 1, 1, 1), groups=C)`` for a fixed
+    2-D kernel ``f`` (<= 5x5) whose padding keeps the size -- the blur behind the pixel-shuffle upsampler
+    (networks/utils/convnext_utils.py:250-255) -- as one pass of the streaming blur kernel with clamp-to-edge addressing.
+    ``padding`` = (left, right, top, bottom) as for ``F.pad``.  Returns None when the kernel does not apply (caller composes)."""
+    if x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or (torch.is_grad_enabled() and x.requires_grad):
+        return None
+    pl, pr, pt, pb = [int(v) for v in padding]
+    fh, fw = f.shape
+    if pl + pr != fw - 1 or pt + pb != fh - 1 or pl != pt or not x.is_contiguous():
+        return None
+    _init()
+    f32 = f.to(device=x.device, dtype=torch.float32).contiguous()
+    return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, pl, pr, pt, pb, True, 1.0, pad_mode=1)

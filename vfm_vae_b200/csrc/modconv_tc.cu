@@ -885,7 +885,27 @@ __global__ void __launch_bounds__(256) nhwc_prepass_kernel(const TIn* __restrict
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
     const float gs = gscale ? *gscale : 1.f;
-    {
+    // fast path (fp16, dense 16-byte aligned planes, full tile): 16-byte loads of 8 pixels of one channel -- a warp reads four
+    // 128-byte runs -- instead of 2-byte loads
+    const bool vec_in = (sizeof(TIn) == 2) && !SPLIT && in_pitch == W && (HW % 8) == 0 && p0 + 64 <= HW && c0 + 64 <= C &&
+                        ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    if (vec_in) {
+        const int pg = tid & 7, cl0 = tid >> 3;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int cl = cl0 + 32 * i, c = c0 + cl;
+            const float sc = scale[(size_t)n * C + c] * gs;
+            const float sh = shift ? shift[(size_t)n * C + c] * gs : 0.f;
+            union { uint4 u; __half2 h[4]; } t;
+            t.u = ldg_stream((const __half*)x + ((size_t)n * C + c) * HW + p0 + 8 * pg);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 f = __half22float2(t.h[k]);
+                s[0][8 * pg + 2 * k][cl] = __float2half_rn(fmaf(f.x, sc, sh));
+                s[0][8 * pg + 2 * k + 1][cl] = __float2half_rn(fmaf(f.y, sc, sh));
+            }
+        }
+    } else {
         const int pl = tid & 63, cg = tid >> 6;      // 4 channel groups x 64 pixels
         const int pidx = p0 + pl;
         // input rows may be pitched (the blur backward writes 32-byte aligned rows): pixel -> offset inside the plane

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 2
+#define VFM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -293,6 +293,30 @@ typedef struct {
     double       eps;
 } vfm_group_norm_affine_params;
 VFM_API int vfm_group_norm_affine(const vfm_group_norm_affine_params* p, void* stream);
+
+/* GroupNorm32 itself (networks/utils/shared.py: nn.GroupNorm evaluated in fp32, result cast back to x.dtype), forward and
+ * backward, for the training path of the residual / ConvNeXt layers and the z-convs: statistics pass + one elementwise pass each way
+ * (y = x*A + B;  dx = dy*P + x*Q + R with per-(n,c) coefficients), instead of cast -> moments -> apply -> cast.
+ * dgamma / dbeta are returned per (sample, channel); the caller sums them over the batch. */
+typedef struct {
+    const void*  x;          /* [N,C,HW] contiguous, `dtype` (f16 / f32) */
+    const float* gamma;      /* [C] or NULL */
+    const float* beta;       /* [C] or NULL */
+    void*        y;          /* forward out, `dtype` */
+    float*       mean;       /* [N,groups] forward out / backward in */
+    float*       rstd;       /* [N,groups] forward out / backward in */
+    float*       scratch;    /* 3*N*C floats */
+    const void*  dy;         /* backward in */
+    void*        dx;         /* backward out */
+    float*       dgamma_nc;  /* [N,C] backward out: sum_hw dy * xhat */
+    float*       dbeta_nc;   /* [N,C] backward out: sum_hw dy */
+    int32_t      dtype;
+    int32_t      batch, channels, groups;
+    int64_t      hw;
+    double       eps;
+} vfm_group_norm_params;
+VFM_API int vfm_group_norm_forward(const vfm_group_norm_params* p, void* stream);
+VFM_API int vfm_group_norm_backward(const vfm_group_norm_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

@@ -614,6 +614,30 @@ def test_fused_convnext_mlp(cfg, dtype):
     assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [dict(shape=(2, 128, 16, 16), groups=32), dict(shape=(3, 32, 7, 5), groups=8), dict(shape=(1, 512, 8, 8), groups=32),
+                                 dict(shape=(2, 64, 64, 64), groups=16)], ids=lambda c: 'x'.join(map(str, c['shape'])))
+def test_group_norm32_forward_backward(cfg, dtype):
+    """GroupNorm32 (fp32 statistics, output in x.dtype) forward and gradients against torch.nn.functional.group_norm in fp64."""
+    from vfm_vae_b200.torch_utils.ops.group_norm import group_norm32
+    g = torch.Generator().manual_seed(50)
+    Cc = cfg['shape'][1]
+    xq = (torch.randn(cfg['shape'], generator=g) * 2 + torch.randn(1, Cc, 1, 1, generator=g) * 3).to(dtype).double()
+    w, b = torch.rand(Cc, generator=g).double() + 0.5, torch.randn(Cc, generator=g).double()
+    dyq = torch.randn(cfg['shape'], generator=g).to(dtype).double()
+    ref_in = [t.clone().requires_grad_(True) for t in (xq, w, b)]
+    yr = torch.nn.functional.group_norm(ref_in[0], cfg['groups'], ref_in[1], ref_in[2], eps=1e-5)
+    gr = torch.autograd.grad(yr, ref_in, dyq)
+    x = xq.to(DEV, dtype).requires_grad_(True)
+    wd, bd = w.float().to(DEV).requires_grad_(True), b.float().to(DEV).requires_grad_(True)
+    y = group_norm32(x, cfg['groups'], wd, bd, 1e-5)
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert y.dtype == dtype and rel_err(y, yr) <= tol
+    gg = torch.autograd.grad(y, [x, wd, bd], dyq.to(DEV, dtype))
+    for name, a, r in zip(['dx', 'dweight', 'dbias'], gg, gr):
+        assert rel_err(a, r) <= 2 * tol, name
+
+
 def test_fused_layer_declines_what_it_cannot_do():
     from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
     x = torch.randn(2, 40, 9, 13, device=DEV)            # ragged channels -> generic SIMT path, which does not fuse

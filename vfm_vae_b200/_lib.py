@@ -79,6 +79,11 @@ class GroupNormAffineParams(C.Structure):
                 ('batch', _i32), ('channels', _i32), ('groups', _i32), ('hw', _i64), ('eps', _f64)]
 
 
+class GroupNormParams(C.Structure):
+    _fields_ = [('x', _vp), ('gamma', _vp), ('beta', _vp), ('y', _vp), ('mean', _vp), ('rstd', _vp), ('scratch', _vp), ('dy', _vp), ('dx', _vp),
+                ('dgamma_nc', _vp), ('dbeta_nc', _vp), ('dtype', _i32), ('batch', _i32), ('channels', _i32), ('groups', _i32), ('hw', _i64), ('eps', _f64)]
+
+
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
@@ -105,6 +110,8 @@ SYMBOLS = {
     'vfm_modconv_backward': (C.c_int, [C.POINTER(ModconvBwdParams), _vp]),
     'vfm_modconv_uses_tensor_cores': (C.c_int, [C.POINTER(ModconvDesc)]),
     'vfm_group_norm_affine': (C.c_int, [C.POINTER(GroupNormAffineParams), _vp]),
+    'vfm_group_norm_forward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
+    'vfm_group_norm_backward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
 }
 
 _lib = None
@@ -125,8 +132,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 2:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 2)')
+    if lib.vfm_abi_version() != 3:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 3)')
     _lib = lib
     return lib
 

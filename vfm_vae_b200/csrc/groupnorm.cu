@@ -14,7 +14,8 @@ namespace {
 
 template <class T>
 __global__ void __launch_bounds__(512) gn_affine_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ scale, float* __restrict__ shift, int C, int64_t HW, int groups, float eps) {
+                                                        float* __restrict__ scale, float* __restrict__ shift, int C, int64_t HW, int groups, float eps,
+                                                        float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     constexpr int V = 16 / (int)sizeof(T);
     const int n = blockIdx.x / groups, g = blockIdx.x - n * groups;
     const int cpg = C / groups;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(512) gn_affine_kernel(const T* __restrict__ x,
         if (var < 0.0) var = 0.0;
         s_mean = (float)((double)K + m);
         s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+        if (mean_out) { mean_out[blockIdx.x] = s_mean; rstd_out[blockIdx.x] = s_rstd; }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
@@ -64,6 +66,135 @@ __global__ void __launch_bounds__(512) gn_affine_kernel(const T* __restrict__ x,
         scale[(int64_t)n * C + ch] = a;
         shift[(int64_t)n * C + ch] = (beta ? beta[ch] : 0.f) - s_mean * a;
     }
+}
+
+// out[row, :] = a[row, :] * P[row] (+ b[row, :] * Q[row]) + R[row]   -- one (n, c) plane per blockIdx.y, 16-byte vectors, 4 in flight.
+// Forward apply: NIN = 1 (x, scale, shift).  Backward: NIN = 2 (dy, x) with the coefficients of gn_bwd_reduce_kernel.
+template <class T, int NIN>
+__global__ void __launch_bounds__(256) rows_affine_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ P, const float* __restrict__ Q,
+                                                          const float* __restrict__ R, T* __restrict__ out, int64_t HW, int vec_per_block) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t row = blockIdx.y;
+    const float pp = P[row], qq = (NIN == 2) ? Q[row] : 0.f, rr = R[row];
+    const T* ap = a + row * HW;
+    const T* bp = (NIN == 2) ? b + row * HW : nullptr;
+    T* op = out + row * HW;
+    if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | (NIN == 2 ? reinterpret_cast<uintptr_t>(b) : 0)) & 15u) == 0) {
+        const int64_t nvec = HW / V;
+        const int64_t v_begin = (int64_t)blockIdx.x * vec_per_block, v_end = (v_begin + vec_per_block < nvec) ? v_begin + vec_per_block : nvec;
+        for (int64_t v0 = v_begin + threadIdx.x; v0 < v_end; v0 += (int64_t)blockDim.x * 4) {
+            uint4 ua[4], ub[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t v = v0 + (int64_t)u * blockDim.x;
+                if (v < v_end) { ua[u] = ldg_stream((const uint4*)ap + v); if (NIN == 2) ub[u] = ldg_stream((const uint4*)bp + v); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t v = v0 + (int64_t)u * blockDim.x;
+                if (v >= v_end) continue;
+                const T* ea = (const T*)&ua[u];
+                const T* eb = (const T*)&ub[u];
+                struct alignas(16) { T e[V]; } o;
+#pragma unroll
+                for (int k = 0; k < V; k++) {
+                    float r = fmaf(to_acc(ea[k]), pp, rr);
+                    if (NIN == 2) r = fmaf(to_acc(eb[k]), qq, r);
+                    o.e[k] = from_acc<T, float>(r);
+                }
+                stg_stream((uint4*)op + v, *(const uint4*)&o);
+            }
+        }
+    } else {
+        const int64_t e_begin = (int64_t)blockIdx.x * vec_per_block * V;
+        const int64_t e_end = (e_begin + (int64_t)vec_per_block * V < HW) ? e_begin + (int64_t)vec_per_block * V : HW;
+        for (int64_t i = e_begin + threadIdx.x; i < e_end; i += blockDim.x) {
+            float r = fmaf(to_acc(ap[i]), pp, rr);
+            if (NIN == 2) r = fmaf(to_acc(bp[i]), qq, r);
+            op[i] = from_acc<T, float>(r);
+        }
+    }
+}
+
+// Backward reductions of GroupNorm, one CTA per (sample, group): per channel c1 = sum dy, c2 = sum dy * xhat (-> dbeta / dgamma
+// after a sum over the batch), group sums s1 = sum_c gamma c1, s2 = sum_c gamma c2, and the coefficients of the elementwise pass
+//   dx = dy * P + x * Q + R,   P = rstd * gamma,  Q = -rstd^2 * s2 / m,  R = rstd * (rstd * mean * s2 - s1) / m      (m = group size)
+template <class T>
+__global__ void __launch_bounds__(512) gn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ c1_out,
+                                                            float* __restrict__ c2_out, float* __restrict__ P, float* __restrict__ Q, float* __restrict__ R,
+                                                            int C, int64_t HW, int groups) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int n = blockIdx.x / groups, g = blockIdx.x - n * groups;
+    const int cpg = C / groups;
+    const float mu = mean[blockIdx.x], rs = rstd[blockIdx.x];
+    __shared__ float red[2][32];
+    __shared__ float s_c1[64], s_c2[64];           // cpg <= 64 (checked on the host)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < cpg; c++) {
+        const int ch = g * cpg + c;
+        const T* dyp = dy + ((int64_t)n * C + ch) * HW;
+        const T* xp = x + ((int64_t)n * C + ch) * HW;
+        float a1 = 0.f, a2 = 0.f;
+        if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
+            const int64_t nvec = HW / V;
+            for (int64_t v0 = threadIdx.x; v0 < nvec; v0 += (int64_t)blockDim.x * 2) {
+                uint4 ud[2], ux[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int64_t v = v0 + (int64_t)u * blockDim.x;
+                    if (v < nvec) { ud[u] = ldg_stream((const uint4*)dyp + v); ux[u] = ldg_stream((const uint4*)xp + v); }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (v0 + (int64_t)u * blockDim.x >= nvec) continue;
+                    const T* ed = (const T*)&ud[u];
+                    const T* ex = (const T*)&ux[u];
+#pragma unroll
+                    for (int k = 0; k < V; k++) { const float d = to_acc(ed[k]); a1 += d; a2 = fmaf(d, to_acc(ex[k]) - mu, a2); }
+                }
+            }
+        } else {
+            for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) { const float d = to_acc(dyp[i]); a1 += d; a2 = fmaf(d, to_acc(xp[i]) - mu, a2); }
+        }
+        a1 = warp_sum(a1); a2 = warp_sum(a2);
+        __syncthreads();
+        if (lane == 0) { red[0][warp] = a1; red[1][warp] = a2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { t1 += red[0][w]; t2 += red[1][w]; }
+            s_c1[c] = t1; s_c2[c] = t2 * rs;          // sum dy,  sum dy * xhat
+        }
+    }
+    __syncthreads();
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < cpg; c++) { const float gm = gamma ? gamma[g * cpg + c] : 1.f; s1 = fmaf(gm, s_c1[c], s1); s2 = fmaf(gm, s_c2[c], s2); }
+    const float inv_m = 1.f / ((float)cpg * (float)HW);
+    for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
+        const int ch = g * cpg + c;
+        const int64_t idx = (int64_t)n * C + ch;
+        c1_out[idx] = s_c1[c];
+        c2_out[idx] = s_c2[c];
+        P[idx] = rs * (gamma ? gamma[ch] : 1.f);
+        Q[idx] = -rs * rs * s2 * inv_m;
+        R[idx] = rs * (rs * mu * s2 - s1) * inv_m;
+    }
+}
+
+template <class T, int NIN>
+int launch_rows_affine(const void* a, const void* b, const float* P, const float* Q, const float* R, void* out, int64_t rows, int64_t HW, const char* name,
+                       cudaStream_t stream) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t nvec = (HW + V - 1) / V;
+    int64_t vpb = nvec;
+    while (vpb > 256 * 8 && rows * ((nvec + vpb - 1) / vpb) < (int64_t)kNumSMs * 16) vpb = (vpb + 1) / 2;
+    if (vpb > 256 * 16) vpb = 256 * 16;
+    if (rows > 0x7fffffffLL) { set_error("group_norm: too many rows"); return VFM_ERR_INVALID; }
+    dim3 grid((unsigned)((nvec + vpb - 1) / vpb), (unsigned)rows);
+    KernelTimer timer(name, stream, 0.0, (double)rows * HW * sizeof(T) * (NIN + 1));
+    rows_affine_kernel<T, NIN><<<grid, 256, 0, stream>>>((const T*)a, (const T*)b, P, Q, R, (T*)out, HW, (int)vpb);
+    return launch_status("rows_affine_kernel");
 }
 
 }  // namespace
@@ -83,8 +214,59 @@ extern "C" int vfm_group_norm_affine(const vfm_group_norm_affine_params* p, void
     KernelTimer timer("group_norm_affine", stream, 0.0, (double)p->batch * p->channels * (double)p->hw * es + 8.0 * p->batch * p->channels, "c%dhw%lld",
                       p->channels, (long long)p->hw);
     if (p->dtype == VFM_F16)
-        gn_affine_kernel<__half><<<(unsigned)blocks, 512, 0, stream>>>((const __half*)p->x, p->gamma, p->beta, p->scale, p->shift, p->channels, p->hw, p->groups, (float)p->eps);
+        gn_affine_kernel<__half><<<(unsigned)blocks, 512, 0, stream>>>((const __half*)p->x, p->gamma, p->beta, p->scale, p->shift, p->channels, p->hw, p->groups, (float)p->eps, nullptr, nullptr);
     else
-        gn_affine_kernel<float><<<(unsigned)blocks, 512, 0, stream>>>((const float*)p->x, p->gamma, p->beta, p->scale, p->shift, p->channels, p->hw, p->groups, (float)p->eps);
+        gn_affine_kernel<float><<<(unsigned)blocks, 512, 0, stream>>>((const float*)p->x, p->gamma, p->beta, p->scale, p->shift, p->channels, p->hw, p->groups, (float)p->eps, nullptr, nullptr);
     return launch_status("gn_affine_kernel");
+}
+
+static int gn_check(const vfm_group_norm_params* p, const char* what) {
+    using namespace vfm;
+    VFM_CHECK_ARG(p != nullptr, "%s: params is NULL", what);
+    VFM_CHECK_ARG(p->x && p->mean && p->rstd && p->scratch, "%s: x, mean, rstd and scratch must be non-NULL", what);
+    VFM_CHECK_ARG(p->batch >= 1 && p->channels >= 1 && p->hw >= 1, "%s: x is empty", what);
+    VFM_CHECK_ARG(p->groups >= 1 && p->channels % p->groups == 0 && p->channels / p->groups <= 64, "%s: channels (%d) must be divisible by groups (%d), <= 64 per group", what, p->channels, p->groups);
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "%s: unsupported dtype %d", what, p->dtype);
+    VFM_CHECK_ARG((int64_t)p->batch * p->groups <= 0x7fffffffLL, "%s: grid too large", what);
+    return VFM_OK;
+}
+
+extern "C" int vfm_group_norm_forward(const vfm_group_norm_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = gn_check(p, "group_norm_forward"); if (st) return st;
+    VFM_CHECK_ARG(p->y != nullptr, "group_norm_forward: y must be non-NULL");
+    const size_t nc = (size_t)p->batch * p->channels;
+    float* scale = p->scratch; float* shift = p->scratch + nc;
+    const unsigned blocks = (unsigned)((int64_t)p->batch * p->groups);
+    {
+        KernelTimer timer("group_norm_affine", stream, 0.0, (double)nc * (double)p->hw * (p->dtype == VFM_F16 ? 2.0 : 4.0));
+        if (p->dtype == VFM_F16)
+            gn_affine_kernel<__half><<<blocks, 512, 0, stream>>>((const __half*)p->x, p->gamma, p->beta, scale, shift, p->channels, p->hw, p->groups, (float)p->eps, p->mean, p->rstd);
+        else
+            gn_affine_kernel<float><<<blocks, 512, 0, stream>>>((const float*)p->x, p->gamma, p->beta, scale, shift, p->channels, p->hw, p->groups, (float)p->eps, p->mean, p->rstd);
+    }
+    st = launch_status("gn_affine_kernel"); if (st) return st;
+    if (p->dtype == VFM_F16) return launch_rows_affine<__half, 1>(p->x, nullptr, scale, nullptr, shift, p->y, (int64_t)nc, p->hw, "group_norm_apply", stream);
+    return launch_rows_affine<float, 1>(p->x, nullptr, scale, nullptr, shift, p->y, (int64_t)nc, p->hw, "group_norm_apply", stream);
+}
+
+extern "C" int vfm_group_norm_backward(const vfm_group_norm_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = gn_check(p, "group_norm_backward"); if (st) return st;
+    VFM_CHECK_ARG(p->dy && p->dx && p->dgamma_nc && p->dbeta_nc, "group_norm_backward: dy, dx, dgamma_nc and dbeta_nc must be non-NULL");
+    const size_t nc = (size_t)p->batch * p->channels;
+    float* P = p->scratch; float* Q = p->scratch + nc; float* R = p->scratch + 2 * nc;
+    const unsigned blocks = (unsigned)((int64_t)p->batch * p->groups);
+    {
+        KernelTimer timer("group_norm_bwd_reduce", stream, 0.0, 2.0 * (double)nc * (double)p->hw * (p->dtype == VFM_F16 ? 2.0 : 4.0));
+        if (p->dtype == VFM_F16)
+            gn_bwd_reduce_kernel<__half><<<blocks, 512, 0, stream>>>((const __half*)p->dy, (const __half*)p->x, p->gamma, p->mean, p->rstd, p->dbeta_nc, p->dgamma_nc, P, Q, R, p->channels, p->hw, p->groups);
+        else
+            gn_bwd_reduce_kernel<float><<<blocks, 512, 0, stream>>>((const float*)p->dy, (const float*)p->x, p->gamma, p->mean, p->rstd, p->dbeta_nc, p->dgamma_nc, P, Q, R, p->channels, p->hw, p->groups);
+    }
+    st = launch_status("gn_bwd_reduce_kernel"); if (st) return st;
+    if (p->dtype == VFM_F16) return launch_rows_affine<__half, 2>(p->dy, p->x, P, Q, R, p->dx, (int64_t)nc, p->hw, "group_norm_bwd_apply", stream);
+    return launch_rows_affine<float, 2>(p->dy, p->x, P, Q, R, p->dx, (int64_t)nc, p->hw, "group_norm_bwd_apply", stream);
 }

@@ -71,7 +71,14 @@ class StyleSplit(nn.Module):
 
 
 class GroupNorm32(nn.GroupNorm):
+    """networks/utils/shared.py GroupNorm32: fp32 statistics, result in x.dtype.  CUDA tensors go through the library's
+    two-pass kernels (forward and backward); everything else through the stock module, exactly as the reference."""
+
     def forward(self, x):
+        if x.is_cuda:
+            from .torch_utils.ops import group_norm as _gn          # CUDA only: never reached by the CPU (oracle) runs
+            if _gn.supported(x, self.num_groups):
+                return _gn.group_norm32(x, self.num_groups, self.weight, self.bias, self.eps)
         return super().forward(x.float()).type(x.dtype)
 
 

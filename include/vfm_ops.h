@@ -318,6 +318,23 @@ typedef struct {
 VFM_API int vfm_group_norm_forward(const vfm_group_norm_params* p, void* stream);
 VFM_API int vfm_group_norm_backward(const vfm_group_norm_params* p, void* stream);
 
+/* Row-wise helpers for the layer-scaled residual of the residual SynthesisLayers in training,  y = (gamma*y + x)*sqrt2
+ * (networks/generator.py:272-274): a tensor is `rows` = N*C planes of `hw` contiguous elements of `dtype`.
+ *   vfm_rows_affine: out[r,:] = a[r,:]*P[r] (+ b[r,:]*Q[r]) + R[r]     (b, Q optional, together; out has the dtype of a)
+ *   vfm_rows_dot   : ((float*)out)[r] = sum_i a[r,i]*b[r,i]             (the layer-scale gradient) */
+typedef struct {
+    const void*  a;
+    const void*  b;
+    const float* P;
+    const float* Q;
+    const float* R;
+    void*        out;
+    int32_t      dtype;
+    int64_t      rows, hw;
+} vfm_rows_params;
+VFM_API int vfm_rows_affine(const vfm_rows_params* p, void* stream);
+VFM_API int vfm_rows_dot(const vfm_rows_params* p, void* stream);
+
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);
 VFM_API int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream);

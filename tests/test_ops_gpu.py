@@ -638,6 +638,27 @@ def test_group_norm32_forward_backward(cfg, dtype):
         assert rel_err(a, r) <= 2 * tol, name
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('shape', [(2, 128, 16, 16), (3, 6, 7, 5), (1, 32, 64, 64)], ids=lambda s: 'x'.join(map(str, s)))
+def test_layer_scale_residual(shape, dtype):
+    """(gamma*y + x)*sqrt2 of the residual layers (networks/generator.py:272-274), forward and gradients."""
+    from vfm_vae_b200.torch_utils.ops.layer_scale import layer_scale_residual
+    g = torch.Generator().manual_seed(60)
+    yq, xq = (torch.randn(shape, generator=g).to(dtype).double() for _ in range(2))
+    gam = (torch.rand(1, shape[1], 1, 1, generator=g) + 0.5).double()
+    dq = torch.randn(shape, generator=g).to(dtype).double()
+    ref_in = [t.clone().requires_grad_(True) for t in (yq, xq, gam)]
+    outr = (ref_in[2] * ref_in[0] + ref_in[1]) * math.sqrt(2)
+    gr = torch.autograd.grad(outr, ref_in, dq)
+    dev_in = [yq.to(DEV, dtype).requires_grad_(True), xq.to(DEV, dtype).requires_grad_(True), gam.float().to(DEV).requires_grad_(True)]
+    out = layer_scale_residual(*dev_in, math.sqrt(2))
+    tol = TOL[str(dtype).split('.')[-1]]
+    assert out.dtype == dtype and rel_err(out, outr) <= tol
+    gg = torch.autograd.grad(out, dev_in, dq.to(DEV, dtype))
+    for name, a, r in zip(['dy', 'dx', 'dgamma'], gg, gr):
+        assert rel_err(a, r) <= 2 * tol, name
+
+
 def test_fused_layer_declines_what_it_cannot_do():
     from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
     x = torch.randn(2, 40, 9, 13, device=DEV)            # ragged channels -> generic SIMT path, which does not fuse

@@ -84,6 +84,10 @@ class GroupNormParams(C.Structure):
                 ('dgamma_nc', _vp), ('dbeta_nc', _vp), ('dtype', _i32), ('batch', _i32), ('channels', _i32), ('groups', _i32), ('hw', _i64), ('eps', _f64)]
 
 
+class RowsParams(C.Structure):
+    _fields_ = [('a', _vp), ('b', _vp), ('P', _vp), ('Q', _vp), ('R', _vp), ('out', _vp), ('dtype', _i32), ('rows', _i64), ('hw', _i64)]
+
+
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
@@ -112,6 +116,8 @@ SYMBOLS = {
     'vfm_group_norm_affine': (C.c_int, [C.POINTER(GroupNormAffineParams), _vp]),
     'vfm_group_norm_forward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
     'vfm_group_norm_backward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
+    'vfm_rows_affine': (C.c_int, [C.POINTER(RowsParams), _vp]),
+    'vfm_rows_dot': (C.c_int, [C.POINTER(RowsParams), _vp]),
 }
 
 _lib = None

@@ -270,3 +270,70 @@ extern "C" int vfm_group_norm_backward(const vfm_group_norm_params* p, void* str
     if (p->dtype == VFM_F16) return launch_rows_affine<__half, 2>(p->dy, p->x, P, Q, R, p->dx, (int64_t)nc, p->hw, "group_norm_bwd_apply", stream);
     return launch_rows_affine<float, 2>(p->dy, p->x, P, Q, R, p->dx, (int64_t)nc, p->hw, "group_norm_bwd_apply", stream);
 }
+
+
+// ---- generic row-wise helpers behind the fused layer-scaled residual of the training path (networks/generator.py:272-274) ----
+//   vfm_rows_affine: out[r, :] = a[r, :] * P[r] (+ b[r, :] * Q[r]) + R[r]       rows = N*C planes of hw elements
+//   vfm_rows_dot   : out[r]    = sum_i a[r, i] * b[r, i]
+namespace vfm {
+namespace {
+template <class T>
+__global__ void __launch_bounds__(256) rows_dot_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, int64_t HW) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t row = blockIdx.x;
+    const T* ap = a + row * HW;
+    const T* bp = b + row * HW;
+    float acc = 0.f;
+    if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0) {
+        const int64_t nvec = HW / V;
+        for (int64_t v0 = threadIdx.x; v0 < nvec; v0 += (int64_t)blockDim.x * 4) {
+            uint4 ua[4], ub[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t v = v0 + (int64_t)u * blockDim.x;
+                if (v < nvec) { ua[u] = ldg_stream((const uint4*)ap + v); ub[u] = ldg_stream((const uint4*)bp + v); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (v0 + (int64_t)u * blockDim.x >= nvec) continue;
+                const T* ea = (const T*)&ua[u];
+                const T* eb = (const T*)&ub[u];
+#pragma unroll
+                for (int k = 0; k < V; k++) acc = fmaf(to_acc(ea[k]), to_acc(eb[k]), acc);
+            }
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) acc = fmaf(to_acc(ap[i]), to_acc(bp[i]), acc);
+    }
+    __shared__ float red[32];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[row] = acc;
+}
+}  // namespace
+}  // namespace vfm
+
+extern "C" int vfm_rows_affine(const vfm_rows_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p && p->a && p->out && p->P && p->R, "rows_affine: a, out, P and R must be non-NULL");
+    VFM_CHECK_ARG((p->b == nullptr) == (p->Q == nullptr), "rows_affine: b and Q come together");
+    VFM_CHECK_ARG(p->rows >= 1 && p->hw >= 1, "rows_affine: empty tensor");
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "rows_affine: unsupported dtype %d", p->dtype);
+    if (p->dtype == VFM_F16)
+        return p->b ? launch_rows_affine<__half, 2>(p->a, p->b, p->P, p->Q, p->R, p->out, p->rows, p->hw, "rows_affine", stream)
+                    : launch_rows_affine<__half, 1>(p->a, nullptr, p->P, nullptr, p->R, p->out, p->rows, p->hw, "rows_affine", stream);
+    return p->b ? launch_rows_affine<float, 2>(p->a, p->b, p->P, p->Q, p->R, p->out, p->rows, p->hw, "rows_affine", stream)
+                : launch_rows_affine<float, 1>(p->a, nullptr, p->P, nullptr, p->R, p->out, p->rows, p->hw, "rows_affine", stream);
+}
+
+extern "C" int vfm_rows_dot(const vfm_rows_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p && p->a && p->b && p->out, "rows_dot: a, b and out must be non-NULL");
+    VFM_CHECK_ARG(p->rows >= 1 && p->rows <= 0x7fffffffLL && p->hw >= 1, "rows_dot: bad shape");
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "rows_dot: unsupported dtype %d", p->dtype);
+    KernelTimer timer("rows_dot", stream, 0.0, 2.0 * (double)p->rows * (double)p->hw * (p->dtype == VFM_F16 ? 2.0 : 4.0));
+    if (p->dtype == VFM_F16) rows_dot_kernel<__half><<<(unsigned)p->rows, 256, 0, stream>>>((const __half*)p->a, (const __half*)p->b, (float*)p->out, p->hw);
+    else rows_dot_kernel<float><<<(unsigned)p->rows, 256, 0, stream>>>((const float*)p->a, (const float*)p->b, (float*)p->out, p->hw);
+    return launch_status("rows_dot_kernel");
+}

@@ -245,6 +245,10 @@ class SynthesisLayer(nn.Module):
         y = y.to(dtype)
         y = self.ops.bias_act(y, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
         if self.residual:
+            if y.is_cuda:
+                from .torch_utils.ops import layer_scale as _ls         # CUDA only: never reached by the CPU (oracle) runs
+                if _ls.supported(y, x, self.gamma):
+                    return _ls.layer_scale_residual(y, x, self.gamma, float(np.sqrt(2)))
             y = (self.gamma * y).to(dtype).add_(x).mul(np.sqrt(2))
         return y
 

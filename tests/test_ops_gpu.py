@@ -659,6 +659,40 @@ def test_layer_scale_residual(shape, dtype):
         assert rel_err(a, r) <= 2 * tol, name
 
 
+@pytest.mark.parametrize('bias', [True, False])
+def test_glue_conv1x1_strict_fp32(bias):
+    """decoder.Conv1x1: with TF32 off (the reference's training setting) the glue layers' 1x1 convs run on the tcgen05 split-fp16
+    kernels, forward and gradients, at fp32 accuracy; with TF32 allowed they stay on cuDNN."""
+    from vfm_vae_b200.decoder import Conv1x1
+    from vfm_vae_b200 import _lib
+    torch.manual_seed(5)
+    conv = Conv1x1(256, 512, 1, bias=bias).to(DEV)
+    x = torch.randn(3, 256, 16, 16, device=DEV, requires_grad=True)
+    dy = torch.randn(3, 512, 16, 16, device=DEV)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        params = [x, conv.weight] + ([conv.bias] if bias else [])
+        xr = x.detach().double().requires_grad_(True)
+        wr = conv.weight.detach().double().requires_grad_(True)
+        br = conv.bias.detach().double().requires_grad_(True) if bias else None
+        yr = torch.nn.functional.conv2d(xr, wr, br)
+        gr = torch.autograd.grad(yr, [xr, wr] + ([br] if bias else []), dy.double())
+        n0 = _lib.launch_count()
+        y = conv(x)
+        assert _lib.launch_count() > n0, 'strict-fp32 mode must use the library kernels'
+        assert rel_err(y, yr) <= 1e-5
+        gg = torch.autograd.grad(y, params, dy)
+        for name, a, r in zip(['dx', 'dw', 'db'], gg, gr):
+            assert rel_err(a, r) <= 2e-5, name
+        torch.backends.cudnn.allow_tf32 = True
+        n0 = _lib.launch_count()
+        conv(x)
+        assert _lib.launch_count() == n0, 'with TF32 allowed the stock cuDNN path is kept'
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def test_fused_layer_declines_what_it_cannot_do():
     from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_modconv_bias_act
     x = torch.randn(2, 40, 9, 13, device=DEV)            # ragged channels -> generic SIMT path, which does not fuse

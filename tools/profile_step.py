@@ -14,6 +14,7 @@ ap.add_argument('--mode', default='decode')
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--rows', type=int, default=40)
 args = ap.parse_args()
+torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = 'cuda'

@@ -36,6 +36,27 @@ def default_ops():
 
 # ------------------------------------------------------------------------------------------- small shared layers
 
+class Conv1x1(nn.Conv2d):
+    """A plain 1x1 conv of the glue layers (attention projections / feed-forward, z-convs, the upsampler's pointwise conv) --
+    same parameters and state-dict names as ``nn.Conv2d(cin, cout, 1)``.
+
+    The reference trains with TF32 off (training/training_loop.py:504-505), which leaves cuDNN with its fp32 SIMT kernels for
+    these layers: forward, data and weight gradients together were ~30% of the training step.  In exactly that strict-fp32
+    setting (fp32 CUDA tensors, no autocast, ``torch.backends.cudnn.allow_tf32 == False``) the conv runs on the library's
+    modulated-conv kernels with unit styles and no demodulation instead: tcgen05 with the 2-term fp16 split (error ~1e-6, i.e.
+    fp32-grade like the kernels it replaces), forward and backward.  With TF32 allowed (PyTorch's default, the decode tools)
+    cuDNN's own tensor-core kernels are faster and the stock path is kept."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled() and not torch.backends.cudnn.allow_tf32
+                and self.in_channels % 128 == 0 and self.out_channels % 128 == 0 and x.is_contiguous()):
+            from .torch_utils.ops.modulated_conv2d import modulated_conv2d      # CUDA only: never reached by the CPU (oracle) runs
+            ones = torch.ones([x.shape[0], self.in_channels], dtype=torch.float32, device=x.device)
+            y = modulated_conv2d(x, self.weight, ones, demodulate=False)
+            return y if self.bias is None else y + self.bias.reshape(1, -1, 1, 1)
+        return super().forward(x)
+
+
 class FullyConnectedLayer(nn.Module):
     """Equalised-lr linear layer (networks/utils/shared.py:24-106)."""
 
@@ -100,11 +121,11 @@ class SelfAttention(nn.Module):
         self.heads = heads
         inner = dim_head * heads
         self.norm = ChannelRMSNorm(dim)
-        self.to_q = nn.Conv2d(dim, inner, 1, bias=False)
-        self.to_k = nn.Conv2d(dim, inner, 1, bias=False)
-        self.to_v = nn.Conv2d(dim, inner, 1, bias=False)
+        self.to_q = Conv1x1(dim, inner, 1, bias=False)
+        self.to_k = Conv1x1(dim, inner, 1, bias=False)
+        self.to_v = Conv1x1(dim, inner, 1, bias=False)
         self.null_kv = nn.Parameter(torch.randn(2, heads, dim_head) * 0.02)
-        self.to_out = nn.Conv2d(inner, dim, 1, bias=False)
+        self.to_out = Conv1x1(inner, dim, 1, bias=False)
         nn.init.zeros_(self.to_out.weight)
 
     def forward(self, fmap):
@@ -131,9 +152,9 @@ class SelfAttentionBlock(nn.Module):
         super().__init__()
         self.attn = SelfAttention(dim=dim, dim_head=dim_head, heads=heads)
         hidden = int(dim * ff_mult)
-        proj2 = nn.Conv2d(hidden, dim, 1)
+        proj2 = Conv1x1(hidden, dim, 1)
         nn.init.zeros_(proj2.weight)
-        self.ff = nn.Sequential(ChannelRMSNorm(dim), nn.Conv2d(dim, hidden, 1), nn.GELU(), proj2)
+        self.ff = nn.Sequential(ChannelRMSNorm(dim), Conv1x1(dim, hidden, 1), nn.GELU(), proj2)
 
     def forward(self, x):
         x = self.attn(x) + x
@@ -154,7 +175,7 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
         nc = in_channels if pre_normalize else out_channels
         self.norm = nn.GroupNorm(min(32, nc // 4), nc)
         self.depthwise = nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False)
-        self.pointwise = nn.Conv2d(in_channels, out_channels * upscale_factor ** 2, 1, bias=False)
+        self.pointwise = Conv1x1(in_channels, out_channels * upscale_factor ** 2, 1, bias=False)
         self.shuffle = nn.PixelShuffle(upscale_factor)
         if use_gaussian_blur:
             k = torch.tensor(_BLUR_TAPS[blur_kernel] if isinstance(blur_kernel, str) else blur_kernel, dtype=torch.float32)
@@ -306,7 +327,7 @@ class ConvNeXtSynthesisLayer(nn.Module):
             self.register_buffer('noise_const', torch.randn([resolution, resolution]))
             self.noise_strength = nn.Parameter(torch.zeros([]))
         self.pwconv1 = ModulatedPointwiseConv2DLayer(channels, 4 * channels, demodulate, ops=ops)
-        self.pwconv2 = nn.Conv2d(4 * channels, channels, kernel_size=1)
+        self.pwconv2 = Conv1x1(4 * channels, channels, kernel_size=1)
         nn.init.trunc_normal_(self.pwconv2.weight, std=0.02)
         nn.init.zeros_(self.pwconv2.bias)
         self.norm = GroupNorm32(min(32, channels // 4), channels)
@@ -512,11 +533,11 @@ class SynthesisNetwork(nn.Module):
         return {'lrelu': lambda: nn.LeakyReLU(negative_slope=0.2), 'silu': nn.SiLU, 'gelu': nn.GELU}[name]()
 
     def _conv3x3(self, cin, cout, activation):
-        return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), nn.Conv2d(cin, cout, 1, bias=False),
+        return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), Conv1x1(cin, cout, 1, bias=False),
                              GroupNorm32(min(32, cout), cout), self._act(activation))
 
     def _conv1x1(self, cin, cout):
-        return nn.Sequential(nn.Conv2d(cin, cout, 1, bias=False), GroupNorm32(min(32, cout), cout))
+        return nn.Sequential(Conv1x1(cin, cout, 1, bias=False), GroupNorm32(min(32, cout), cout))
 
     def forward(self, z, ws, text=None, text_mask=None, **block_kwargs):
         ws = ws.to(torch.float32)

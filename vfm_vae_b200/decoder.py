@@ -49,10 +49,10 @@ class Conv1x1(nn.Conv2d):
 
     def forward(self, x):
         if (x.is_cuda and x.dtype == torch.float32 and not torch.is_autocast_enabled() and not torch.backends.cudnn.allow_tf32
-                and self.in_channels % 128 == 0 and self.out_channels % 128 == 0 and x.is_contiguous()):
+                and self.in_channels % 128 == 0 and self.out_channels % 128 == 0):
             from .torch_utils.ops.modulated_conv2d import modulated_conv2d      # CUDA only: never reached by the CPU (oracle) runs
             ones = torch.ones([x.shape[0], self.in_channels], dtype=torch.float32, device=x.device)
-            y = modulated_conv2d(x, self.weight, ones, demodulate=False)
+            y = modulated_conv2d(x.contiguous(), self.weight, ones, demodulate=False)
             return y if self.bias is None else y + self.bias.reshape(1, -1, 1, 1)
         return super().forward(x)
 

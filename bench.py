@@ -340,12 +340,12 @@ def run_ours(args):
                 entry['gbs'] = round(s['bytes'] / (s['total_ms'] * 1e-3) / 1e9, 1)
             kernels.append(entry)
         # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
-        # (profiles/r01b_traffic.json, written by tools/ncu_summarize.py); None when no capture covers the kernel
+        # (profiles/r01c_traffic.json, written by tools/ncu_summarize.py); None when no capture covers the kernel
         def ncu_traffic(name):
             key = {'modconv_tc_fwd': 'conv_tc_kernel<__half, 0, 0', 'modconv_tc_fwd_split': 'conv_tc_kernel<float, 0, 1',
                    'modconv_nhwc_prepass': 'nhwc_prepass_kernel<__half', 'upfirdn2d_blur': 'upfirdn2d_blur<__half'}.get(name.split(':')[0])
             try:
-                tr = json.load(open(os.path.join(REPO, 'profiles', 'r01b_traffic.json')))
+                tr = json.load(open(os.path.join(REPO, 'profiles', 'r01c_traffic.json')))
             except Exception:
                 return None
             sel = [v for k, v in tr.items() if key and key in k]
@@ -357,13 +357,13 @@ def run_ours(args):
                 ach = top['flops'] / (top['total_ms'] * 1e-3) / 1e12
                 roofline = {'kernel': top['name'], 'bound': 'tensor', 'achieved': ach, 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': ach / tc_peak,
                             'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
-                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01b_ncu_full_decode.md)',
+                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01c_ncu_full_decode.md)',
                             'algorithmic_per_launch': top['flops'] / max(top['launches'], 1), 'peak_source': tc_src, 'share_of_step': top['total_ms'] / ms}
             else:
                 ach = top['bytes'] / (top['total_ms'] * 1e-3) / 1e9
                 roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
                             'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
-                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01b_ncu_full_decode.md)',
+                            'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01c_ncu_full_decode.md)',
                             'algorithmic_per_launch': top['bytes'] / max(top['launches'], 1), 'peak_source': hbm_src, 'share_of_step': top['total_ms'] / ms}
         line = {
             'metric': f'images/sec ({args.mode})', 'value': total_imgs / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,

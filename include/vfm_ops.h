@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 3
+#define VFM_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -141,6 +141,10 @@ typedef struct {
      * <= 5x5 taps: F.pad(x, mode='replicate') + depthwise conv with a fixed kernel, the blur behind the pixel-shuffle upsampler
      * (networks/utils/convnext_utils.py:250-255).  Returns VFM_ERR_NO_KERNEL where the streaming kernel does not apply. */
     int32_t      pad_mode;
+    /* != 0: f holds one fh x fw filter per channel, f_stride_c elements apart: a depthwise conv with learned taps (fp16 / fp32, 5x5 / 7x7,
+     * "same" zero padding: padx0 = fw/2), the dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128);
+     * together with flip = 1 (correlation) and the ep_bias epilogue it is nn.Conv2d(C, C, k, padding=k//2, groups=C).  Inference. */
+    int64_t      f_stride_c;
 } vfm_upfirdn2d_params;
 
 VFM_API int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream);

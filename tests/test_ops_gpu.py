@@ -231,6 +231,25 @@ def test_blur2d_replicate(cfg, dtype):
     assert rel_err(y, yr) <= TOL[str(dtype).split('.')[-1]]
 
 
+@pytest.mark.parametrize('cfg', [dict(shape=(2, 6, 16, 32), k=5), dict(shape=(2, 5, 24, 64), k=7), dict(shape=(1, 3, 9, 8), k=7),
+                                 dict(shape=(1, 2, 70, 512), k=7), dict(shape=(3, 4, 12, 24), k=5)], ids=lambda c: f"k{c['k']}-{c['shape'][2]}x{c['shape'][3]}")
+@pytest.mark.parametrize('bias', [True, False])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_depthwise_conv2d(cfg, bias, dtype):
+    """k x k depthwise conv + bias of the ConvNeXt layers (convnext_utils.py:99,128) against F.conv2d in fp64."""
+    V = _ops()
+    g = torch.Generator().manual_seed(14)
+    Cc, k = cfg['shape'][1], cfg['k']
+    xq = torch.randn(cfg['shape'], generator=g).to(dtype).double()
+    w = (torch.randn(Cc, 1, k, k, generator=g) * 0.2).double()
+    b = (torch.randn(Cc, generator=g) * 0.3).double() if bias else None
+    yr = torch.nn.functional.conv2d(xq, w, b, padding=k // 2, groups=Cc)
+    with torch.no_grad():
+        y = V.upfirdn2d.depthwise_conv2d(xq.to(DEV, dtype), w.float().to(DEV), b.float().to(DEV) if bias else None)
+    assert y is not None and y.shape == yr.shape and y.dtype == dtype
+    assert rel_err(y, yr) <= (2e-3 if dtype == torch.float16 else 1e-5)
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

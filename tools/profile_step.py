@@ -7,19 +7,20 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vfm_vae_b200.decoder import SynthesisNetwork, F16D32_LEGACY_KWARGS  # noqa: E402
+from vfm_vae_b200.decoder import SynthesisNetwork, F16D32_LEGACY_KWARGS, F16D32_CONVNEXT_KWARGS  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--mode', default='decode')
 ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--rows', type=int, default=40)
+ap.add_argument('--variant', default='legacy')
 args = ap.parse_args()
 torch.backends.cudnn.benchmark = True
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = 'cuda'
 torch.manual_seed(0)
-net = SynthesisNetwork(**F16D32_LEGACY_KWARGS).to(dev)
+net = SynthesisNetwork(**(F16D32_CONVNEXT_KWARGS if args.variant == 'convnext' else F16D32_LEGACY_KWARGS)).to(dev)
 z = torch.randn(args.batch, 512, 16, 16, device=dev)
 ws = torch.randn(args.batch, net.num_ws, 512, device=dev)
 if args.mode == 'decode':

@@ -33,7 +33,7 @@ class Upfirdn2dParams(C.Structure):
                 ('out_stride_w', _i64), ('out_stride_h', _i64), ('out_stride_c', _i64), ('out_stride_n', _i64),
                 ('add', _vp), ('add_stride_h', _i64), ('add_stride_n', _i64),
                 ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64), ('ep_bias', _vp),
-                ('pad_mode', _i32)]
+                ('pad_mode', _i32), ('f_stride_c', _i64)]
 
 
 class FilteredLreluParams(C.Structure):
@@ -138,8 +138,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 3:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 3)')
+    if lib.vfm_abi_version() != 4:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 4)')
     _lib = lib
     return lib
 

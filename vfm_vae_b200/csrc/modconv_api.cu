@@ -64,7 +64,7 @@ static int call_upfirdn(int dtype, const void* in, void* out, const float* f, in
     u.out_w = ow; u.out_h = oh;
     u.out_stride_w = 1; u.out_stride_h = out_pitch; u.out_stride_c = (int64_t)oh * out_pitch; u.out_stride_n = (int64_t)C * oh * out_pitch;
     u.add = add; u.add_stride_h = ow; u.add_stride_n = add_sn;
-    u.ep_enable = 0; u.ep_act = 1; u.ep_alpha = 0; u.ep_gain = 1; u.ep_clamp = -1; u.ep_bias = nullptr; u.pad_mode = 0;
+    u.ep_enable = 0; u.ep_act = 1; u.ep_alpha = 0; u.ep_gain = 1; u.ep_clamp = -1; u.ep_bias = nullptr; u.pad_mode = 0; u.f_stride_c = 0;
     if (ep && ep->enable) { u.ep_enable = 1; u.ep_act = ep->act; u.ep_alpha = ep->alpha; u.ep_gain = ep->gain; u.ep_clamp = ep->clamp; u.ep_bias = ep->bias; }
     return vfm_upfirdn2d(&u, stream);
 }

@@ -33,6 +33,7 @@ struct UpfirdnArgs {
     int vec_ok;   // input rows can be staged with 16-byte loads
     int ep_enable, ep_act; float ep_alpha, ep_gain, ep_clamp; const void* ep_bias;
     int pad_mode;    // 0 = zero padding, 1 = replicate (clamp to edge; streaming blur kernel only)
+    int64_t fsc;     // per-channel stride of f (0 = one shared filter; != 0: depthwise conv with learned taps)
 };
 
 template <class T, class S> __device__ __forceinline__ S ep_apply(const UpfirdnArgs& p, S v, int c) {
@@ -575,6 +576,48 @@ __global__ void __launch_bounds__(128, 3) upfirdn2d_blur_repl(UpfirdnArgs p, int
     else blur_body<T, PX, false, 8, FT, true>(p, k, cg, strips, strip_rows);
 }
 
+// Depthwise k x k conv (k = 5, 7; stride 1, "same" zero padding) with learned per-channel taps + bias: the dwconv of the ConvNeXt
+// synthesis layers (networks/utils/convnext_utils.py:99,128).  It is the same streaming kernel -- a k-row ring of partially
+// accumulated output rows in registers -- with the taps of the thread's channel in registers (49 FMAs per output: FMA-issue
+// bound, ~1.5 ms for [64,128,256,256] fp16 against ~20 ms of the stock depthwise kernel).
+template <class T, int FT, int PX>
+__global__ void __launch_bounds__(128, 2) upfirdn2d_dw(UpfirdnArgs p, int cg, int strips, int strip_rows) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t plane = (gid / cg) / strips;
+    const int c = (plane < (int64_t)p.channels * p.batch) ? (int)(plane % p.channels) : 0;
+    const float* fp = p.f + (int64_t)c * p.fsc;
+    BlurTaps<FT> k;
+#pragma unroll
+    for (int ty = 0; ty < FT; ty++)
+#pragma unroll
+        for (int tx = 0; tx < FT; tx++) {
+            float v = 0.f;
+            if (tx < p.fw && ty < p.fh) {
+                const int fx = p.flip ? tx : p.fw - 1 - tx, fy = p.flip ? ty : p.fh - 1 - ty;
+                v = __ldg(&fp[fy * p.fsh + fx * p.fsw]) * (float)p.gain;
+                if (p.ep_enable) v *= p.ep_gain;
+            }
+            k.f[ty][tx] = v;
+        }
+    blur_body<T, PX, false, 8, FT, false>(p, k, cg, strips, strip_rows);
+}
+
+template <class T>
+int launch_dw(const UpfirdnArgs& a, cudaStream_t stream) {
+    const int groups = ceil_div(a.out_w, 8);
+    const int64_t planes = (int64_t)a.channels * a.batch;
+    int strip_rows = 64;
+    while (strip_rows > 8 && planes * ceil_div(a.out_h, strip_rows) * groups < (int64_t)kNumSMs * 1024) strip_rows >>= 1;
+    const int strips = ceil_div(a.out_h, strip_rows);
+    const int64_t blocks = ceil_div64(planes * strips * groups, 128);
+    if (blocks > 0x7fffffffLL) { set_error("upfirdn2d: grid too large"); return VFM_ERR_INVALID; }
+    KernelTimer timer("depthwise_conv", stream, 0.0, ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T),
+                      "k%dw%dc%d", a.fw, a.out_w, a.channels);
+    if (a.fw == 7) upfirdn2d_dw<T, 7, 3><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+    else upfirdn2d_dw<T, 5, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+    return launch_status("upfirdn2d_dw");
+}
+
 template <class T>
 int launch_blur(const UpfirdnArgs& a, cudaStream_t stream) {
     // 16 columns per thread when the rows are fp16, 32-byte aligned and wide enough to keep a warp busy
@@ -654,6 +697,14 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
         // streaming blur: up = down = 1, <= 4x4 taps, 16-byte aligned rows, and the left padding inside the halo it handles
         const int es = (int)sizeof(T);
         const bool rows16 = a.vec_ok && aligned16(a.y) && (a.osh * es) % 16 == 0 && (a.osc * es) % 16 == 0 && (a.osn * es) % 16 == 0;
+        if (a.fsc != 0) {
+            // depthwise conv with per-channel taps: k in {5, 7}, same-size output
+            if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw == a.fh && (a.fw == 5 || a.fw == 7) && rows16 &&
+                !a.add && !a.pad_mode && a.padx0 == a.fw / 2 && a.pady0 == a.fh / 2 && a.out_w == a.in_w && a.out_h == a.in_h)
+                return launch_dw<T>(a, stream);
+            set_error("upfirdn2d: per-channel filters are only implemented for same-size 5x5 / 7x7 depthwise convs of 16-byte aligned rows");
+            return VFM_ERR_NO_KERNEL;
+        }
         if (a.pad_mode) {
             // replicate padding: same-size output, rows of whole 8-column groups
             if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw <= 5 && a.fh <= 5 && rows16 && !a.add && !a.ep_enable &&
@@ -667,7 +718,7 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
             (!a.ep_enable || (a.ep_gain > 0.f && (a.ep_act != 3 || (a.ep_alpha >= 0.f && a.ep_alpha <= 1.f)))))
             return launch_blur<T>(a, stream);
     }
-    if (a.pad_mode) { set_error("upfirdn2d: replicate padding needs fp16/fp32"); return VFM_ERR_NO_KERNEL; }
+    if (a.pad_mode || a.fsc != 0) { set_error("upfirdn2d: replicate padding / per-channel filters need fp16/fp32"); return VFM_ERR_NO_KERNEL; }
     if (wcontig && sym && a.out_w >= 32 && a.out_h >= 8) {
         int up = a.upx, down = a.downx;
         if (up == 1 && down == 1 && a.fw <= 4 && a.fh <= 4) return launch_tiled<T, 1, 1, 4, 4>(a, stream);
@@ -714,6 +765,7 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
     a.ep_enable = p->ep_enable; a.ep_act = p->ep_act; a.ep_alpha = (float)p->ep_alpha; a.ep_gain = (float)p->ep_gain; a.ep_clamp = (float)p->ep_clamp; a.ep_bias = p->ep_bias;
     VFM_CHECK_ARG(!p->ep_enable || p->ep_act == 1 || p->ep_act == 3, "upfirdn2d: fused epilogue supports linear and lrelu only");
     a.pad_mode = p->pad_mode;
+    a.fsc = p->f_stride_c;
     a.xstart = a.ystart = a.tiles_x = a.tiles_y = 0;
     {
         const int64_t es = (p->dtype == VFM_F16) ? 2 : (p->dtype == VFM_F32 ? 4 : 8);

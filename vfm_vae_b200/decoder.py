@@ -30,6 +30,7 @@ def default_ops():
     from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act, modulated_pointwise_conv2d, fused_convnext_mlp
     return SimpleNamespace(fused_layer=fused_modconv_bias_act, bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
                            setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d, blur2d_replicate=upfirdn2d.blur2d_replicate,
+                           depthwise_conv2d=upfirdn2d.depthwise_conv2d,
                            modulated_conv2d=modulated_conv2d, modulated_pointwise_conv2d=modulated_pointwise_conv2d,
                            fused_convnext_mlp=None if os.environ.get('VFM_NO_FUSED_CONVNEXT') else fused_convnext_mlp)
 
@@ -338,7 +339,12 @@ class ConvNeXtSynthesisLayer(nn.Module):
         dtype = x.dtype
         x_in = x
         style = self.affine_pw1(w)
-        x = self.dwconv(x)
+        dw = getattr(self.ops, 'depthwise_conv2d', None)
+        y = None
+        if dw is not None and not torch.is_grad_enabled() and x.is_cuda:
+            xin = x.to(torch.get_autocast_dtype('cuda')) if torch.is_autocast_enabled() else x
+            y = dw(xin, self.dwconv.weight, self.dwconv.bias)       # k x k depthwise conv + bias on the streaming stencil kernel (fp16)
+        x = y if y is not None else self.dwconv(x)
         if self.legacy:
             noise = self.noise_const[None, None] * self.noise_strength
             noise = F.interpolate(noise, size=x.shape[2:], mode='bilinear', align_corners=False)
@@ -375,7 +381,7 @@ class ConvNeXtToRGBLayer(nn.Module):
     def forward(self, x, w):
         style = self.affine(w) * self.weight_gain
         if torch.is_autocast_enabled() and x.is_cuda:
-            x = x.to(torch.get_autocast_gpu_dtype())
+            x = x.to(torch.get_autocast_dtype('cuda'))
         y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=style, demodulate=False)
         return y + self.bias
 

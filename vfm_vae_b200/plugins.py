@@ -111,19 +111,21 @@ class _BiasActPlugin:
 
 class _Upfirdn2dPlugin:
     @staticmethod
-    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, pad_mode=0):
-        """``pad_mode=1`` (extension): replicate padding; returns None where no kernel implements it."""
+    def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, pad_mode=0, bias=None):
+        """``pad_mode=1`` (extension): replicate padding; a rank-3 ``f`` [C,fh,fw] (extension) is one filter per channel = a depthwise
+        conv, optionally with ``bias`` [C]; both return None where no kernel implements them."""
         _check(x.is_cuda, 'x must reside on CUDA device')
         _check(f.device == x.device, 'f must reside on the same device as x')
         _check(f.dtype == torch.float32, 'f must be float32')
         _check(x.numel() > 0, 'x has zero size')
         _check(f.numel() > 0, 'f has zero size')
         _check(x.dim() == 4, 'x must be rank 4')
-        _check(f.dim() == 2, 'f must be rank 2')
+        per_channel = f.dim() == 3
+        _check(f.dim() == 2 or (per_channel and f.size(0) == x.size(1) and f.is_contiguous()), 'f must be rank 2 (or [C,fh,fw] contiguous)')
         _check(upx >= 1 and upy >= 1, 'upsampling factor must be at least 1')
         _check(downx >= 1 and downy >= 1, 'downsampling factor must be at least 1')
-        out_w = (x.size(3) * upx + padx0 + padx1 - f.size(1) + downx) // downx
-        out_h = (x.size(2) * upy + pady0 + pady1 - f.size(0) + downy) // downy
+        out_w = (x.size(3) * upx + padx0 + padx1 - f.size(-1) + downx) // downx
+        out_h = (x.size(2) * upy + pady0 + pady1 - f.size(-2) + downy) // downy
         _check(out_w >= 1 and out_h >= 1, 'output must be at least 1x1')
         cl = x.dim() == 4 and x.stride(1) == 1 and x.size(1) > 1 and not x.is_contiguous()
         y = torch.empty([x.size(0), x.size(1), out_h, out_w], dtype=x.dtype, device=x.device,
@@ -135,7 +137,10 @@ class _Upfirdn2dPlugin:
         p.padx0, p.pady0, p.flip, p.gain = int(padx0), int(pady0), int(bool(flip)), float(gain)
         p.in_w, p.in_h, p.channels, p.batch = x.size(3), x.size(2), x.size(1), x.size(0)
         p.in_stride_w, p.in_stride_h, p.in_stride_c, p.in_stride_n = x.stride(3), x.stride(2), x.stride(1), x.stride(0)
-        p.fw, p.fh, p.f_stride_w, p.f_stride_h = f.size(1), f.size(0), f.stride(1), f.stride(0)
+        p.fw, p.fh, p.f_stride_w, p.f_stride_h = f.size(-1), f.size(-2), f.stride(-1), f.stride(-2)
+        p.f_stride_c = f.stride(0) if per_channel else 0
+        if bias is not None:
+            p.ep_enable, p.ep_act, p.ep_alpha, p.ep_gain, p.ep_clamp, p.ep_bias = 1, 1, 0.0, 1.0, -1.0, _ptr(bias)
         p.out_w, p.out_h = out_w, out_h
         p.out_stride_w, p.out_stride_h, p.out_stride_c, p.out_stride_n = y.stride(3), y.stride(2), y.stride(1), y.stride(0)
         p.add, p.add_stride_h, p.add_stride_n = None, 0, 0
@@ -146,7 +151,7 @@ class _Upfirdn2dPlugin:
         p.pad_mode = int(pad_mode)
         with torch.cuda.device(x.device):
             st = _lib.load().vfm_upfirdn2d(C.byref(p), _stream(x))
-        if pad_mode and st == _lib.VFM_ERR_NO_KERNEL:
+        if (pad_mode or per_channel) and st == _lib.VFM_ERR_NO_KERNEL:
             return None
         _lib.check(st, 'upfirdn2d')
         return y

@@ -243,9 +243,13 @@ def test_depthwise_conv2d(cfg, bias, dtype):
     xq = torch.randn(cfg['shape'], generator=g).to(dtype).double()
     w = (torch.randn(Cc, 1, k, k, generator=g) * 0.2).double()
     b = (torch.randn(Cc, generator=g) * 0.3).double() if bias else None
+    noise = torch.randn(1, 1, *cfg['shape'][2:], generator=g) if bias else None       # the legacy layers' broadcast noise addend
     yr = torch.nn.functional.conv2d(xq, w, b, padding=k // 2, groups=Cc)
+    if noise is not None:
+        yr = yr + noise.double()
     with torch.no_grad():
-        y = V.upfirdn2d.depthwise_conv2d(xq.to(DEV, dtype), w.float().to(DEV), b.float().to(DEV) if bias else None)
+        y = V.upfirdn2d.depthwise_conv2d(xq.to(DEV, dtype), w.float().to(DEV), b.float().to(DEV) if bias else None,
+                                         noise.to(DEV) if noise is not None else None)
     assert y is not None and y.shape == yr.shape and y.dtype == dtype
     assert rel_err(y, yr) <= (2e-3 if dtype == torch.float16 else 1e-5)
 

@@ -135,6 +135,7 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
         if (p->ep_act == VFM_EP_ACT_GELU && !(use_tc(d) && d.up == 1 && !(use_pw(d) && aligned16(p->x) && aligned16(p->y)))) {
             set_error("modulated_conv2d: the gelu epilogue is only implemented in the tcgen05 kernel (up = 1)"); return VFM_ERR_NO_KERNEL;
         }
+        VFM_CHECK_ARG(p->ep_act != VFM_EP_ACT_GELU || p->ep_gain > 0, "modulated_conv2d: the gelu epilogue needs ep_gain > 0");
         VFM_CHECK_ARG(!p->ep_residual || p->ep_gamma, "modulated_conv2d: ep_residual needs ep_gamma");
         const bool fusable = (use_pw(d) && aligned16(p->x) && aligned16(p->y)) || (use_tc(d) && (d.up == 1 || !p->ep_residual));
         if (!fusable) { set_error("modulated_conv2d: no kernel fuses the epilogue for this descriptor"); return VFM_ERR_NO_KERNEL; }

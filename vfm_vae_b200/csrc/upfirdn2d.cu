@@ -434,7 +434,7 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps<F
     T* op = yp + ox0 + (int64_t)(oy_begin - (FT - 1)) * p.osh;                           // its address (dereferenced only for 0 <= orow < emit_rows)
     auto emit = [&](float* o, const float* addv) {
         if ((unsigned)orow < emit_rows) {
-            if (FT == 4 && p.add) {
+            if (p.add) {
 #pragma unroll
                 for (int i = 0; i < NC; i++) o[i] = fmaf(addv[i], eg, o[i]);
             }
@@ -468,13 +468,14 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps<F
 
     // input row r (0-based inside the strip) feeds output rows r - ty (ty < FT); output row r - (FT-1) is complete after it.
     // A ring of FT row vectors is kept in flight (a slot is refilled with row r + FT as soon as row r has been unpacked)
-    // and the addend of an output row is fetched two rows before it is needed (FT == 4 only).
+    // and the addend of an output row is fetched two rows (FT == 4; otherwise one row) before it is needed.
     uint32_t wq[FT][NW + NE];
-    float addq[2][NC];
-    const bool use_add = (FT == 4) && p.add != nullptr;
+    constexpr int AD = (FT == 4) ? 2 : 1;            // addend rows in flight (other tap counts: one row ahead, the addend is L2-resident noise)
+    float addq[AD][NC];
+    const bool use_add = p.add != nullptr;
 #pragma unroll
     for (int rr = 0; rr < FT; rr++) fetch(wq[rr]);
-    if (use_add) { fetch_add(addq[1]); fetch_add(addq[0]); }
+    if (use_add) { fetch_add(addq[AD - 1]); if (AD == 2) fetch_add(addq[0]); }
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows_warp; r0 += FT) {
 #pragma unroll
@@ -505,8 +506,8 @@ __device__ __forceinline__ void blur_body(const UpfirdnArgs& p, const BlurTaps<F
             }
             // output row r - (FT-1) used accumulator slot (rr + 1) % FT
             const bool emitted = orow >= 0;
-            emit(acc[(rr + 1) % FT], addq[rr & 1]);
-            if (use_add && emitted) fetch_add(addq[rr & 1]);
+            emit(acc[(rr + 1) % FT], addq[rr & (AD - 1)]);
+            if (use_add && emitted) fetch_add(addq[rr & (AD - 1)]);
 #pragma unroll
             for (int i = 0; i < NC; i++) acc[(rr + 1) % FT][i] = acc_init;
         }
@@ -700,7 +701,7 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
         if (a.fsc != 0) {
             // depthwise conv with per-channel taps: k in {5, 7}, same-size output
             if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw == a.fh && (a.fw == 5 || a.fw == 7) && rows16 &&
-                !a.add && !a.pad_mode && a.padx0 == a.fw / 2 && a.pady0 == a.fh / 2 && a.out_w == a.in_w && a.out_h == a.in_h)
+                !a.pad_mode && a.padx0 == a.fw / 2 && a.pady0 == a.fh / 2 && a.out_w == a.in_w && a.out_h == a.in_h)
                 return launch_dw<T>(a, stream);
             set_error("upfirdn2d: per-channel filters are only implemented for same-size 5x5 / 7x7 depthwise convs of 16-byte aligned rows");
             return VFM_ERR_NO_KERNEL;

@@ -339,24 +339,27 @@ class ConvNeXtSynthesisLayer(nn.Module):
         dtype = x.dtype
         x_in = x
         style = self.affine_pw1(w)
-        dw = getattr(self.ops, 'depthwise_conv2d', None)
-        y = None
-        if dw is not None and not torch.is_grad_enabled() and x.is_cuda:
-            xin = x.to(torch.get_autocast_dtype('cuda')) if torch.is_autocast_enabled() else x
-            y = dw(xin, self.dwconv.weight, self.dwconv.bias)       # k x k depthwise conv + bias on the streaming stencil kernel (fp16)
-        x = y if y is not None else self.dwconv(x)
+        noise = None
         if self.legacy:
             noise = self.noise_const[None, None] * self.noise_strength
             noise = F.interpolate(noise, size=x.shape[2:], mode='bilinear', align_corners=False)
+        dw = getattr(self.ops, 'depthwise_conv2d', None)
+        y = None
+        if dw is not None and not torch.is_grad_enabled() and x.is_cuda:
+            # k x k depthwise conv + bias + noise on the streaming stencil kernel (one rounding of the sum to the activation dtype)
+            xin = x.to(torch.get_autocast_dtype('cuda')) if torch.is_autocast_enabled() else x
+            y = dw(xin, self.dwconv.weight, self.dwconv.bias, noise)
+        noise_done = y is not None
+        x = y if y is not None else self.dwconv(x)
         fused = getattr(self.ops, 'fused_convnext_mlp', None)
         if fused is not None and not torch.is_grad_enabled():
             # inference: one GroupNorm statistics pass + two tensor-core 1x1 convs with everything else in their epilogues
-            xd = torch.add(x, noise.to(x.dtype)) if self.legacy else x
+            xd = torch.add(x, noise.to(x.dtype)) if (self.legacy and not noise_done) else x
             y = fused(xd.to(dtype), x_in, self.norm.weight, self.norm.bias, self.norm.num_groups, self.norm.eps, self.pwconv1.weight,
                       self.pwconv1.bias, style, self.pwconv2.weight, self.pwconv2.bias, self.gamma, self.pwconv1.demodulate)
             if y is not None:
                 return y
-        if self.legacy:
+        if self.legacy and not noise_done:
             x = x + noise
         x = self.norm(x)
         x = self.pwconv1(x, style)

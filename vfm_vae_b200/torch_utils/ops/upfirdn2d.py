@@ -165,8 +165,8 @@ def blur2d_replicate(x, f, padding):
     return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, pl, pr, pt, pb, True, 1.0, pad_mode=1)
 
 
-def depthwise_conv2d(x, weight, bias=None):
-    """Inference-only: ``F.conv2d(x, weight, bias, padding=k // 2, groups=C)`` for ``weight`` [C,1,k,k], k in {5, 7}, fp16 / fp32 ``x`` -- the
+def depthwise_conv2d(x, weight, bias=None, noise=None):
+    """Inference-only: ``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {5, 7}, fp16 / fp32 ``x`` -- the
     dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128) -- on the streaming stencil kernel with the
     channel's taps in registers.  Returns None when the kernel does not apply (the caller uses the stock module)."""
     if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
@@ -177,4 +177,5 @@ def depthwise_conv2d(x, weight, bias=None):
     k = weight.shape[2]
     f = weight.detach().to(torch.float32).reshape(weight.shape[0], k, k).contiguous()
     b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
-    return _plugin.upfirdn2d(x, f, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, bias=b)
+    add = noise.detach().to(torch.float32).reshape(x.shape[2], x.shape[3]).contiguous() if noise is not None else None
+    return _plugin.upfirdn2d(x, f, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, add=add, bias=b)

@@ -466,15 +466,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             const bool wide_item = wide && p.vec_out && (!side_base || p.vec_side) && (PAIR || p.out_s == 1) &&
                                    (PAIR ? (2 * (w0 + p.tw) <= p.out_W) : (w0 + p.tw <= ph0.Wg && w0 + p.tw + ph0.ox <= p.out_W));
             // side input (x of the dstyles reduction / residual of the fused layer): this thread's 16-pixel chunks, prefetched
-            uint32_t pre[PRE ? NIT * RW : 1];
+            // (a rolling window of PF chunks: the first PF are requested before the accumulators are awaited, chunk c + PF when
+            // chunk c has been unpacked -- holding all NIT chunks costs 64 registers and serialises the epilogue arithmetic)
+            constexpr int PF = NIT < 4 ? NIT : 4;
+            uint32_t pre[PRE ? PF * RW : 1];
+            auto side_fetch = [&](int c, uint32_t* dst) {
+                int n, gh, gw;
+                locate(chalf * (NPIX / 2) + c * 16, n0, h0, w0, n, gh, gw);
+                if (n < p.N && gh < ph0.Hg && gh < p.out_H)
+                    raw16_load<TOut>(side_base + ((size_t)n * p.Nout + ch) * side_plane + (size_t)gh * side_pitch + gw, dst);
+            };
             if (PRE && side_base && wide_item) {
 #pragma unroll
-                for (int c = 0; c < NIT; c++) {
-                    int n, gh, gw;
-                    locate(chalf * (NPIX / 2) + c * 16, n0, h0, w0, n, gh, gw);
-                    if (n < p.N && gh < ph0.Hg && gh < p.out_H)
-                        raw16_load<TOut>(side_base + ((size_t)n * p.Nout + ch) * side_plane + (size_t)gh * side_pitch + gw, &pre[c * RW]);
-                }
+                for (int c = 0; c < PF; c++) side_fetch(c, &pre[c * RW]);
             }
             if (has_add) asm volatile("bar.sync 1, 256;" ::: "memory");
 
@@ -517,22 +521,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                     } else if (p.ep.act == VFM_EP_ACT_GELU) {
                         const float hg = 0.5f * p.ep.gain;
                         if (sizeof(TOut) == 2) {
-                            // fp16 output: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7) with the approximate reciprocal and
-                            // exp2 of the SFU (2^-22 relative, far below half precision): 15 branch-free instructions per element
-                            // instead of ~40 with the IEEE reciprocal's fix-up path -- the 4C-wide GELU epilogue is issue-bound
+                            // fp16 output: erfc by Abramowitz-Stegun 7.1.28, erfc(z) = (1 + a1 z + .. + a6 z^6)^-16 (|error| < 3e-7), with
+                            // z = |x| / sqrt2 folded into the coefficients and the SFU's approximate reciprocal: one SFU and 14 FP32
+                            // instructions per element, branch-free (7.1.26 needs a second SFU op for exp(-z^2); the IEEE reciprocal
+                            // and expf cost ~40) -- the 4C-wide GELU epilogue is bound by issue slots and the SFU, not by the MMAs.
+                            //   gelu(x) g = h + |h| erf(z) = (h + |h|) - |h| erfc(z),  h = g x / 2,  g > 0  (no cancellation for x < 0)
+                            // Written stage by stage over groups of 8 elements: the two epilogue warps per scheduler cannot hide the
+                            // latencies of one element's dependent chain, eight interleaved chains can.
+                            constexpr float r2 = 0.70710678118654752f;
+                            constexpr float c1 = 0.0705230784f * r2, c2 = 0.0422820123f * r2 * r2, c3 = 0.0092705272f * r2 * r2 * r2,
+                                            c4 = 0.0001520143f * r2 * r2 * r2 * r2, c5 = 0.0002765672f * r2 * r2 * r2 * r2 * r2,
+                                            c6 = 0.0000430638f * r2 * r2 * r2 * r2 * r2 * r2;
+                            constexpr int G = NV >= 8 ? 8 : NV;
 #pragma unroll
-                            for (int i = 0; i < NV; i++) {
-                                const float z = fabsf(o[i]) * 0.70710678118654752f;
-                                float t, ex;
-                                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * z * -1.4426950408889634f));
-                                float q = fmaf(1.061405429f, t, -1.453152027f);
-                                q = fmaf(q, t, 1.421413741f);
-                                q = fmaf(q, t, -0.284496736f);
-                                q = fmaf(q, t, 0.254829592f);
-                                const float e = fmaf(-(q * t), ex, 1.f);                 // erf(|x| / sqrt2)
-                                const float ho = hg * o[i];
-                                o[i] = fmaf(fabsf(ho), e, ho);                           // 0.5 g x (1 + sign(x) erf(|x|/sqrt2)),  g > 0
+                            for (int i0 = 0; i0 < NV; i0 += G) {
+                                float a[G], q[G];
+#pragma unroll
+                                for (int i = 0; i < G; i++) { a[i] = fabsf(o[i0 + i]); q[i] = fmaf(c6, a[i], c5); }
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] = fmaf(q[i], a[i], c4);
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] = fmaf(q[i], a[i], c3);
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] = fmaf(q[i], a[i], c2);
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] = fmaf(q[i], a[i], c1);
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] = fmaf(q[i], a[i], 1.f);
+#pragma unroll
+                                for (int i = 0; i < G; i++) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q[i]) : "f"(q[i]));
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] *= q[i];
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] *= q[i];
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] *= q[i];
+#pragma unroll
+                                for (int i = 0; i < G; i++) q[i] *= q[i];               // erfc(|x| / sqrt2)
+#pragma unroll
+                                for (int i = 0; i < G; i++) {
+                                    const float h = hg * o[i0 + i];
+                                    o[i0 + i] = fmaf(-fabsf(h), q[i], h + fabsf(h));
+                                }
                             }
                         } else {
 #pragma unroll
@@ -576,6 +606,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         int n, gh, gw0;
                         locate(chalf * (NPIX / 2) + jw, n0, h0, w0, n, gh, gw0);
                         set_sample(n);
+                        float sd[16];
+                        if (PRE && side_base) {         // (before the range check: the window slot is recycled for every chunk)
+                            raw16_unpack<TOut>(&pre[(step % PF) * RW], sd);
+                            if (step + PF < NIT) side_fetch(step + PF, &pre[(step % PF) * RW]);
+                        }
                         const int oy = gh * p.out_s + ph0.oy;
                         if (n >= p.N || gh >= ph0.Hg || oy >= p.out_H) break;
                         float v[NSUB][16];
@@ -601,8 +636,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         const int ox0 = gw0 + ph0.ox;
                         const size_t off = plane * HW + (size_t)oy * p.out_pitch + ox0;
                         float* o = v[0];
-                        float sd[16];
-                        if (PRE && side_base) raw16_unpack<TOut>(&pre[step * RW], sd);
                         if (DGRAD) {
                             if (do_ds) {
 #pragma unroll

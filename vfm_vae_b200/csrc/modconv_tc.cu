@@ -468,7 +468,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             // side input (x of the dstyles reduction / residual of the fused layer): this thread's 16-pixel chunks, prefetched
             // (a rolling window of PF chunks: the first PF are requested before the accumulators are awaited, chunk c + PF when
             // chunk c has been unpacked -- holding all NIT chunks costs 64 registers and serialises the epilogue arithmetic)
-            constexpr int PF = NIT < 4 ? NIT : 4;
+            static_assert(NIT % 2 == 0, "the step loop is unrolled by two");
+            constexpr int UNR = MNP ? 2 : NIT;                 // unroll factor of the step loop of the fast path (see there)
+            constexpr int PF = (UNR < 4 || sizeof(TOut) == 4) ? 2 : 4;      // divides UNR (static register slots); fp32 chunks are 16 words
             uint32_t pre[PRE ? PF * RW : 1];
             auto side_fetch = [&](int c, uint32_t* dst) {
                 int n, gh, gw;
@@ -597,9 +599,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 };
                 issue(0, 0);
                 tmem_ld_wait();
+                // 1x1 convs (MNP), whose epilogue is not hidden behind the MMAs: unrolled by two only (static register slots of the
+                // TMEM / side-input double buffers) -- fully unrolled, the ~3000 straight-line instructions per item starve the two
+                // warps per scheduler of instructions (30 % of the stall samples of the 1x1 GELU conv were no_instructions).  The
+                // k x k convs keep the full unroll (3 % faster there: compile-time addressing, deeper side-input window).
+#pragma unroll 1
+                for (int step0 = 0; step0 < NIT; step0 += UNR) {
 #pragma unroll
-                for (int step = 0; step < NIT; step++) {
-                    const int slot = step & 1;
+                  for (int u = 0; u < UNR; u++) {
+                    const int step = step0 + u;
+                    const int slot = u & 1;
                     if (step + 1 < NIT) issue(step + 1, slot ^ 1);     // in flight while this step is processed
                     do {
                         const int jw = step * 16;                      // column inside this warp's half
@@ -608,8 +617,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         set_sample(n);
                         float sd[16];
                         if (PRE && side_base) {         // (before the range check: the window slot is recycled for every chunk)
-                            raw16_unpack<TOut>(&pre[(step % PF) * RW], sd);
-                            if (step + PF < NIT) side_fetch(step + PF, &pre[(step % PF) * RW]);
+                            raw16_unpack<TOut>(&pre[(u % PF) * RW], sd);
+                            if (step + PF < NIT) side_fetch(step + PF, &pre[(u % PF) * RW]);
                         }
                         const int oy = gh * p.out_s + ph0.oy;
                         if (n >= p.N || gh >= ph0.Hg || oy >= p.out_H) break;
@@ -657,6 +666,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                         store16<TOut>((TOut*)p.out + off, o, 16, true);
                     } while (0);
                     if (step + 1 < NIT) tmem_ld_wait();
+                  }
                 }
             } else {
                 // tiles of rows shorter than 16 pixels (images up to 8x8): one element at a time, compact code

@@ -141,7 +141,7 @@ typedef struct {
      * <= 5x5 taps: F.pad(x, mode='replicate') + depthwise conv with a fixed kernel, the blur behind the pixel-shuffle upsampler
      * (networks/utils/convnext_utils.py:250-255).  Returns VFM_ERR_NO_KERNEL where the streaming kernel does not apply. */
     int32_t      pad_mode;
-    /* != 0: f holds one fh x fw filter per channel, f_stride_c elements apart: a depthwise conv with learned taps (fp16 / fp32, 5x5 / 7x7,
+    /* != 0: f holds one fh x fw filter per channel, f_stride_c elements apart: a depthwise conv with learned taps (fp16 / fp32, 3x3 / 5x5 / 7x7,
      * "same" zero padding: padx0 = fw/2), the dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128);
      * together with flip = 1 (correlation) and the ep_bias epilogue it is nn.Conv2d(C, C, k, padding=k//2, groups=C).  Inference. */
     int64_t      f_stride_c;
@@ -338,6 +338,17 @@ typedef struct {
 } vfm_rows_params;
 VFM_API int vfm_rows_affine(const vfm_rows_params* p, void* stream);
 VFM_API int vfm_rows_dot(const vfm_rows_params* p, void* stream);
+
+/* PixelShuffle(2): y[n, c, 2h+i, 2w+j] = x[n, 4c + 2i + j, h, w];  x [batch, 4*out_channels, in_h, in_w] -> y [batch, out_channels,
+ * 2 in_h, 2 in_w], both contiguous NCHW, fp16 / fp32, in_w % 4 == 0.  Replaces nn.PixelShuffle(2) in the reference's
+ * SeparableUpsampleWithFixedBlur (networks/utils/convnext_utils.py:197-257); the Python mirror uses it under no_grad. */
+typedef struct {
+    const void* x;
+    void*       y;
+    int32_t     dtype;
+    int32_t     batch, out_channels, in_h, in_w;
+} vfm_pixel_shuffle2_params;
+VFM_API int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

@@ -254,6 +254,32 @@ def test_depthwise_conv2d(cfg, bias, dtype):
     assert rel_err(y, yr) <= (2e-3 if dtype == torch.float16 else 1e-5)
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+@pytest.mark.parametrize('shape', [(2, 8, 6, 8), (1, 4, 5, 4), (3, 12, 16, 64), (2, 16, 33, 128)], ids=lambda s: 'x'.join(map(str, s)))
+def test_pixel_shuffle2(shape, dtype):
+    """PixelShuffle(2) of SeparableUpsampleWithFixedBlur (convnext_utils.py:197-257): a pure permutation, bit-exact."""
+    V = _ops()
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(shape, generator=g).to(dtype).to(DEV)
+    with torch.no_grad():
+        y = V.upfirdn2d.pixel_shuffle2(x)
+    assert y is not None and torch.equal(y, torch.nn.functional.pixel_shuffle(x, 2))
+    assert V.upfirdn2d.pixel_shuffle2(x[:, :, :, :3].contiguous()) is None        # W % 4 != 0: the caller keeps the stock op
+
+
+def test_depthwise_conv2d_k3():
+    """3x3 depthwise conv (no bias) of SeparableUpsampleWithFixedBlur against F.conv2d."""
+    V = _ops()
+    g = torch.Generator().manual_seed(16)
+    for dtype, tol in ((torch.float16, 2e-3), (torch.float32, 1e-5)):
+        xq = torch.randn(2, 6, 20, 40, generator=g).to(dtype).double()
+        w = (torch.randn(6, 1, 3, 3, generator=g) * 0.3).double()
+        yr = torch.nn.functional.conv2d(xq, w, None, padding=1, groups=6)
+        with torch.no_grad():
+            y = V.upfirdn2d.depthwise_conv2d(xq.to(DEV, dtype), w.float().to(DEV))
+        assert y is not None and rel_err(y, yr) <= tol
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

@@ -88,6 +88,10 @@ class RowsParams(C.Structure):
     _fields_ = [('a', _vp), ('b', _vp), ('P', _vp), ('Q', _vp), ('R', _vp), ('out', _vp), ('dtype', _i32), ('rows', _i64), ('hw', _i64)]
 
 
+class PixelShuffle2Params(C.Structure):
+    _fields_ = [('x', _vp), ('y', _vp), ('dtype', _i32), ('batch', _i32), ('out_channels', _i32), ('in_h', _i32), ('in_w', _i32)]
+
+
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
@@ -118,6 +122,7 @@ SYMBOLS = {
     'vfm_group_norm_backward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
     'vfm_rows_affine': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_rows_dot': (C.c_int, [C.POINTER(RowsParams), _vp]),
+    'vfm_pixel_shuffle2': (C.c_int, [C.POINTER(PixelShuffle2Params), _vp]),
 }
 
 _lib = None

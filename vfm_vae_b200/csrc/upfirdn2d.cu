@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(128, 3) upfirdn2d_blur_repl(UpfirdnArgs p, int
     else blur_body<T, PX, false, 8, FT, true>(p, k, cg, strips, strip_rows);
 }
 
-// Depthwise k x k conv (k = 5, 7; stride 1, "same" zero padding) with learned per-channel taps + bias: the dwconv of the ConvNeXt
+// Depthwise k x k conv (k = 3, 5, 7; stride 1, "same" zero padding) with learned per-channel taps + bias: the dwconv of the ConvNeXt
 // synthesis layers (networks/utils/convnext_utils.py:99,128).  It is the same streaming kernel -- a k-row ring of partially
 // accumulated output rows in registers -- with the taps of the thread's channel in registers (49 FMAs per output: FMA-issue
 // bound, ~1.5 ms for [64,128,256,256] fp16 against ~20 ms of the stock depthwise kernel).
@@ -615,7 +615,8 @@ int launch_dw(const UpfirdnArgs& a, cudaStream_t stream) {
     KernelTimer timer("depthwise_conv", stream, 0.0, ((double)a.in_w * a.in_h + (double)a.out_w * a.out_h) * a.channels * a.batch * sizeof(T),
                       "k%dw%dc%d", a.fw, a.out_w, a.channels);
     if (a.fw == 7) upfirdn2d_dw<T, 7, 3><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
-    else upfirdn2d_dw<T, 5, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+    else if (a.fw == 5) upfirdn2d_dw<T, 5, 2><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
+    else upfirdn2d_dw<T, 3, 1><<<(unsigned)blocks, 128, 0, stream>>>(a, groups, strips, strip_rows);
     return launch_status("upfirdn2d_dw");
 }
 
@@ -699,11 +700,11 @@ int launch(UpfirdnArgs a, cudaStream_t stream) {
         const int es = (int)sizeof(T);
         const bool rows16 = a.vec_ok && aligned16(a.y) && (a.osh * es) % 16 == 0 && (a.osc * es) % 16 == 0 && (a.osn * es) % 16 == 0;
         if (a.fsc != 0) {
-            // depthwise conv with per-channel taps: k in {5, 7}, same-size output
-            if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw == a.fh && (a.fw == 5 || a.fw == 7) && rows16 &&
+            // depthwise conv with per-channel taps: k in {3, 5, 7}, same-size output
+            if (wcontig && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.fw == a.fh && (a.fw == 3 || a.fw == 5 || a.fw == 7) && rows16 &&
                 !a.pad_mode && a.padx0 == a.fw / 2 && a.pady0 == a.fh / 2 && a.out_w == a.in_w && a.out_h == a.in_h)
                 return launch_dw<T>(a, stream);
-            set_error("upfirdn2d: per-channel filters are only implemented for same-size 5x5 / 7x7 depthwise convs of 16-byte aligned rows");
+            set_error("upfirdn2d: per-channel filters are only implemented for same-size 3x3 / 5x5 / 7x7 depthwise convs of 16-byte aligned rows");
             return VFM_ERR_NO_KERNEL;
         }
         if (a.pad_mode) {
@@ -777,4 +778,69 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
         case VFM_F32: return launch<float>(a, stream);
         default:      return launch<double>(a, stream);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// PixelShuffle(2): y[n, c, 2h + i, 2w + j] = x[n, 4c + 2i + j, h, w]  (the upsampling step of SeparableUpsampleWithFixedBlur,
+// networks/utils/convnext_utils.py:197-257).  One thread = 8 output pixels of one row: 4 + 4 inputs of the two source planes of
+// that row parity, interleaved in registers -- every access is a full 8/16-byte vector, so the copy runs at the HBM rate (the
+// generic 6-d permute copy it replaces reaches 1.3 TB/s).
+namespace vfm {
+namespace {
+
+template <class T>
+__global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t planes, int H, int W) {
+    constexpr int NB = 4 * (int)sizeof(T);                 // bytes of the 4 inputs a thread takes from each source plane
+    const int gpr = W / 4;                                 // groups of 8 output pixels per output row
+    const int64_t total = planes * (2 * H) * gpr;
+    for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(gid % gpr);
+        const int64_t r = gid / gpr;
+        const int oy = (int)(r % (2 * H));
+        const int64_t pl = r / (2 * H);                    // n * C + c
+        const T* s0 = x + ((pl * 4 + (oy & 1) * 2) * H + (oy >> 1)) * (int64_t)W + g * 4;
+        const T* s1 = s0 + (int64_t)H * W;
+        uint32_t a[NB / 4], b[NB / 4], o[NB / 2];
+        if (NB == 8) {
+            const uint2 ua = __ldg((const uint2*)s0), ub = __ldg((const uint2*)s1);
+            a[0] = ua.x; a[1] = ua.y; b[0] = ub.x; b[1] = ub.y;
+        } else {
+            ldg_words<16>(s0, a);
+            ldg_words<16>(s1, b);
+        }
+        if (sizeof(T) == 2) {
+#pragma unroll
+            for (int i = 0; i < NB / 4; i++) {
+                o[2 * i] = __byte_perm(a[i], b[i], 0x5410);          // a.lo, b.lo
+                o[2 * i + 1] = __byte_perm(a[i], b[i], 0x7632);      // a.hi, b.hi
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NB / 4; i++) { o[2 * i] = a[i]; o[2 * i + 1] = b[i]; }
+        }
+        T* d = y + (pl * (2 * H) + oy) * (int64_t)(2 * W) + g * 8;
+        if (sizeof(T) == 2) stg_words<16>(d, o);
+        else { stg_words<16>(d, o); stg_words<16>(d + 4, o + 4); }
+    }
+}
+
+}  // namespace
+}  // namespace vfm
+
+extern "C" int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p != nullptr && p->x && p->y, "pixel_shuffle2: NULL argument");
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "pixel_shuffle2: fp16 / fp32 only");
+    VFM_CHECK_ARG(p->batch >= 1 && p->out_channels >= 1 && p->in_h >= 1 && p->in_w >= 4 && p->in_w % 4 == 0, "pixel_shuffle2: in_w must be a positive multiple of 4");
+    VFM_CHECK_ARG(aligned16(p->x) && aligned16(p->y), "pixel_shuffle2: x and y must be 16-byte aligned");
+    const int64_t planes = (int64_t)p->batch * p->out_channels;
+    const int64_t total = planes * 2 * p->in_h * (p->in_w / 4);
+    const int64_t blocks = std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 32);
+    const int es = p->dtype == VFM_F16 ? 2 : 4;
+    KernelTimer timer("pixel_shuffle2", stream, 0.0, 2.0 * (double)planes * 4 * p->in_h * p->in_w * es, "c%dh%d", p->out_channels, p->in_h);
+    if (p->dtype == VFM_F16) pixel_shuffle2_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)p->x, (__half*)p->y, planes, p->in_h, p->in_w);
+    else pixel_shuffle2_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)p->x, (float*)p->y, planes, p->in_h, p->in_w);
+    return launch_status("pixel_shuffle2");
 }

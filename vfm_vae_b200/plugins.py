@@ -111,6 +111,19 @@ class _BiasActPlugin:
 
 class _Upfirdn2dPlugin:
     @staticmethod
+    def pixel_shuffle2(x):
+        """``F.pixel_shuffle(x, 2)`` (extension; contiguous fp16/fp32 NCHW, W % 4 == 0)."""
+        _check(x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.shape[1] % 4 == 0 and x.shape[3] % 4 == 0, 'pixel_shuffle2: bad input')
+        n, c4, h, w = x.shape
+        y = torch.empty([n, c4 // 4, 2 * h, 2 * w], dtype=x.dtype, device=x.device)
+        p = _lib.PixelShuffle2Params()
+        p.x, p.y, p.dtype = _ptr(x), _ptr(y), _dtype_code(x, 'pixel_shuffle2')
+        p.batch, p.out_channels, p.in_h, p.in_w = n, c4 // 4, h, w
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().vfm_pixel_shuffle2(C.byref(p), _stream(x)), 'pixel_shuffle2')
+        return y
+
+    @staticmethod
     def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, pad_mode=0, bias=None):
         """``pad_mode=1`` (extension): replicate padding; a rank-3 ``f`` [C,fh,fw] (extension) is one filter per channel = a depthwise
         conv, optionally with ``bias`` [C]; both return None where no kernel implements them."""

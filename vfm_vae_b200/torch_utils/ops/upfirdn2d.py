@@ -166,11 +166,11 @@ def blur2d_replicate(x, f, padding):
 
 
 def depthwise_conv2d(x, weight, bias=None, noise=None):
-    """Inference-only: ``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {5, 7}, fp16 / fp32 ``x`` -- the
+    """Inference-only: ``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {3, 5, 7}, fp16 / fp32 ``x`` -- the
     dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128) -- on the streaming stencil kernel with the
     channel's taps in registers.  Returns None when the kernel does not apply (the caller uses the stock module)."""
     if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
-            or weight.dim() != 4 or weight.shape[1] != 1 or weight.shape[2] != weight.shape[3] or weight.shape[2] not in (5, 7) or not x.is_contiguous()
+            or weight.dim() != 4 or weight.shape[1] != 1 or weight.shape[2] != weight.shape[3] or weight.shape[2] not in (3, 5, 7) or not x.is_contiguous()
             or (x.shape[3] * x.element_size()) % 16 != 0):
         return None
     _init()
@@ -179,3 +179,14 @@ def depthwise_conv2d(x, weight, bias=None, noise=None):
     b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
     add = noise.detach().to(torch.float32).reshape(x.shape[2], x.shape[3]).contiguous() if noise is not None else None
     return _plugin.upfirdn2d(x, f, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, add=add, bias=b)
+
+
+def pixel_shuffle2(x):
+    """Inference-only ``F.pixel_shuffle(x, 2)`` for contiguous fp16 / fp32 NCHW CUDA tensors with W % 4 == 0 (the upsampling step of
+    SeparableUpsampleWithFixedBlur, networks/utils/convnext_utils.py:197-257) as a vectorised copy at the HBM rate.  Returns None
+    when the kernel does not apply (the caller uses the stock op)."""
+    if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or x.dim() != 4 or x.shape[1] % 4 != 0 or x.shape[3] % 4 != 0
+            or not x.is_contiguous() or x.numel() == 0 or (torch.is_grad_enabled() and x.requires_grad)):
+        return None
+    _init()
+    return _plugin.pixel_shuffle2(x)

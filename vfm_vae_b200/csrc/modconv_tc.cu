@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 // 1x1 convs (MNP), whose epilogue is not hidden behind the MMAs: unrolled by two only (static register slots of the
                 // TMEM / side-input double buffers) -- fully unrolled, the ~3000 straight-line instructions per item starve the two
                 // warps per scheduler of instructions (30 % of the stall samples of the 1x1 GELU conv were no_instructions).  The
-                // k x k convs keep the full unroll (3 % faster there: compile-time addressing, deeper side-input window).
+                // k x k convs keep the full unroll (compile-time addressing, deeper side-input window; their epilogue hides behind the MMAs).
 #pragma unroll 1
                 for (int step0 = 0; step0 < NIT; step0 += UNR) {
 #pragma unroll

@@ -347,8 +347,25 @@ typedef struct {
     void*       y;
     int32_t     dtype;
     int32_t     batch, out_channels, in_h, in_w;
+    int32_t     inverse;      /* != 0: PixelUnshuffle(2) (the backward): x is the [batch, out_channels, 2 in_h, 2 in_w] tensor, y the 4-plane one */
 } vfm_pixel_shuffle2_params;
 VFM_API int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stream);
+
+/* Weight and bias gradient of the depthwise k x k conv (k = 3, 5, 7; "same" zero padding; see vfm_upfirdn2d_params::f_stride_c for
+ * the forward; the data gradient is the forward with flip = 0):
+ *   dweight[c,ty,tx] += sum_{n,y,x} dy[n,c,y,x] * x[n,c,y+ty-k/2,x+tx-k/2],   dbias[c] += sum_{n,y,x} dy[n,c,y,x]   (dbias optional)
+ * x, dy contiguous NCHW of `dtype` (fp16 / fp32), W % 8 == 0; dweight [C,k,k] and dbias [C] are fp32 and ACCUMULATED into
+ * (atomics): pass zeroed buffers.  Replaces the stock autograd of nn.Conv2d(C, C, k, groups=C) in the ConvNeXt layers
+ * (networks/utils/convnext_utils.py:99,128).  VFM_ERR_NO_KERNEL for other shapes (the caller keeps the stock op). */
+typedef struct {
+    const void* x;
+    const void* dy;
+    float*      dweight;
+    float*      dbias;
+    int32_t     dtype;
+    int32_t     batch, channels, h, w, k;
+} vfm_depthwise_wgrad_params;
+VFM_API int vfm_depthwise_wgrad(const vfm_depthwise_wgrad_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

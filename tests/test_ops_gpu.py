@@ -280,6 +280,46 @@ def test_depthwise_conv2d_k3():
         assert y is not None and rel_err(y, yr) <= tol
 
 
+@pytest.mark.parametrize('cfg', [dict(shape=(2, 6, 16, 32), k=5), dict(shape=(2, 5, 24, 64), k=7), dict(shape=(3, 4, 12, 24), k=3),
+                                 dict(shape=(1, 3, 70, 256), k=7), dict(shape=(2, 4, 8, 8), k=5)], ids=lambda c: f"k{c['k']}-{c['shape'][2]}x{c['shape'][3]}")
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_depthwise_conv2d_autograd(cfg, dtype):
+    """Gradients of the depthwise conv (data gradient = the same kernel with flipped taps, weight / bias gradient by
+    vfm_depthwise_wgrad) against stock autograd of F.conv2d in fp64."""
+    V = _ops()
+    g = torch.Generator().manual_seed(17)
+    Cc, k = cfg['shape'][1], cfg['k']
+    x0 = torch.randn(cfg['shape'], generator=g).to(dtype)
+    w0 = torch.randn(Cc, 1, k, k, generator=g) * 0.2
+    b0 = torch.randn(Cc, generator=g) * 0.3
+    dy0 = torch.randn(cfg['shape'], generator=g).to(dtype)
+    xr, wr, br = x0.double().requires_grad_(True), w0.double().requires_grad_(True), b0.double().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, br, padding=k // 2, groups=Cc)
+    gr = torch.autograd.grad(yr, [xr, wr, br], dy0.double())
+    x, w, b = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True), b0.to(DEV).requires_grad_(True)
+    y = V.upfirdn2d.depthwise_conv2d(x, w, b)
+    assert y is not None and y.requires_grad and y.dtype == dtype
+    gx, gw, gb = torch.autograd.grad(y, [x, w, b], dy0.to(DEV))
+    tol = 2e-3 if dtype == torch.float16 else 1e-5
+    assert rel_err(y, yr) <= tol
+    assert gx.dtype == dtype and gw.dtype == torch.float32 and gw.shape == w.shape
+    assert rel_err(gx, gr[0]) <= tol
+    assert rel_err(gw, gr[1]) <= tol
+    assert rel_err(gb, gr[2]) <= tol
+
+
+def test_pixel_shuffle2_autograd():
+    V = _ops()
+    g = torch.Generator().manual_seed(18)
+    for dtype in (torch.float16, torch.float32):
+        x = torch.randn(2, 8, 6, 16, generator=g).to(dtype).to(DEV).requires_grad_(True)
+        dy = torch.randn(2, 2, 12, 32, generator=g).to(dtype).to(DEV)
+        y = V.upfirdn2d.pixel_shuffle2(x)
+        assert torch.equal(y, torch.nn.functional.pixel_shuffle(x, 2))
+        (gx,) = torch.autograd.grad(y, [x], dy)
+        assert torch.equal(gx, torch.nn.functional.pixel_unshuffle(dy, 2))
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

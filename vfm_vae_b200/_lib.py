@@ -89,7 +89,12 @@ class RowsParams(C.Structure):
 
 
 class PixelShuffle2Params(C.Structure):
-    _fields_ = [('x', _vp), ('y', _vp), ('dtype', _i32), ('batch', _i32), ('out_channels', _i32), ('in_h', _i32), ('in_w', _i32)]
+    _fields_ = [('x', _vp), ('y', _vp), ('dtype', _i32), ('batch', _i32), ('out_channels', _i32), ('in_h', _i32), ('in_w', _i32), ('inverse', _i32)]
+
+
+class DepthwiseWgradParams(C.Structure):
+    _fields_ = [('x', _vp), ('dy', _vp), ('dweight', _vp), ('dbias', _vp), ('dtype', _i32), ('batch', _i32), ('channels', _i32), ('h', _i32),
+                ('w', _i32), ('k', _i32)]
 
 
 class ModconvBwdParams(C.Structure):
@@ -123,6 +128,7 @@ SYMBOLS = {
     'vfm_rows_affine': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_rows_dot': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_pixel_shuffle2': (C.c_int, [C.POINTER(PixelShuffle2Params), _vp]),
+    'vfm_depthwise_wgrad': (C.c_int, [C.POINTER(DepthwiseWgradParams), _vp]),
 }
 
 _lib = None

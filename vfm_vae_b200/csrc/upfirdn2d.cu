@@ -789,39 +789,187 @@ extern "C" int vfm_upfirdn2d(const vfm_upfirdn2d_params* p, void* stream_) {
 namespace vfm {
 namespace {
 
-template <class T>
+template <class T, bool INV>
 __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t planes, int H, int W) {
-    constexpr int NB = 4 * (int)sizeof(T);                 // bytes of the 4 inputs a thread takes from each source plane
-    const int gpr = W / 4;                                 // groups of 8 output pixels per output row
+    // INV = false: x = the 4-plane tensor [planes*4, H, W], y = the shuffled one [planes, 2H, 2W];  INV = true: the other way round
+    // (PixelUnshuffle(2) = the backward of the shuffle)
+    constexpr int NB = 4 * (int)sizeof(T);                 // bytes of the 4 elements a thread moves per source plane
+    const int gpr = W / 4;                                 // groups of 8 shuffled pixels per shuffled row
     const int64_t total = planes * (2 * H) * gpr;
     for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(gid % gpr);
         const int64_t r = gid / gpr;
         const int oy = (int)(r % (2 * H));
         const int64_t pl = r / (2 * H);                    // n * C + c
-        const T* s0 = x + ((pl * 4 + (oy & 1) * 2) * H + (oy >> 1)) * (int64_t)W + g * 4;
-        const T* s1 = s0 + (int64_t)H * W;
+        const int64_t o0 = ((pl * 4 + (oy & 1) * 2) * H + (oy >> 1)) * (int64_t)W + g * 4;      // plane 2i, then plane 2i + 1 at + H*W
+        const int64_t o1 = o0 + (int64_t)H * W;
+        const int64_t os = (pl * (2 * H) + oy) * (int64_t)(2 * W) + g * 8;
         uint32_t a[NB / 4], b[NB / 4], o[NB / 2];
-        if (NB == 8) {
-            const uint2 ua = __ldg((const uint2*)s0), ub = __ldg((const uint2*)s1);
-            a[0] = ua.x; a[1] = ua.y; b[0] = ub.x; b[1] = ub.y;
-        } else {
-            ldg_words<16>(s0, a);
-            ldg_words<16>(s1, b);
-        }
-        if (sizeof(T) == 2) {
-#pragma unroll
-            for (int i = 0; i < NB / 4; i++) {
-                o[2 * i] = __byte_perm(a[i], b[i], 0x5410);          // a.lo, b.lo
-                o[2 * i + 1] = __byte_perm(a[i], b[i], 0x7632);      // a.hi, b.hi
+        if (!INV) {
+            if (NB == 8) {
+                const uint2 ua = __ldg((const uint2*)(x + o0)), ub = __ldg((const uint2*)(x + o1));
+                a[0] = ua.x; a[1] = ua.y; b[0] = ub.x; b[1] = ub.y;
+            } else {
+                ldg_words<16>(x + o0, a);
+                ldg_words<16>(x + o1, b);
             }
+            if (sizeof(T) == 2) {
+#pragma unroll
+                for (int i = 0; i < NB / 4; i++) {
+                    o[2 * i] = __byte_perm(a[i], b[i], 0x5410);          // a.lo, b.lo
+                    o[2 * i + 1] = __byte_perm(a[i], b[i], 0x7632);      // a.hi, b.hi
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB / 4; i++) { o[2 * i] = a[i]; o[2 * i + 1] = b[i]; }
+            }
+            if (sizeof(T) == 2) stg_words<16>(y + os, o);
+            else { stg_words<16>(y + os, o); stg_words<16>(y + os + 4, o + 4); }
+        } else {
+            if (sizeof(T) == 2) ldg_words<16>(x + os, o);
+            else { ldg_words<16>(x + os, o); ldg_words<16>(x + os + 4, o + 4); }
+            if (sizeof(T) == 2) {
+#pragma unroll
+                for (int i = 0; i < NB / 4; i++) {
+                    a[i] = __byte_perm(o[2 * i], o[2 * i + 1], 0x5410);  // even pixels
+                    b[i] = __byte_perm(o[2 * i], o[2 * i + 1], 0x7632);  // odd pixels
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB / 4; i++) { a[i] = o[2 * i]; b[i] = o[2 * i + 1]; }
+            }
+            if (NB == 8) {
+                *(uint2*)(y + o0) = make_uint2(a[0], a[1]);
+                *(uint2*)(y + o1) = make_uint2(b[0], b[1]);
+            } else {
+                stg_words<16>(y + o0, a);
+                stg_words<16>(y + o1, b);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight / bias gradient of the depthwise k x k conv:  dweight[c,ty,tx] = sum_{n,y,x} dy[n,c,y,x] * x[n,c,y+ty-P,x+tx-P],
+// dbias[c] = sum dy.  A thread owns 8 columns of a strip of rows of one (n, c) plane: per row one vector of dy and one of x
+// (requested one row ahead) plus the halo columns (L1 hits: the neighbouring threads' vectors), the k most recent x rows
+// expanded in registers, k*k running sums; block reduction by shuffles + shared memory, one atomicAdd per (block, tap).
+template <class T, int K>
+__global__ void __launch_bounds__(128) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwt, float* __restrict__ db,
+                                                        int C, int H, int W, int strip_rows) {
+    constexpr int P = K / 2;
+    constexpr int EW = (int)(4 / sizeof(T));
+    constexpr int NW = 8 / EW;                              // words of 8 elements
+    const int c = blockIdx.y, n = blockIdx.z;
+    const int cg = W >> 3;                                  // column groups per row (W % 8 == 0, cg <= 128)
+    const int spb = 128 / cg;                               // strips per block
+    const int g = threadIdx.x % cg, sl = threadIdx.x / cg;
+    const int y0 = (blockIdx.x * spb + sl) * strip_rows;
+    const int y1 = min(y0 + strip_rows, H);
+    const bool active = sl < spb && y0 < H;
+    const int x0 = g * 8;
+    const T* xp = x + ((int64_t)n * C + c) * H * (int64_t)W;
+    const T* dp = dy + ((int64_t)n * C + c) * H * (int64_t)W;
+
+    float acc[K][K], accb = 0.f;
+#pragma unroll
+    for (int a = 0; a < K; a++)
+#pragma unroll
+        for (int b = 0; b < K; b++) acc[a][b] = 0.f;
+
+    struct Raw { uint32_t w[NW]; T hl[P], hr[P]; };
+    auto fetch_x = [&](int iy, Raw& r) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) r.w[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < P; i++) { r.hl[i] = from_acc<T, float>(0.f); r.hr[i] = from_acc<T, float>(0.f); }
+        if (iy >= 0 && iy < H) {
+            const T* rp = xp + (int64_t)iy * W + x0;
+            if (sizeof(T) == 2) ldg_words<16>(rp, r.w);
+            else { ldg_words<16>(rp, r.w); ldg_words<16>(rp + 4, r.w + 4); }
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                if (x0 - P + i >= 0) r.hl[i] = __ldg(rp - P + i);
+                if (x0 + 8 + i < W) r.hr[i] = __ldg(rp + 8 + i);
+            }
+        }
+    };
+    auto expand8 = [&](const uint32_t* w, float* o) {
+        if (EW == 2) {
+#pragma unroll
+            for (int i = 0; i < NW; i++) { const float2 t = __half22float2(*(const __half2*)&w[i]); o[2 * i] = t.x; o[2 * i + 1] = t.y; }
         } else {
 #pragma unroll
-            for (int i = 0; i < NB / 4; i++) { o[2 * i] = a[i]; o[2 * i + 1] = b[i]; }
+            for (int i = 0; i < NW; i++) o[i] = __uint_as_float(w[i]);
         }
-        T* d = y + (pl * (2 * H) + oy) * (int64_t)(2 * W) + g * 8;
-        if (sizeof(T) == 2) stg_words<16>(d, o);
-        else { stg_words<16>(d, o); stg_words<16>(d + 4, o + 4); }
+    };
+    auto expand_x = [&](const Raw& r, float* o) {          // o[j] = x[iy][x0 - P + j], j < 8 + 2P
+#pragma unroll
+        for (int i = 0; i < P; i++) { o[i] = to_acc(r.hl[i]); o[P + 8 + i] = to_acc(r.hr[i]); }
+        expand8(r.w, o + P);
+    };
+
+    if (active) {
+        float ring[K][8 + K - 1];
+        // rows y0 - P .. y0 + P - 1 -> slots 0 .. K-2;  row y + P goes to slot (y - y0 + K - 1) % K
+#pragma unroll
+        for (int j = 0; j < K - 1; j++) { Raw r; fetch_x(y0 - P + j, r); expand_x(r, ring[j]); }
+        Raw nx;
+        uint32_t nd[NW];
+        fetch_x(y0 + P, nx);
+        if (sizeof(T) == 2) ldg_words<16>(dp + (int64_t)y0 * W + x0, nd);
+        else { ldg_words<16>(dp + (int64_t)y0 * W + x0, nd); ldg_words<16>(dp + (int64_t)y0 * W + x0 + 4, nd + 4); }
+#pragma unroll 1
+        for (int yb = y0; yb < y1; yb += K) {
+#pragma unroll
+            for (int u = 0; u < K; u++) {
+                const int y = yb + u;
+                if (y < y1) {
+                    float d[8];
+                    expand_x(nx, ring[(u + K - 1) % K]);
+                    expand8(nd, d);
+                    if (y + 1 < y1) {                       // next row's vectors are in flight during this row's FMAs
+                        fetch_x(y + 1 + P, nx);
+                        const T* q = dp + (int64_t)(y + 1) * W + x0;
+                        if (sizeof(T) == 2) ldg_words<16>(q, nd);
+                        else { ldg_words<16>(q, nd); ldg_words<16>(q + 4, nd + 4); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) accb += d[i];
+                    // column outermost: consecutive FMAs go to K*K different sums (with i innermost each sum is a dependent chain of 8)
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int ty = 0; ty < K; ty++)
+#pragma unroll
+                            for (int tx = 0; tx < K; tx++) acc[ty][tx] = fmaf(d[i], ring[(u + ty) % K][i + tx], acc[ty][tx]);
+                }
+            }
+        }
+    }
+    // block reduction of the K*K + 1 sums
+    __shared__ float red[4][K * K + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < K; a++)
+#pragma unroll
+        for (int b = 0; b < K; b++) {
+            float v = acc[a][b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][a * K + b] = v;
+        }
+    {
+        float v = accb;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][K * K] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= K * K) {
+        const float v = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+        if (threadIdx.x < K * K) atomicAdd(&dwt[(int64_t)c * K * K + threadIdx.x], v);
+        else if (db) atomicAdd(&db[c], v);
     }
 }
 
@@ -837,10 +985,48 @@ extern "C" int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stre
     VFM_CHECK_ARG(aligned16(p->x) && aligned16(p->y), "pixel_shuffle2: x and y must be 16-byte aligned");
     const int64_t planes = (int64_t)p->batch * p->out_channels;
     const int64_t total = planes * 2 * p->in_h * (p->in_w / 4);
-    const int64_t blocks = std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 32);
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 32);
     const int es = p->dtype == VFM_F16 ? 2 : 4;
-    KernelTimer timer("pixel_shuffle2", stream, 0.0, 2.0 * (double)planes * 4 * p->in_h * p->in_w * es, "c%dh%d", p->out_channels, p->in_h);
-    if (p->dtype == VFM_F16) pixel_shuffle2_kernel<__half><<<(unsigned)blocks, 256, 0, stream>>>((const __half*)p->x, (__half*)p->y, planes, p->in_h, p->in_w);
-    else pixel_shuffle2_kernel<float><<<(unsigned)blocks, 256, 0, stream>>>((const float*)p->x, (float*)p->y, planes, p->in_h, p->in_w);
+    KernelTimer timer(p->inverse ? "pixel_unshuffle2" : "pixel_shuffle2", stream, 0.0, 2.0 * (double)planes * 4 * p->in_h * p->in_w * es, "c%dh%d", p->out_channels, p->in_h);
+    if (p->dtype == VFM_F16) {
+        if (p->inverse) pixel_shuffle2_kernel<__half, true><<<blocks, 256, 0, stream>>>((const __half*)p->x, (__half*)p->y, planes, p->in_h, p->in_w);
+        else pixel_shuffle2_kernel<__half, false><<<blocks, 256, 0, stream>>>((const __half*)p->x, (__half*)p->y, planes, p->in_h, p->in_w);
+    } else {
+        if (p->inverse) pixel_shuffle2_kernel<float, true><<<blocks, 256, 0, stream>>>((const float*)p->x, (float*)p->y, planes, p->in_h, p->in_w);
+        else pixel_shuffle2_kernel<float, false><<<blocks, 256, 0, stream>>>((const float*)p->x, (float*)p->y, planes, p->in_h, p->in_w);
+    }
     return launch_status("pixel_shuffle2");
+}
+
+namespace vfm {
+namespace {
+template <class T, int K>
+int launch_dw_wgrad(const vfm_depthwise_wgrad_params* p, cudaStream_t stream) {
+    const int cg = p->w / 8, spb = 128 / cg;
+    int strip_rows = 32;
+    while (strip_rows > 8 && (int64_t)p->batch * p->channels * ceil_div(ceil_div(p->h, strip_rows), spb) < (int64_t)kNumSMs * 8) strip_rows >>= 1;
+    const int strips = ceil_div(p->h, strip_rows);
+    dim3 grid((unsigned)ceil_div(strips, spb), (unsigned)p->channels, (unsigned)p->batch);
+    KernelTimer timer("depthwise_wgrad", stream, 0.0, 2.0 * (double)p->batch * p->channels * p->h * p->w * sizeof(T), "k%dw%dc%d", K, p->w, p->channels);
+    dw_wgrad_kernel<T, K><<<grid, 128, 0, stream>>>((const T*)p->x, (const T*)p->dy, p->dweight, p->dbias, p->channels, p->h, p->w, strip_rows);
+    return launch_status("depthwise_wgrad");
+}
+}  // namespace
+}  // namespace vfm
+
+extern "C" int vfm_depthwise_wgrad(const vfm_depthwise_wgrad_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p != nullptr && p->x && p->dy && p->dweight, "depthwise_wgrad: NULL argument");
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "depthwise_wgrad: fp16 / fp32 only");
+    VFM_CHECK_ARG(p->k == 3 || p->k == 5 || p->k == 7, "depthwise_wgrad: k must be 3, 5 or 7");
+    VFM_CHECK_ARG(p->batch >= 1 && p->batch <= 65535 && p->channels >= 1 && p->channels <= 65535 && p->h >= 1, "depthwise_wgrad: bad shape");
+    if (p->w < 8 || p->w % 8 != 0 || p->w > 1024 || !aligned16(p->x) || !aligned16(p->dy)) {
+        set_error("depthwise_wgrad: needs 16-byte aligned tensors with 8 <= W <= 1024, W %% 8 == 0"); return VFM_ERR_NO_KERNEL;
+    }
+    // dweight / dbias are accumulated with atomics: the caller passes zero-initialised buffers (or accumulates on purpose)
+    if (p->dtype == VFM_F16) {
+        switch (p->k) { case 3: return launch_dw_wgrad<__half, 3>(p, stream); case 5: return launch_dw_wgrad<__half, 5>(p, stream); default: return launch_dw_wgrad<__half, 7>(p, stream); }
+    }
+    switch (p->k) { case 3: return launch_dw_wgrad<float, 3>(p, stream); case 5: return launch_dw_wgrad<float, 5>(p, stream); default: return launch_dw_wgrad<float, 7>(p, stream); }
 }

@@ -187,34 +187,33 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
             self.pad = (pw, pw + int(kw % 2 == 0), ph, ph + int(kh % 2 == 0))
             self.register_buffer('blur_weight', k2[None, None].repeat(out_channels, 1, 1, 1))
 
-    # Inference on CUDA: the GroupNorm (stock: cast -> fp32 moments/normalise -> cast under autocast), the 3x3 depthwise conv and the
-    # PixelShuffle run on the library's kernels (statistics in fp32, each result rounded to the activation dtype exactly where the
+    # On CUDA the GroupNorm (stock: cast -> fp32 moments/normalise -> cast under autocast), the 3x3 depthwise conv and the
+    # PixelShuffle run on the library's kernels, forward and backward (statistics in fp32, each result rounded to the activation dtype exactly where the
     # reference's autocast rounds it); 4.7 ms of the 56 ms f16d32-D decode step were these three stock ops at the two largest blocks.
-    def _norm(self, x, fast):
-        if fast:
-            from .torch_utils.ops import group_norm as _gn
+    def _norm(self, x):
+        if x.is_cuda:
+            from .torch_utils.ops import group_norm as _gn          # forward and backward kernels
             if _gn.supported(x, self.norm.num_groups):
                 return _gn.group_norm32(x, self.norm.num_groups, self.norm.weight, self.norm.bias, self.norm.eps)
         return self.norm(x)
 
-    def _depthwise(self, x, fast):
-        dw = getattr(self.ops, 'depthwise_conv2d', None) if fast else None
+    def _depthwise(self, x):
+        dw = getattr(self.ops, 'depthwise_conv2d', None) if (self.ops is not None and x.is_cuda) else None
         y = dw(x, self.depthwise.weight, None) if dw is not None else None
         return y if y is not None else self.depthwise(x)
 
-    def _shuffle(self, x, fast):
-        ps = getattr(self.ops, 'pixel_shuffle2', None) if fast else None
-        y = ps(x) if (ps is not None and self.shuffle.upscale_factor == 2) else None
+    def _shuffle(self, x):
+        ps = getattr(self.ops, 'pixel_shuffle2', None) if (self.ops is not None and x.is_cuda and self.shuffle.upscale_factor == 2) else None
+        y = ps(x) if ps is not None else None
         return y if y is not None else self.shuffle(x)
 
     def forward(self, x):
-        fast = self.ops is not None and x.is_cuda and not torch.is_grad_enabled()
-        if fast and torch.is_autocast_enabled():
+        if x.is_cuda and torch.is_autocast_enabled():
             x = x.to(torch.get_autocast_dtype('cuda'))
         if self.pre_normalize:
-            x = self._shuffle(self.pointwise(self._depthwise(self._norm(x, fast), fast)), fast)
+            x = self._shuffle(self.pointwise(self._depthwise(self._norm(x))))
         else:
-            x = self._norm(self._shuffle(self.pointwise(self._depthwise(x, fast)), fast), fast)
+            x = self._norm(self._shuffle(self.pointwise(self._depthwise(x))))
         if self.use_gaussian_blur:
             fused = getattr(self.ops, 'blur2d_replicate', None) if self.ops is not None else None
             if fused is not None and not torch.is_grad_enabled():
@@ -368,11 +367,13 @@ class ConvNeXtSynthesisLayer(nn.Module):
             noise = F.interpolate(noise, size=x.shape[2:], mode='bilinear', align_corners=False)
         dw = getattr(self.ops, 'depthwise_conv2d', None)
         y = None
-        if dw is not None and not torch.is_grad_enabled() and x.is_cuda:
-            # k x k depthwise conv + bias + noise on the streaming stencil kernel (one rounding of the sum to the activation dtype)
+        infer = not torch.is_grad_enabled()
+        if dw is not None and x.is_cuda:
+            # k x k depthwise conv + bias on the streaming stencil kernel (autograd: data gradient on the same kernel + vfm_depthwise_wgrad);
+            # under no_grad the noise add is folded in (one rounding of the sum to the activation dtype)
             xin = x.to(torch.get_autocast_dtype('cuda')) if torch.is_autocast_enabled() else x
-            y = dw(xin, self.dwconv.weight, self.dwconv.bias, noise)
-        noise_done = y is not None
+            y = dw(xin, self.dwconv.weight, self.dwconv.bias, noise if infer else None)
+        noise_done = y is not None and infer
         x = y if y is not None else self.dwconv(x)
         fused = getattr(self.ops, 'fused_convnext_mlp', None)
         if fused is not None and not torch.is_grad_enabled():

@@ -111,17 +111,44 @@ class _BiasActPlugin:
 
 class _Upfirdn2dPlugin:
     @staticmethod
-    def pixel_shuffle2(x):
-        """``F.pixel_shuffle(x, 2)`` (extension; contiguous fp16/fp32 NCHW, W % 4 == 0)."""
-        _check(x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.shape[1] % 4 == 0 and x.shape[3] % 4 == 0, 'pixel_shuffle2: bad input')
-        n, c4, h, w = x.shape
-        y = torch.empty([n, c4 // 4, 2 * h, 2 * w], dtype=x.dtype, device=x.device)
+    def pixel_shuffle2(x, inverse=False):
+        """``F.pixel_shuffle(x, 2)`` / with ``inverse`` ``F.pixel_unshuffle(x, 2)`` (extension; contiguous fp16/fp32 NCHW, width of
+        the 4-plane tensor % 4 == 0)."""
+        _check(x.is_cuda and x.dim() == 4 and x.is_contiguous(), 'pixel_shuffle2: x must be a contiguous NCHW CUDA tensor')
+        if inverse:
+            n, c, h2, w2 = x.shape
+            _check(h2 % 2 == 0 and w2 % 8 == 0, 'pixel_unshuffle2: bad input shape')
+            c_out, h, w = c, h2 // 2, w2 // 2
+            y = torch.empty([n, 4 * c, h, w], dtype=x.dtype, device=x.device)
+        else:
+            n, c4, h, w = x.shape
+            _check(c4 % 4 == 0 and w % 4 == 0, 'pixel_shuffle2: bad input shape')
+            c_out = c4 // 4
+            y = torch.empty([n, c_out, 2 * h, 2 * w], dtype=x.dtype, device=x.device)
         p = _lib.PixelShuffle2Params()
         p.x, p.y, p.dtype = _ptr(x), _ptr(y), _dtype_code(x, 'pixel_shuffle2')
-        p.batch, p.out_channels, p.in_h, p.in_w = n, c4 // 4, h, w
+        p.batch, p.out_channels, p.in_h, p.in_w, p.inverse = n, c_out, h, w, int(bool(inverse))
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().vfm_pixel_shuffle2(C.byref(p), _stream(x)), 'pixel_shuffle2')
         return y
+
+    @staticmethod
+    def depthwise_wgrad(x, dy, k, want_bias=True):
+        """-> (dweight [C,k,k] fp32, dbias [C] fp32 | None) of the depthwise k x k conv (extension), or None where no kernel applies."""
+        _check(x.is_cuda and x.dim() == 4 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype,
+               'depthwise_wgrad: x and dy must be contiguous NCHW CUDA tensors of the same shape and dtype')
+        n, c, h, w = x.shape
+        dw = torch.zeros([c, k, k], dtype=torch.float32, device=x.device)
+        db = torch.zeros([c], dtype=torch.float32, device=x.device) if want_bias else None
+        p = _lib.DepthwiseWgradParams()
+        p.x, p.dy, p.dweight, p.dbias, p.dtype = _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _dtype_code(x, 'depthwise_wgrad')
+        p.batch, p.channels, p.h, p.w, p.k = n, c, h, w, int(k)
+        with torch.cuda.device(x.device):
+            st = _lib.load().vfm_depthwise_wgrad(C.byref(p), _stream(x))
+        if st == _lib.VFM_ERR_NO_KERNEL:
+            return None
+        _lib.check(st, 'depthwise_wgrad')
+        return dw, db
 
     @staticmethod
     def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, pad_mode=0, bias=None):

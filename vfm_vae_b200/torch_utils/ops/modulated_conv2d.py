@@ -166,7 +166,7 @@ def modulated_pointwise_conv2d(x, weight, style, bias=None, demodulate=True):
     plus the broadcast bias.  Runs on the tcgen05 kernel when the channel counts are multiples of 128; autograd as modulated_conv2d.
     Like the reference under autocast, the contraction runs in the autocast dtype."""
     if torch.is_autocast_enabled() and x.is_cuda:
-        x = x.to(torch.get_autocast_gpu_dtype())
+        x = x.to(torch.get_autocast_dtype('cuda'))
     y = modulated_conv2d(x, weight, style, noise=None, up=1, padding=0, demodulate=demodulate, flip_weight=True)
     if bias is not None:
         y = y + bias          # [1,O,1,1] fp32 parameter: promotes like the reference does

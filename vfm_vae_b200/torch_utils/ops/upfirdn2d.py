@@ -165,28 +165,86 @@ def blur2d_replicate(x, f, padding):
     return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, pl, pr, pt, pb, True, 1.0, pad_mode=1)
 
 
+def _dw_call(x, f, k, flip, bias=None, add=None):
+    return _plugin.upfirdn2d(x, f, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, flip, 1.0, add=add, bias=bias)
+
+
+class _DepthwiseConv2d(torch.autograd.Function):
+    """nn.Conv2d(C, C, k, padding=k//2, groups=C): forward and data gradient on the streaming stencil kernel (the data gradient is the
+    same conv with the taps flipped), weight / bias gradient by vfm_depthwise_wgrad.  First-order autograd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        k = weight.shape[2]
+        f = weight.detach().to(torch.float32).reshape(weight.shape[0], k, k).contiguous()
+        b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
+        y = _dw_call(x, f, k, True, bias=b)
+        if y is None:
+            raise RuntimeError('depthwise_conv2d: no kernel for this input (checked by the caller)')
+        ctx.save_for_backward(x, f)
+        ctx.cfg = (k, weight.shape, weight.dtype, bias.dtype if bias is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, f = ctx.saved_tensors
+        k, wshape, wdt, bdt = ctx.cfg
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _dw_call(dy, f, k, False)
+        if ctx.needs_input_grad[1] or (bdt is not None and ctx.needs_input_grad[2]):
+            out = _plugin.depthwise_wgrad(x, dy, k, bdt is not None)
+            if out is None:
+                raise RuntimeError('depthwise_conv2d: no weight-gradient kernel for this input (checked by the caller)')
+            dw = out[0].reshape(wshape).to(wdt) if ctx.needs_input_grad[1] else None
+            db = out[1].to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+class _PixelShuffle2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _plugin.pixel_shuffle2(x, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _plugin.pixel_shuffle2(dy.contiguous(), True)
+
+
 def depthwise_conv2d(x, weight, bias=None, noise=None):
-    """Inference-only: ``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {3, 5, 7}, fp16 / fp32 ``x`` -- the
-    dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128) -- on the streaming stencil kernel with the
-    channel's taps in registers.  Returns None when the kernel does not apply (the caller uses the stock module)."""
-    if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
-            or weight.dim() != 4 or weight.shape[1] != 1 or weight.shape[2] != weight.shape[3] or weight.shape[2] not in (3, 5, 7) or not x.is_contiguous()
-            or (x.shape[3] * x.element_size()) % 16 != 0):
+    """``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {3, 5, 7}, fp16 / fp32
+    contiguous NCHW CUDA ``x`` -- the dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128) and of
+    SeparableUpsampleWithFixedBlur -- on the streaming stencil kernel with the channel's taps in registers.  Under ``no_grad`` the
+    noise add is folded into the kernel; with gradients the op is an autograd function (data gradient on the same kernel, weight /
+    bias gradient by ``vfm_depthwise_wgrad``) and the noise is added by torch, as in the reference.  Returns None when the kernels do
+    not apply (the caller uses the stock module)."""
+    if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or x.dim() != 4 or weight.dim() != 4 or weight.shape[1] != 1
+            or weight.shape[0] != x.shape[1] or weight.shape[2] != weight.shape[3] or weight.shape[2] not in (3, 5, 7) or not x.is_contiguous()
+            or (x.shape[3] * x.element_size()) % 16 != 0 or x.numel() == 0):
         return None
     _init()
     k = weight.shape[2]
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad))
+    if needs_grad:
+        if x.shape[3] % 8 != 0 or x.shape[3] > 1024 or x.shape[0] > 65535 or x.shape[1] > 65535:
+            return None
+        y = _DepthwiseConv2d.apply(x, weight, bias)
+        return y if noise is None else y + noise
     f = weight.detach().to(torch.float32).reshape(weight.shape[0], k, k).contiguous()
     b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
     add = noise.detach().to(torch.float32).reshape(x.shape[2], x.shape[3]).contiguous() if noise is not None else None
-    return _plugin.upfirdn2d(x, f, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, add=add, bias=b)
+    return _dw_call(x, f, k, True, bias=b, add=add)
 
 
 def pixel_shuffle2(x):
-    """Inference-only ``F.pixel_shuffle(x, 2)`` for contiguous fp16 / fp32 NCHW CUDA tensors with W % 4 == 0 (the upsampling step of
-    SeparableUpsampleWithFixedBlur, networks/utils/convnext_utils.py:197-257) as a vectorised copy at the HBM rate.  Returns None
-    when the kernel does not apply (the caller uses the stock op)."""
+    """``F.pixel_shuffle(x, 2)`` for contiguous fp16 / fp32 NCHW CUDA tensors with W % 4 == 0 (the upsampling step of
+    SeparableUpsampleWithFixedBlur, networks/utils/convnext_utils.py:197-257) as a vectorised copy at the HBM rate; the backward is
+    the inverse permutation on the same kernel.  Returns None when the kernel does not apply (the caller uses the stock op)."""
     if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or x.dim() != 4 or x.shape[1] % 4 != 0 or x.shape[3] % 4 != 0
-            or not x.is_contiguous() or x.numel() == 0 or (torch.is_grad_enabled() and x.requires_grad)):
+            or not x.is_contiguous() or x.numel() == 0):
         return None
     _init()
+    if torch.is_grad_enabled() and x.requires_grad:
+        return _PixelShuffle2.apply(x)
     return _plugin.pixel_shuffle2(x)

@@ -856,17 +856,21 @@ __global__ void __launch_bounds__(256) pixel_shuffle2_kernel(const T* __restrict
 // expanded in registers, k*k running sums; block reduction by shuffles + shared memory, one atomicAdd per (block, tap).
 template <class T, int K>
 __global__ void __launch_bounds__(128) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dwt, float* __restrict__ db,
-                                                        int C, int H, int W, int strip_rows) {
+                                                        int N, int C, int H, int W, int strips, int strip_rows) {
     constexpr int P = K / 2;
     constexpr int EW = (int)(4 / sizeof(T));
     constexpr int NW = 8 / EW;                              // words of 8 elements
-    const int c = blockIdx.y, n = blockIdx.z;
-    const int cg = W >> 3;                                  // column groups per row (W % 8 == 0, cg <= 128)
-    const int spb = 128 / cg;                               // strips per block
-    const int g = threadIdx.x % cg, sl = threadIdx.x / cg;
-    const int y0 = (blockIdx.x * spb + sl) * strip_rows;
+    // work items of a channel = (sample, strip of rows, group of 8 columns), flattened over the blocks of the channel so that small
+    // images still fill the CTAs (the reduction below only needs all threads of a CTA to share the channel)
+    const int c = blockIdx.y;
+    const int cg = W >> 3;                                  // column groups per row (W % 8 == 0)
+    const int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const bool active = item < (int64_t)N * strips * cg;
+    const int g = (int)(item % cg);
+    const int strip = (int)((item / cg) % strips);
+    const int n = active ? (int)(item / ((int64_t)cg * strips)) : 0;
+    const int y0 = strip * strip_rows;
     const int y1 = min(y0 + strip_rows, H);
-    const bool active = sl < spb && y0 < H;
     const int x0 = g * 8;
     const T* xp = x + ((int64_t)n * C + c) * H * (int64_t)W;
     const T* dp = dy + ((int64_t)n * C + c) * H * (int64_t)W;
@@ -1002,13 +1006,15 @@ namespace vfm {
 namespace {
 template <class T, int K>
 int launch_dw_wgrad(const vfm_depthwise_wgrad_params* p, cudaStream_t stream) {
-    const int cg = p->w / 8, spb = 128 / cg;
+    const int cg = p->w / 8;
     int strip_rows = 32;
-    while (strip_rows > 8 && (int64_t)p->batch * p->channels * ceil_div(ceil_div(p->h, strip_rows), spb) < (int64_t)kNumSMs * 8) strip_rows >>= 1;
+    while (strip_rows > 8 && (int64_t)p->batch * p->channels * ceil_div(p->h, strip_rows) * cg < (int64_t)kNumSMs * 2048) strip_rows >>= 1;
     const int strips = ceil_div(p->h, strip_rows);
-    dim3 grid((unsigned)ceil_div(strips, spb), (unsigned)p->channels, (unsigned)p->batch);
+    const int64_t bx = ceil_div64((int64_t)p->batch * strips * cg, 128);
+    if (bx > 0x7fffffffLL) { set_error("depthwise_wgrad: grid too large"); return VFM_ERR_INVALID; }
+    dim3 grid((unsigned)bx, (unsigned)p->channels, 1);
     KernelTimer timer("depthwise_wgrad", stream, 0.0, 2.0 * (double)p->batch * p->channels * p->h * p->w * sizeof(T), "k%dw%dc%d", K, p->w, p->channels);
-    dw_wgrad_kernel<T, K><<<grid, 128, 0, stream>>>((const T*)p->x, (const T*)p->dy, p->dweight, p->dbias, p->channels, p->h, p->w, strip_rows);
+    dw_wgrad_kernel<T, K><<<grid, 128, 0, stream>>>((const T*)p->x, (const T*)p->dy, p->dweight, p->dbias, p->batch, p->channels, p->h, p->w, strips, strip_rows);
     return launch_status("depthwise_wgrad");
 }
 }  // namespace
@@ -1020,7 +1026,7 @@ extern "C" int vfm_depthwise_wgrad(const vfm_depthwise_wgrad_params* p, void* st
     VFM_CHECK_ARG(p != nullptr && p->x && p->dy && p->dweight, "depthwise_wgrad: NULL argument");
     VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "depthwise_wgrad: fp16 / fp32 only");
     VFM_CHECK_ARG(p->k == 3 || p->k == 5 || p->k == 7, "depthwise_wgrad: k must be 3, 5 or 7");
-    VFM_CHECK_ARG(p->batch >= 1 && p->batch <= 65535 && p->channels >= 1 && p->channels <= 65535 && p->h >= 1, "depthwise_wgrad: bad shape");
+    VFM_CHECK_ARG(p->batch >= 1 && p->channels >= 1 && p->channels <= 65535 && p->h >= 1, "depthwise_wgrad: bad shape");
     if (p->w < 8 || p->w % 8 != 0 || p->w > 1024 || !aligned16(p->x) || !aligned16(p->dy)) {
         set_error("depthwise_wgrad: needs 16-byte aligned tensors with 8 <= W <= 1024, W %% 8 == 0"); return VFM_ERR_NO_KERNEL;
     }

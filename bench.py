@@ -44,6 +44,9 @@ def parse():
     ap.add_argument('--variant', choices=['legacy', 'convnext'], default='legacy',
                     help="decoder variant: 'legacy' = use_convnext=False (the path north_star names, default), 'convnext' = the shipped YAMLs' layers")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cuda-graph', choices=['auto', 'on', 'off'], default='off',
+                    help='decode only: replay the whole step as ONE captured CUDA graph in the timed regions (the step is ~900 launches, '
+                         'partly launch-bound in the 8x8..32x32 blocks); the per-kernel table then comes from a separate eager pass')
     ap.add_argument('--no-cudnn-benchmark', action='store_true', help='leave torch.backends.cudnn.benchmark off for the glue layers')
     return ap.parse_args()
 
@@ -273,29 +276,77 @@ def run_ours(args):
         flush.zero_()
     barrier()
 
+    # ---- optional: the decode step as one CUDA graph (captured after the eager warm-up, so cuDNN autotuning is done) ----
+    use_graph = args.mode == 'decode' and args.cuda_graph in ('on', 'auto') and not os.environ.get('VFM_CUDA_PROFILER_RANGE')
+    graph = out_s = None
+    graph_launches = 0
+    if use_graph:
+        try:
+            z_s, ws_s = z.clone(), ws.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(z_s, ws_s)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out_s = step(z_s, ws_s)
+            graph_launches = _lib.launch_count() - l0
+            graph.replay()
+            torch.cuda.synchronize()
+            ref_img = step(z, ws)
+            if not torch.equal(out_s, ref_img):                 # same kernels, same inputs: the replay must reproduce the eager result
+                raise RuntimeError('graph replay differs from the eager step')
+        except Exception as e:                                    # noqa: BLE001
+            if args.cuda_graph == 'on':
+                raise
+            print(f'[bench] CUDA graph capture unavailable ({e}); timing the eager step', file=sys.stderr)
+            graph = None
+    barrier()
+
     # ---- device-timed region: inputs resident in HBM ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.vfm_timing_enable(1)
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     prof_range = bool(os.environ.get('VFM_CUDA_PROFILER_RANGE'))     # ncu --profile-from-start off: capture the timed region only
-    if prof_range:
-        torch.cuda.profiler.start()
-    e0.record()
-    for _ in range(args.steps):
-        step(z, ws)
-        flush.zero_()          # L2 flush between iterations (256 MiB write, ~0.05 ms)
-    e1.record()
-    barrier()
-    if prof_range:
-        torch.cuda.profiler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
-    lib.vfm_timing_enable(0)
-    stats = timing_report()
+    if graph is not None:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            graph.replay()
+            flush.zero_()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = graph_launches * args.steps
+        # per-kernel durations (roofline, kernel table): the same kernels in an eager pass with per-launch events, outside `value`
+        lib.vfm_timing_enable(1)
+        for _ in range(args.steps):
+            step(z, ws)
+            flush.zero_()
+        barrier()
+        lib.vfm_timing_enable(0)
+        stats = timing_report()
+    else:
+        lib.vfm_timing_enable(1)
+        launches0 = _lib.launch_count()
+        barrier()
+        if prof_range:
+            torch.cuda.profiler.start()
+        e0.record()
+        for _ in range(args.steps):
+            step(z, ws)
+            flush.zero_()          # L2 flush between iterations (256 MiB write, ~0.05 ms)
+        e1.record()
+        barrier()
+        if prof_range:
+            torch.cuda.profiler.stop()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        lib.vfm_timing_enable(0)
+        stats = timing_report()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -307,10 +358,16 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        zd = z_h.to(dev, non_blocking=True)
-        wd = ws_h.to(dev, non_blocking=True)
-        img = step(zd, wd)
-        out_h.copy_(img.detach(), non_blocking=True)
+        if graph is not None:
+            z_s.copy_(z_h, non_blocking=True)
+            ws_s.copy_(ws_h, non_blocking=True)
+            graph.replay()
+            out_h.copy_(out_s, non_blocking=True)
+        else:
+            zd = z_h.to(dev, non_blocking=True)
+            wd = ws_h.to(dev, non_blocking=True)
+            img = step(zd, wd)
+            out_h.copy_(img.detach(), non_blocking=True)
         flush.zero_()
     e1.record()
     barrier()
@@ -371,7 +428,9 @@ def run_ours(args):
             'dtype': 'f16' if args.fp16_res > 0 else 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(args), 'global_batch': args.batch * world, 'parallelism': f'batch-sharded x{world}' + (' (replicas, no collective)' if args.mode == 'decode' else ' + gradient all-mean (NCCL)'),
                        'l2': 'explicit 256 MiB flush write between timed iterations; per-step activations (GBs) exceed the 126 MB L2 anyway',
-                       'decoder_variant': 'D-legacy (use_convnext=False)' if args.variant == 'legacy' else 'D-convnext (use_convnext=True)', 'cudnn_benchmark': bool(torch.backends.cudnn.benchmark)},
+                       'decoder_variant': 'D-legacy (use_convnext=False)' if args.variant == 'legacy' else 'D-convnext (use_convnext=True)', 'cudnn_benchmark': bool(torch.backends.cudnn.benchmark),
+                       'timed_region': ('one CUDA graph replay per step (captured eager step, bit-identical output checked); kernel table / roofline from a '
+                                        'separate eager pass with per-launch events') if graph is not None else 'eager step, per-launch events inside the timed region'},
             'e2e': {'value': total_imgs / (ms_e2e * 1e-3), 'unit': 'images/s',
                     'h2d_bytes_per_step': (z_h.numel() + ws_h.numel()) * 4, 'd2h_bytes_per_step': out_h.numel() * 4},
             'gpu_launches': int(launches),

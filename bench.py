@@ -408,18 +408,20 @@ def run_ours(args):
             sel = [v for k, v in tr.items() if key and key in k]
             n = sum(v['launches'] for v in sel)
             return sum(v['launches'] * v['dram_bytes_per_launch'] for v in sel) / n if n else None
+        # the committed ncu capture is of the default workload (legacy decoder, decode, 256x256, batch 64): other runs report null
+        traffic_applies = args.mode == 'decode' and args.variant == 'legacy' and args.res == 256 and args.batch == 64 and args.fp16_res == 3
         if stats:
             top = stats[0]
             if top['flops'] > 0:
                 ach = top['flops'] / (top['total_ms'] * 1e-3) / 1e12
                 roofline = {'kernel': top['name'], 'bound': 'tensor', 'achieved': ach, 'peak': tc_peak, 'unit': 'TFLOP/s', 'frac': ach / tc_peak,
-                            'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
+                            'traffic': ncu_traffic(top['name']) if traffic_applies else None,
                             'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01c_ncu_full_decode.md)',
                             'algorithmic_per_launch': top['flops'] / max(top['launches'], 1), 'peak_source': tc_src, 'share_of_step': top['total_ms'] / ms}
             else:
                 ach = top['bytes'] / (top['total_ms'] * 1e-3) / 1e9
                 roofline = {'kernel': top['name'], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                            'traffic': ncu_traffic(top['name']) if args.mode == 'decode' else None,
+                            'traffic': ncu_traffic(top['name']) if traffic_applies else None,
                             'traffic_unit': 'bytes/launch (dram read+write, ncu --set full, profiles/r01c_ncu_full_decode.md)',
                             'algorithmic_per_launch': top['bytes'] / max(top['launches'], 1), 'peak_source': hbm_src, 'share_of_step': top['total_ms'] / ms}
         line = {

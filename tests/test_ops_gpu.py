@@ -295,12 +295,17 @@ def test_depthwise_conv2d_autograd(cfg, dtype):
     dy0 = torch.randn(cfg['shape'], generator=g).to(dtype)
     xr, wr, br = x0.double().requires_grad_(True), w0.double().requires_grad_(True), b0.double().requires_grad_(True)
     yr = torch.nn.functional.conv2d(xr, wr, br, padding=k // 2, groups=Cc)
-    gr = torch.autograd.grad(yr, [xr, wr, br], dy0.double())
     x, w, b = x0.to(DEV).requires_grad_(True), w0.to(DEV).requires_grad_(True), b0.to(DEV).requires_grad_(True)
-    y = V.upfirdn2d.depthwise_conv2d(x, w, b)
-    assert y is not None and y.requires_grad and y.dtype == dtype
-    gx, gw, gb = torch.autograd.grad(y, [x, w, b], dy0.to(DEV))
     tol = 2e-3 if dtype == torch.float16 else 1e-5
+    nz0 = torch.randn(1, 1, *cfg['shape'][2:], generator=g)
+    nzr = nz0.double().requires_grad_(True)
+    yr = yr + nzr
+    gr = torch.autograd.grad(yr, [xr, wr, br, nzr], dy0.double())
+    nz = nz0.to(DEV).requires_grad_(True)
+    y = V.upfirdn2d.depthwise_conv2d(x, w, b, nz)
+    assert y is not None and y.requires_grad and y.dtype == dtype
+    gx, gw, gb, gn = torch.autograd.grad(y, [x, w, b, nz], dy0.to(DEV))
+    assert gn.shape == nz.shape and rel_err(gn, gr[3]) <= tol
     assert rel_err(y, yr) <= tol
     assert gx.dtype == dtype and gw.dtype == torch.float32 and gw.shape == w.shape
     assert rel_err(gx, gr[0]) <= tol

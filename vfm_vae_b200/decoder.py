@@ -367,13 +367,13 @@ class ConvNeXtSynthesisLayer(nn.Module):
             noise = F.interpolate(noise, size=x.shape[2:], mode='bilinear', align_corners=False)
         dw = getattr(self.ops, 'depthwise_conv2d', None)
         y = None
-        infer = not torch.is_grad_enabled()
         if dw is not None and x.is_cuda:
-            # k x k depthwise conv + bias on the streaming stencil kernel (autograd: data gradient on the same kernel + vfm_depthwise_wgrad);
-            # under no_grad the noise add is folded in (one rounding of the sum to the activation dtype)
+            # k x k depthwise conv + bias + noise on the streaming stencil kernel, one rounding of the sum to the activation dtype (the
+            # reference promotes `dwconv(x) + noise` to fp32 and feeds GroupNorm32 / the autocast cast with it: same statistics up to
+            # that rounding, a third of the bytes); autograd: data gradient on the same kernel + vfm_depthwise_wgrad
             xin = x.to(torch.get_autocast_dtype('cuda')) if torch.is_autocast_enabled() else x
-            y = dw(xin, self.dwconv.weight, self.dwconv.bias, noise if infer else None)
-        noise_done = y is not None and infer
+            y = dw(xin, self.dwconv.weight, self.dwconv.bias, noise)
+        noise_done = y is not None
         x = y if y is not None else self.dwconv(x)
         fused = getattr(self.ops, 'fused_convnext_mlp', None)
         if fused is not None and not torch.is_grad_enabled():

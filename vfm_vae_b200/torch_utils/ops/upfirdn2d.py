@@ -174,23 +174,25 @@ class _DepthwiseConv2d(torch.autograd.Function):
     same conv with the taps flipped), weight / bias gradient by vfm_depthwise_wgrad.  First-order autograd."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, noise):
         k = weight.shape[2]
         f = weight.detach().to(torch.float32).reshape(weight.shape[0], k, k).contiguous()
         b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
-        y = _dw_call(x, f, k, True, bias=b)
+        add = noise.detach().to(torch.float32).reshape(x.shape[2], x.shape[3]).contiguous() if noise is not None else None
+        y = _dw_call(x, f, k, True, bias=b, add=add)
         if y is None:
             raise RuntimeError('depthwise_conv2d: no kernel for this input (checked by the caller)')
         ctx.save_for_backward(x, f)
-        ctx.cfg = (k, weight.shape, weight.dtype, bias.dtype if bias is not None else None)
+        ctx.cfg = (k, weight.shape, weight.dtype, bias.dtype if bias is not None else None,
+                   (noise.shape, noise.dtype) if noise is not None else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, f = ctx.saved_tensors
-        k, wshape, wdt, bdt = ctx.cfg
+        k, wshape, wdt, bdt, nz = ctx.cfg
         dy = dy.contiguous()
-        dx = dw = db = None
+        dx = dw = db = dn = None
         if ctx.needs_input_grad[0]:
             dx = _dw_call(dy, f, k, False)
         if ctx.needs_input_grad[1] or (bdt is not None and ctx.needs_input_grad[2]):
@@ -199,7 +201,9 @@ class _DepthwiseConv2d(torch.autograd.Function):
                 raise RuntimeError('depthwise_conv2d: no weight-gradient kernel for this input (checked by the caller)')
             dw = out[0].reshape(wshape).to(wdt) if ctx.needs_input_grad[1] else None
             db = out[1].to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
-        return dx, dw, db
+        if nz is not None and ctx.needs_input_grad[3]:
+            dn = dy.sum(dim=(0, 1), dtype=torch.float32).reshape(nz[0]).to(nz[1])       # the addend is broadcast over samples and channels
+        return dx, dw, db, dn
 
 
 class _PixelShuffle2(torch.autograd.Function):
@@ -215,9 +219,10 @@ class _PixelShuffle2(torch.autograd.Function):
 def depthwise_conv2d(x, weight, bias=None, noise=None):
     """``F.conv2d(x, weight, bias, padding=k // 2, groups=C) (+ noise [1,1,H,W])`` for ``weight`` [C,1,k,k], k in {3, 5, 7}, fp16 / fp32
     contiguous NCHW CUDA ``x`` -- the dwconv of the ConvNeXt synthesis layers (networks/utils/convnext_utils.py:99,128) and of
-    SeparableUpsampleWithFixedBlur -- on the streaming stencil kernel with the channel's taps in registers.  Under ``no_grad`` the
-    noise add is folded into the kernel; with gradients the op is an autograd function (data gradient on the same kernel, weight /
-    bias gradient by ``vfm_depthwise_wgrad``) and the noise is added by torch, as in the reference.  Returns None when the kernels do
+    SeparableUpsampleWithFixedBlur -- on the streaming stencil kernel with the channel's taps in registers.  The noise add is
+    folded into the kernel (one rounding of conv + bias + noise to ``x.dtype``; the reference rounds the conv output to fp16 under
+    autocast and then adds the fp32 noise); with gradients the op is an autograd function (data gradient on the same kernel, weight /
+    bias gradient by ``vfm_depthwise_wgrad``, noise gradient = the sum of dy over samples and channels).  Returns None when the kernels do
     not apply (the caller uses the stock module)."""
     if (x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or x.dim() != 4 or weight.dim() != 4 or weight.shape[1] != 1
             or weight.shape[0] != x.shape[1] or weight.shape[2] != weight.shape[3] or weight.shape[2] not in (3, 5, 7) or not x.is_contiguous()
@@ -225,12 +230,12 @@ def depthwise_conv2d(x, weight, bias=None, noise=None):
         return None
     _init()
     k = weight.shape[2]
-    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad))
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
+                                              or (noise is not None and noise.requires_grad))
     if needs_grad:
         if x.shape[3] % 8 != 0 or x.shape[3] > 1024 or x.shape[0] > 65535 or x.shape[1] > 65535:
             return None
-        y = _DepthwiseConv2d.apply(x, weight, bias)
-        return y if noise is None else y + noise
+        return _DepthwiseConv2d.apply(x, weight, bias, noise)
     f = weight.detach().to(torch.float32).reshape(weight.shape[0], k, k).contiguous()
     b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
     add = noise.detach().to(torch.float32).reshape(x.shape[2], x.shape[3]).contiguous() if noise is not None else None

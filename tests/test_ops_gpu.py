@@ -325,6 +325,29 @@ def test_pixel_shuffle2_autograd():
         assert torch.equal(gx, torch.nn.functional.pixel_unshuffle(dy, 2))
 
 
+@pytest.mark.parametrize('k', [3, 5])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_blur2d_replicate_autograd(k, dtype):
+    """Backward of replicate-pad + fixed blur (SeparableUpsampleWithFixedBlur, convnext_utils.py:250-255): one zero-padded stencil pass
+    over dy + the pad rows / columns folded onto the edges, against stock autograd in fp64 (random, non-symmetric taps)."""
+    V = _ops()
+    g = torch.Generator().manual_seed(19)
+    p = k // 2
+    for shape in ((2, 3, 16, 24), (1, 2, 40, 64), (2, 2, 8, 8)):
+        f = torch.randn(k, k, generator=g) * 0.3
+        x0 = torch.randn(shape, generator=g).to(dtype)
+        dy0 = torch.randn(shape, generator=g).to(dtype)
+        xr = x0.double().requires_grad_(True)
+        yr = torch.nn.functional.conv2d(torch.nn.functional.pad(xr, (p, p, p, p), mode='replicate'), f.double()[None, None].repeat(shape[1], 1, 1, 1), groups=shape[1])
+        (gr,) = torch.autograd.grad(yr, [xr], dy0.double())
+        x = x0.to(DEV).requires_grad_(True)
+        y = V.upfirdn2d.blur2d_replicate(x, f.to(DEV), (p, p, p, p))
+        assert y is not None and y.requires_grad
+        (gx,) = torch.autograd.grad(y, [x], dy0.to(DEV))
+        tol = 2e-3 if dtype == torch.float16 else 1e-5
+        assert rel_err(y, yr) <= tol and rel_err(gx, gr) <= tol
+
+
 def test_upfirdn2d_errors():
     V = _ops()
     x = torch.randn(1, 1, 4, 4, device=DEV)

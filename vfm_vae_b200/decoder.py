@@ -216,8 +216,8 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
             x = self._norm(self._shuffle(self.pointwise(self._depthwise(x))))
         if self.use_gaussian_blur:
             fused = getattr(self.ops, 'blur2d_replicate', None) if self.ops is not None else None
-            if fused is not None and not torch.is_grad_enabled():
-                y = fused(x, self.blur_weight[0, 0], self.pad)       # replicate pad + fixed blur in one pass
+            if fused is not None and x.is_cuda:
+                y = fused(x, self.blur_weight[0, 0], self.pad)       # replicate pad + fixed blur in one pass (forward and backward)
                 if y is not None:
                     return y
             x = F.conv2d(F.pad(x, self.pad, mode='replicate'), self.blur_weight.to(x.dtype) if not torch.is_autocast_enabled() else self.blur_weight,

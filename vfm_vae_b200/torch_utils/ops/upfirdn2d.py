@@ -149,19 +149,71 @@ def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl='cuda'
     return upfirdn2d(x, f, down=down, padding=p, flip_filter=flip_filter, gain=gain, impl=impl)
 
 
+def replicate_blur_adjoint(dy, fw, core):
+    """Gradient w.r.t. x of ``y = F.conv2d(F.pad(x, (p,p,p,p), mode='replicate'), fw, groups=C)`` (fw [C,1,k,k], k odd, p = k//2).
+
+    With Z = the adjoint of the valid correlation on the padded domain (size (H+2p) x (W+2p)), dx is Z's interior plus Z's p pad rows /
+    columns folded back onto the edge row / column they replicate.  ``core`` = Z[p:H+p, p:W+p] (the data gradient of the zero-padded
+    "same" conv: one pass of the stencil kernel on the GPU) is supplied by the caller and updated in place; the four border strips of Z
+    only depend on the outermost p rows / columns of dy and are computed here from those thin slices (fp32, a few MB)."""
+    import torch.nn.functional as F
+    c, k = dy.shape[1], fw.shape[-1]
+    p = k // 2
+    h, w = dy.shape[2:]
+    w32 = fw.to(torch.float32)
+    ct = lambda a: F.conv_transpose2d(a.to(torch.float32), w32, groups=c)       # noqa: E731  exact adjoint of the valid correlation
+    dx = core
+    top, bot = ct(dy[:, :, :p, :]), ct(dy[:, :, h - p:, :])                        # rows [0,p) resp. the last p rows of Z, all W+2p columns
+    dx[:, :, 0, :] += top[:, :, :p, p:w + p].sum(2).to(dx.dtype)
+    dx[:, :, h - 1, :] += bot[:, :, -p:, p:w + p].sum(2).to(dx.dtype)
+    for strip, col, sl in ((ct(dy[:, :, :, :p]), 0, slice(0, p)), (ct(dy[:, :, :, w - p:]), w - 1, slice(-p, None))):
+        cols = strip[:, :, p:h + p, sl].clone()                                    # Z[:, pad columns] with its own pad rows folded first
+        cols[:, :, 0] += strip[:, :, :p, sl].sum(2)
+        cols[:, :, h - 1] += strip[:, :, h + p:, sl].sum(2)
+        dx[:, :, :, col] += cols.sum(3).to(dx.dtype)
+    return dx
+
+
+class _ReplicateBlur(torch.autograd.Function):
+    """replicate-pad + fixed depthwise blur (k = 3, 5) as one pass of the streaming kernel; backward = one pass of the zero-padded
+    stencil kernel over dy + the edge folding of ``replicate_blur_adjoint``."""
+
+    @staticmethod
+    def forward(ctx, x, f32):
+        k = f32.shape[0]
+        ctx.f = f32
+        return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, pad_mode=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        f32 = ctx.f
+        k, c = f32.shape[0], dy.shape[1]
+        dy = dy.contiguous()
+        fc = f32[None].repeat(c, 1, 1)
+        core = _dw_call(dy, fc, k, False)
+        return replicate_blur_adjoint(dy, fc[:, None], core), None
+
+
 def blur2d_replicate(x, f, padding):
-    """Inference-only: ``F.conv2d(F.pad(x, padding, mode='replicate'), f[None, None].repeat(C, 1, 1, 1), groups=C)`` for a fixed
-    2-D kernel ``f`` (<= 5x5) whose padding keeps the size -- the blur behind the pixel-shuffle upsampler
-    (networks/utils/convnext_utils.py:250-255) -- as one pass of the streaming blur kernel with clamp-to-edge addressing.
-    ``padding`` = (left, right, top, bottom) as for ``F.pad``.  Returns None when the kernel does not apply (caller composes)."""
-    if x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32) or (torch.is_grad_enabled() and x.requires_grad):
+    """``F.conv2d(F.pad(x, padding, mode='replicate'), f[None, None].repeat(C, 1, 1, 1), groups=C)`` for a fixed 2-D kernel ``f``
+    (<= 5x5) whose padding keeps the size -- the blur behind the pixel-shuffle upsampler (networks/utils/convnext_utils.py:250-255) --
+    as one pass of the streaming blur kernel with clamp-to-edge addressing.  ``padding`` = (left, right, top, bottom) as for ``F.pad``.
+    With gradients (odd square kernels, k = 3, 5) it is an autograd function whose backward is one pass of the zero-padded stencil
+    kernel over dy plus the folding of the pad rows / columns onto the edges.  Returns None when the kernels do not apply (caller
+    composes the stock ops)."""
+    if x.device.type != 'cuda' or x.dtype not in (torch.float16, torch.float32):
         return None
     pl, pr, pt, pb = [int(v) for v in padding]
     fh, fw = f.shape
     if pl + pr != fw - 1 or pt + pb != fh - 1 or pl != pt or not x.is_contiguous():
         return None
     _init()
-    f32 = f.to(device=x.device, dtype=torch.float32).contiguous()
+    f32 = f.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    if torch.is_grad_enabled() and x.requires_grad:
+        if (fh != fw or fh not in (3, 5) or pl != pr or pt != pb or x.dim() != 4 or min(x.shape[2:]) < fh
+                or (x.shape[3] * x.element_size()) % 16 != 0 or x.shape[3] % 8 != 0):
+            return None
+        return _ReplicateBlur.apply(x, f32)
     return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, pl, pr, pt, pb, True, 1.0, pad_mode=1)
 
 

@@ -1,0 +1,31 @@
+"""Host-side logic of the replicate-pad blur backward (no GPU): the edge folding of ``replicate_blur_adjoint`` against stock
+autograd of ``F.conv2d(F.pad(x, mode='replicate'), f, groups=C)`` (networks/utils/convnext_utils.py:250-255) in fp64, with the
+interior ("core") supplied by ``conv_transpose2d`` in place of the CUDA stencil pass."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from vfm_vae_b200.torch_utils.ops.upfirdn2d import replicate_blur_adjoint
+
+
+@pytest.mark.parametrize('k', [3, 5])
+@pytest.mark.parametrize('shape', [(2, 3, 9, 12), (1, 2, 5, 5), (2, 1, 16, 8), (1, 4, 7, 33)], ids=lambda s: 'x'.join(map(str, s)))
+@pytest.mark.parametrize('symmetric', [True, False], ids=['binomial', 'random'])
+def test_replicate_blur_adjoint_matches_autograd(k, shape, symmetric):
+    g = torch.Generator().manual_seed(7)
+    n, c, h, w = shape
+    p = k // 2
+    if symmetric:
+        t = torch.tensor({3: [1, 2, 1], 5: [1, 4, 6, 4, 1]}[k], dtype=torch.float64)
+        f = torch.outer(t, t) / t.sum() ** 2
+    else:
+        f = torch.randn(k, k, generator=g, dtype=torch.float64)
+    fw = f[None, None].repeat(c, 1, 1, 1)
+    x = torch.randn(shape, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(F.pad(x, (p, p, p, p), mode='replicate'), fw, groups=c)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (want,) = torch.autograd.grad(y, [x], dy)
+    core = F.conv_transpose2d(dy, fw, groups=c)[:, :, p:h + p, p:w + p].clone()      # what the zero-padded stencil pass over dy computes
+    got = replicate_blur_adjoint(dy, fw, core)
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 5e-6 * max(1.0, want.abs().max().item())     # the border strips are evaluated in fp32

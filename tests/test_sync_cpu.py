@@ -36,7 +36,8 @@ def _worker(rank, world, port, q):
     if rank == 1:
         params[1].grad[0] = float('inf')
     sync.sync_grads(params, gain=1.0)
-    q.put((rank, [p.grad.clone() for p in params], [p.data.clone() for p in params]))
+    # by value (numpy): a tensor in an mp.Queue travels as a shared-memory fd that dies with this process if the parent is slow to fetch it
+    q.put((rank, [p.grad.numpy().copy() for p in params], [p.data.numpy().copy() for p in params]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,7 +52,7 @@ def test_sync_grads_two_ranks():
     out = dict()
     for _ in range(2):
         rank, grads, params = q.get(timeout=120)
-        out[rank] = (grads, params)
+        out[rank] = ([torch.from_numpy(a) for a in grads], [torch.from_numpy(a) for a in params])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

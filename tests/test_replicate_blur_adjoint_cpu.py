@@ -29,3 +29,13 @@ def test_replicate_blur_adjoint_matches_autograd(k, shape, symmetric):
     got = replicate_blur_adjoint(dy, fw, core)
     assert got.shape == want.shape
     assert (got - want).abs().max().item() <= 5e-6 * max(1.0, want.abs().max().item())     # the border strips are evaluated in fp32
+
+
+def test_extension_ops_decline_cpu_tensors():
+    """The inference / training extensions of the upsampler and ConvNeXt layers only apply to CUDA tensors: on CPU they return None
+    (the decoder mirror then runs the stock module, which is what the CPU oracle runs use) -- they never compute on the CPU."""
+    from vfm_vae_b200.torch_utils.ops import upfirdn2d as U
+    x = torch.randn(1, 4, 8, 8)
+    assert U.depthwise_conv2d(x, torch.randn(4, 1, 3, 3), None) is None
+    assert U.pixel_shuffle2(x) is None
+    assert U.blur2d_replicate(x, torch.ones(3, 3) / 9, (1, 1, 1, 1)) is None

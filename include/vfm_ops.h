@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 4
+#define VFM_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -366,6 +366,22 @@ typedef struct {
     int32_t     batch, channels, h, w, k;
 } vfm_depthwise_wgrad_params;
 VFM_API int vfm_depthwise_wgrad(const vfm_depthwise_wgrad_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Gradient exchange, the post-all-reduce pass of the reference's sync_grads (training/training_loop.py:281-289) over the
+ * flat fp32 gradient buffer, in place and in ONE pass:
+ *     g = g / world_size;   if (use_gain) g = g * gain;   g = nan_to_num(g, nan, posinf, neginf)     (reference: 0, 1e5, -1e5)
+ * `grads` must be 16-byte aligned.  The all-reduce itself is torch.distributed / NCCL plumbing (vfm_vae_b200/sync.py).
+ */
+typedef struct {
+    float*   grads;       /* [numel] fp32, in place */
+    int64_t  numel;
+    int32_t  world_size;  /* >= 1 */
+    int32_t  use_gain;    /* 0 = the reference's `gain is None` */
+    double   gain;
+    double   nan, posinf, neginf;
+} vfm_grad_finalize_params;
+VFM_API int vfm_grad_finalize(const vfm_grad_finalize_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

@@ -97,6 +97,11 @@ class DepthwiseWgradParams(C.Structure):
                 ('w', _i32), ('k', _i32)]
 
 
+class GradFinalizeParams(C.Structure):
+    _fields_ = [('grads', _vp), ('numel', _i64), ('world_size', _i32), ('use_gain', _i32), ('gain', _f64), ('nan', _f64), ('posinf', _f64),
+                ('neginf', _f64)]
+
+
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
@@ -129,6 +134,7 @@ SYMBOLS = {
     'vfm_rows_dot': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_pixel_shuffle2': (C.c_int, [C.POINTER(PixelShuffle2Params), _vp]),
     'vfm_depthwise_wgrad': (C.c_int, [C.POINTER(DepthwiseWgradParams), _vp]),
+    'vfm_grad_finalize': (C.c_int, [C.POINTER(GradFinalizeParams), _vp]),
 }
 
 _lib = None
@@ -149,8 +155,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 4:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 4)')
+    if lib.vfm_abi_version() != 5:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 5)')
     _lib = lib
     return lib
 

@@ -68,20 +68,22 @@ __global__ void __launch_bounds__(512) gn_affine_kernel(const T* __restrict__ x,
     }
 }
 
-// out[row, :] = a[row, :] * P[row] (+ b[row, :] * Q[row]) + R[row]   -- one (n, c) plane per blockIdx.y, 16-byte vectors, 4 in flight.
+// out[row, :] = a[row, :] * P[row] (+ b[row, :] * Q[row]) + R[row]   -- one (n, c) plane per run of blocks_per_row CTAs, 16-byte vectors, 4 in flight.
 // Forward apply: NIN = 1 (x, scale, shift).  Backward: NIN = 2 (dy, x) with the coefficients of gn_bwd_reduce_kernel.
 template <class T, int NIN>
 __global__ void __launch_bounds__(256) rows_affine_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ P, const float* __restrict__ Q,
-                                                          const float* __restrict__ R, T* __restrict__ out, int64_t HW, int vec_per_block) {
+                                                          const float* __restrict__ R, T* __restrict__ out, int64_t HW, int vec_per_block, int blocks_per_row) {
     constexpr int V = 16 / (int)sizeof(T);
-    const int64_t row = blockIdx.y;
+    // 1-D grid (rows * blocks_per_row <= 2^31 - 1): gridDim.y would cap N*C at 65535
+    const int64_t row = blockIdx.x / (unsigned)blocks_per_row;
+    const int chunk = (int)(blockIdx.x - (unsigned)row * (unsigned)blocks_per_row);
     const float pp = P[row], qq = (NIN == 2) ? Q[row] : 0.f, rr = R[row];
     const T* ap = a + row * HW;
     const T* bp = (NIN == 2) ? b + row * HW : nullptr;
     T* op = out + row * HW;
     if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | (NIN == 2 ? reinterpret_cast<uintptr_t>(b) : 0)) & 15u) == 0) {
         const int64_t nvec = HW / V;
-        const int64_t v_begin = (int64_t)blockIdx.x * vec_per_block, v_end = (v_begin + vec_per_block < nvec) ? v_begin + vec_per_block : nvec;
+        const int64_t v_begin = (int64_t)chunk * vec_per_block, v_end = (v_begin + vec_per_block < nvec) ? v_begin + vec_per_block : nvec;
         for (int64_t v0 = v_begin + threadIdx.x; v0 < v_end; v0 += (int64_t)blockDim.x * 4) {
             uint4 ua[4], ub[4];
 #pragma unroll
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(256) rows_affine_kernel(const T* __restrict__ 
             }
         }
     } else {
-        const int64_t e_begin = (int64_t)blockIdx.x * vec_per_block * V;
+        const int64_t e_begin = (int64_t)chunk * vec_per_block * V;
         const int64_t e_end = (e_begin + (int64_t)vec_per_block * V < HW) ? e_begin + (int64_t)vec_per_block * V : HW;
         for (int64_t i = e_begin + threadIdx.x; i < e_end; i += blockDim.x) {
             float r = fmaf(to_acc(ap[i]), pp, rr);
@@ -190,10 +192,10 @@ int launch_rows_affine(const void* a, const void* b, const float* P, const float
     int64_t vpb = nvec;
     while (vpb > 256 * 8 && rows * ((nvec + vpb - 1) / vpb) < (int64_t)kNumSMs * 16) vpb = (vpb + 1) / 2;
     if (vpb > 256 * 16) vpb = 256 * 16;
-    if (rows > 0x7fffffffLL) { set_error("group_norm: too many rows"); return VFM_ERR_INVALID; }
-    dim3 grid((unsigned)((nvec + vpb - 1) / vpb), (unsigned)rows);
+    const int64_t nblk = (nvec + vpb - 1) / vpb;
+    if (rows * nblk > 0x7fffffffLL) { set_error("%s: too many rows (%lld x %lld blocks)", name, (long long)rows, (long long)nblk); return VFM_ERR_INVALID; }
     KernelTimer timer(name, stream, 0.0, (double)rows * HW * sizeof(T) * (NIN + 1));
-    rows_affine_kernel<T, NIN><<<grid, 256, 0, stream>>>((const T*)a, (const T*)b, P, Q, R, (T*)out, HW, (int)vpb);
+    rows_affine_kernel<T, NIN><<<(unsigned)(rows * nblk), 256, 0, stream>>>((const T*)a, (const T*)b, P, Q, R, (T*)out, HW, (int)vpb, (int)nblk);
     return launch_status("rows_affine_kernel");
 }
 

@@ -51,6 +51,13 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
 
 _bias_act_cuda_cache = dict()
 
+#: Gradient of a clamped *linear* bias_act (ToRGB with conv_clamp) where |y| >= clamp.  The reference disagrees with itself here:
+#: its impl='ref' path (``x.clamp``, bias_act.py:118-119) zeroes it, its CUDA path keeps y only for activations whose derivative is
+#: written in terms of y (bias_act.py:151-154) and therefore lets it through.  'ref' (default) follows impl='ref' -- the path
+#: north_star defines parity against and the golden vectors pin; 'cuda' reproduces the reference's CUDA training behaviour, which is
+#: also what the reference's own wrapper does when it runs on these kernels through integration.install().
+linear_clamp_grad = 'ref'
+
 
 def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     assert clamp is None or clamp >= 0
@@ -58,16 +65,15 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
     alpha = float(alpha if alpha is not None else spec.def_alpha)
     gain = float(gain if gain is not None else spec.def_gain)
     clamp = float(clamp if clamp is not None else -1)
-    key = (dim, act, alpha, gain, clamp)
+    assert linear_clamp_grad in ('ref', 'cuda')
+    key = (dim, act, alpha, gain, clamp, linear_clamp_grad)
     if key in _bias_act_cuda_cache:
         return _bias_act_cuda_cache[key]
 
     trivial = (act == 'linear' and gain == 1 and clamp < 0)
     needs_x = ('x' in spec.ref) or spec.has_2nd_grad
-    # The clamp mask of the gradient needs y.  The reference only keeps y for activations whose derivative is written in
-    # terms of y, so its CUDA path lets gradients through a clamped *linear* bias_act (ToRGB) while its impl='ref' path
-    # does not; parity is defined against impl='ref', hence y is also kept for linear + clamp.
-    needs_y = ('y' in spec.ref) or (clamp >= 0 and 'x' not in spec.ref)
+    # The clamp mask of the gradient needs y; see ``linear_clamp_grad`` above for the one case where the reference's two paths differ.
+    needs_y = ('y' in spec.ref) or (clamp >= 0 and 'x' not in spec.ref and linear_clamp_grad == 'ref')
 
     def _mem_format(t):
         return torch.channels_last if t.ndim > 2 and t.stride(1) == 1 else torch.contiguous_format

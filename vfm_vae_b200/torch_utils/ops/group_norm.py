@@ -39,6 +39,7 @@ class _GroupNorm32(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, w32, mean, rstd = ctx.saved_tensors
         groups, eps, has_w, has_b, wdt, bdt = ctx.cfg

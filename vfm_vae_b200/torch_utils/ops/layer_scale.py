@@ -35,6 +35,7 @@ class _LayerScaleResidual(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
         y, P, Q, R = ctx.saved_tensors
         scale, gshape, gdtype = ctx.cfg

@@ -64,6 +64,7 @@ class _ModulatedConv2d(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         xc, w32, s32, n32, dcoefs, y, f32 = ctx.saved_tensors
         up, padding, demodulate, flip_weight = ctx.cfg

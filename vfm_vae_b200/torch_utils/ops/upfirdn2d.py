@@ -185,6 +185,7 @@ class _ReplicateBlur(torch.autograd.Function):
         return _plugin.upfirdn2d(x, f32, 1, 1, 1, 1, k // 2, k // 2, k // 2, k // 2, True, 1.0, pad_mode=1)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         f32 = ctx.f
         k, c = f32.shape[0], dy.shape[1]
@@ -240,6 +241,7 @@ class _DepthwiseConv2d(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, f = ctx.saved_tensors
         k, wshape, wdt, bdt, nz = ctx.cfg

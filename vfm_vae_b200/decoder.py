@@ -58,6 +58,34 @@ class Conv1x1(nn.Conv2d):
         return super().forward(x)
 
 
+class DepthwiseConv2d(nn.Conv2d):
+    """``nn.Conv2d(C, C, k, padding=k // 2, groups=C)`` of the glue layers (z-convs, generator.py:729-783; the pixel-shuffle upsampler,
+    convnext_utils.py:219) -- same parameters and state-dict names.  On CUDA it runs on the library's streaming stencil kernel
+    (``depthwise_conv2d``: forward, data and weight gradients) wherever that applies.
+
+    This is not only faster: PyTorch's stock fp16 depthwise conv in NCHW layout is WRONG on this platform (B200, torch 2.11.0+cu128, cuDNN
+    9.22): for images of 32x32 and larger it returns garbage / NaN that depends on the allocator's state (tools/stock_fp16_probe.py;
+    channels_last is fine).  Where the library kernel does not apply, fp16 inputs therefore take the channels_last stock kernel."""
+
+    def __init__(self, channels, kernel_size=3, bias=False, ops=None):
+        super().__init__(channels, channels, kernel_size, padding=kernel_size // 2, groups=channels, bias=bias)
+        self.ops = ops
+
+    def forward(self, x):
+        if x.is_cuda:
+            if torch.is_autocast_enabled():
+                x = x.to(torch.get_autocast_dtype('cuda'))
+            dw = getattr(self.ops, 'depthwise_conv2d', None) if self.ops is not None else None
+            y = dw(x.contiguous(), self.weight, self.bias) if dw is not None else None
+            if y is not None:
+                return y
+            if x.dtype == torch.float16:
+                w = self.weight.to(x.dtype)
+                b = self.bias.to(x.dtype) if self.bias is not None else None
+                return F.conv2d(x.contiguous(memory_format=torch.channels_last), w, b, padding=self.padding, groups=self.groups).contiguous()
+        return super().forward(x)
+
+
 class FullyConnectedLayer(nn.Module):
     """Equalised-lr linear layer (networks/utils/shared.py:24-106)."""
 
@@ -175,7 +203,7 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
         self.out_channels, self.pre_normalize, self.use_gaussian_blur = out_channels, pre_normalize, use_gaussian_blur
         nc = in_channels if pre_normalize else out_channels
         self.norm = nn.GroupNorm(min(32, nc // 4), nc)
-        self.depthwise = nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels, bias=False)
+        self.depthwise = DepthwiseConv2d(in_channels, 3, bias=False, ops=ops)
         self.pointwise = Conv1x1(in_channels, out_channels * upscale_factor ** 2, 1, bias=False)
         self.shuffle = nn.PixelShuffle(upscale_factor)
         if use_gaussian_blur:
@@ -198,9 +226,7 @@ class SeparableUpsampleWithFixedBlur(nn.Module):
         return self.norm(x)
 
     def _depthwise(self, x):
-        dw = getattr(self.ops, 'depthwise_conv2d', None) if (self.ops is not None and x.is_cuda) else None
-        y = dw(x, self.depthwise.weight, None) if dw is not None else None
-        return y if y is not None else self.depthwise(x)
+        return self.depthwise(x)
 
     def _shuffle(self, x):
         ps = getattr(self.ops, 'pixel_shuffle2', None) if (self.ops is not None and x.is_cuda and self.shuffle.upscale_factor == 2) else None
@@ -348,7 +374,7 @@ class ConvNeXtSynthesisLayer(nn.Module):
         super().__init__()
         self.ops, self.legacy, self.channels, self.kernel_size = ops, legacy, channels, kernel_size
         self.affine_pw1 = StyleSplit(w_dim, channels, bias_init=1)
-        self.dwconv = nn.Conv2d(channels, channels, kernel_size=kernel_size, padding=kernel_size // 2, groups=channels)
+        self.dwconv = DepthwiseConv2d(channels, kernel_size, bias=True, ops=ops)      # its stock fallback is fp16-safe (see the class)
         nn.init.trunc_normal_(self.dwconv.weight, std=0.02)
         nn.init.constant_(self.dwconv.bias, 0)
         if legacy:
@@ -572,7 +598,7 @@ class SynthesisNetwork(nn.Module):
         return {'lrelu': lambda: nn.LeakyReLU(negative_slope=0.2), 'silu': nn.SiLU, 'gelu': nn.GELU}[name]()
 
     def _conv3x3(self, cin, cout, activation):
-        return nn.Sequential(nn.Conv2d(cin, cin, 3, padding=1, groups=cin, bias=False), Conv1x1(cin, cout, 1, bias=False),
+        return nn.Sequential(DepthwiseConv2d(cin, 3, bias=False, ops=self.ops), Conv1x1(cin, cout, 1, bias=False),
                              GroupNorm32(min(32, cout), cout), self._act(activation))
 
     def _conv1x1(self, cin, cout):

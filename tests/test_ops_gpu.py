@@ -563,11 +563,7 @@ def test_tensor_core_path_is_taken_for_decoder_shapes():
     torch.cuda.synchronize()
     lib.vfm_timing_enable(0)
 
-    class Stat(C.Structure):
-        _fields_ = [('name', C.c_char * 64), ('launches', C.c_int64), ('total_ms', C.c_double), ('flops', C.c_double), ('bytes', C.c_double)]
-    lib.vfm_timing_report.restype = C.c_int
-    lib.vfm_timing_report.argtypes = [C.POINTER(Stat), C.c_int]
-    buf = (Stat * 32)()
+    buf = (_lib.KernelStat * 32)()          # the binding's own struct / argtypes (vfm_vae_b200/_lib.py)
     n = lib.vfm_timing_report(buf, 32)
     names = {buf[i].name.decode() for i in range(min(n, 32))}
     assert 'modconv_tc_fwd' in names and 'modconv_generic_conv' not in names, names

@@ -308,11 +308,17 @@ def _conv_transpose2d_grouped(x, w, stride, pad_y=0, pad_x=0):
     return full[:, :, pad_y: fh - pad_y, pad_x: fw - pad_x]
 
 
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, flip_weight=True, flip_filter=False):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
     """conv with optional up/down-sampling.  ``w`` may be [O,I,kh,kw] or per-sample [N,O,I,kh,kw]
     (the latter restates the reference's groups=N grouped conv on a [1,N*I,H,W] view).
 
-    flip_weight=True = cross-correlation (what conv2d does); False = true convolution."""
+    flip_weight=True = cross-correlation (what conv2d does); False = true convolution.
+    groups > 1 (torch_utils/ops/conv2d_resample.py:113-118): a grouped conv is `groups` independent convs on channel slices and every
+    FIR stage is per channel, so the whole op is evaluated slice by slice."""
+    if groups > 1:
+        ig, og = x.shape[1] // groups, w.shape[0] // groups
+        return torch.cat([conv2d_resample(x[:, g * ig:(g + 1) * ig], w[g * og:(g + 1) * og], f=f, up=up, down=down, padding=padding,
+                                          flip_weight=flip_weight, flip_filter=flip_filter) for g in range(groups)], dim=1)
     kh, kw = w.shape[-2:]
     fw, fh = _fsize(f)
     px0, px1, py0, py1 = _pad4(padding)

@@ -584,16 +584,61 @@ def test_modulated_conv2d_errors():
         V.modulated_conv2d(x, w, s, up=2, padding=1)     # up=2 without a resample filter
 
 
-@pytest.mark.parametrize('case', [c for c in _cases('conv2d_resample') if c['down'] == 1 and isinstance(c['padding'], int)], ids=lambda c: c['key'])
+@pytest.mark.parametrize('case', _cases('conv2d_resample'), ids=lambda c: c['key'])
 def test_conv2d_resample_golden(case):
     V = _ops()
     G = golden('conv2d_resample')
     k = case['key']
-    y = V.conv2d_resample.conv2d_resample(G.t(k + '_x', DEV), G.t(k + '_w', DEV), f=G.t('f', DEV), up=case['up'],
+    y = V.conv2d_resample.conv2d_resample(G.t(k + '_x', DEV), G.t(k + '_w', DEV), f=G.t('f', DEV), up=case['up'], down=case['down'],
                                           padding=case['padding'], flip_weight=case['flip_weight'])
     ref = G.t(k + '_y')
     assert y.shape == ref.shape
     assert rel_err(y, ref) <= 1e-6
+
+
+@pytest.mark.parametrize('case', _cases('conv2d_resample_ext'), ids=lambda c: f"{c['key']}-{c['dtype']}")
+def test_conv2d_resample_ext_golden(case):
+    """Everything beyond the decoder's subset (reference conv2d_resample.py:95-141): groups, down > 1, up and down together, per-axis /
+    asymmetric / negative padding, flip_filter with an asymmetric filter, separable 1-D filters -- forward and input / weight gradients
+    against the oracle."""
+    V = _ops()
+    G = golden('conv2d_resample_ext')
+    k = case['key']
+    kw = dict(up=case['up'], down=case['down'], padding=case['padding'], groups=case['groups'], flip_weight=case['flip_weight'],
+              flip_filter=case['flip_filter'])
+    x = G.t(k + '_x', DEV).requires_grad_(True)
+    w = G.t(k + '_w', DEV).requires_grad_(True)
+    y = V.conv2d_resample.conv2d_resample(x, w, f=G.t('f::' + case['filter'], DEV), **kw)
+    ref = G.t(k + '_y')
+    tol = {'float32': 1e-5, 'float64': 1e-6}[case['dtype']]       # fp64: the fast path consumes fp32 weights (modulated_conv2d)
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    assert rel_err(y, ref) <= tol
+    xr = G.t(k + '_x').requires_grad_(True)
+    wr = G.t(k + '_w').requires_grad_(True)
+    yr = O.conv2d_resample(xr, wr, f=G.t('f::' + case['filter']), **kw)
+    dy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(3), dtype=yr.dtype)
+    gr = torch.autograd.grad(yr, [xr, wr], dy)
+    gg = torch.autograd.grad(y, [x, w], dy.to(DEV))
+    for a, b, name in zip(gg, gr, ['dx', 'dw']):
+        assert rel_err(a, b) <= tol, name
+
+
+def test_fma_matches_addcmul_and_unbroadcasts_gradients():
+    """fma.fma(a, b, c) = a * b + c with gradients summed back over broadcast dimensions (reference torch_utils/ops/fma.py:15-58; the
+    unfused modulated-conv branch calls it with a [N,I,1,1] scale and a [N,1,H,W] / scalar addend)."""
+    from vfm_vae_b200.torch_utils.ops import fma as Fm
+    g = torch.Generator().manual_seed(1)
+    for shapes in [((2, 3, 4, 5), (2, 3, 1, 1), (2, 1, 4, 5)), ((4, 5), (5,), (1,)), ((3, 1, 2), (1, 4, 2), (3, 4, 1)), ((2, 2), (2, 2), (2, 2))]:
+        for dtype in (torch.float32, torch.float64):
+            a, b, c = (torch.randn(s, generator=g, dtype=dtype).to(DEV).requires_grad_(True) for s in shapes)
+            y = Fm.fma(a, b, c)
+            ref = a * b + c
+            assert y.shape == ref.shape and torch.allclose(y, ref, rtol=1e-6, atol=1e-6)
+            dy = torch.randn(ref.shape, generator=g, dtype=dtype).to(DEV)
+            gg = torch.autograd.grad(y, [a, b, c], dy)
+            gr = torch.autograd.grad(ref, [a, b, c], dy)
+            for u, v, t in zip(gg, gr, (a, b, c)):
+                assert u.shape == t.shape and torch.allclose(u, v, rtol=1e-5, atol=1e-6)
 
 
 # ------------------------------------------------------------------------- fused inference layer (SURVEY 8f row 3)

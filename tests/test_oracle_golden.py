@@ -85,6 +85,18 @@ def test_conv2d_resample(case):
     assert rel_err(y, ref) <= 1e-12
 
 
+@pytest.mark.parametrize('case', _cases('conv2d_resample_ext'), ids=lambda c: f"{c['key']}-{c['dtype']}")
+def test_conv2d_resample_ext(case):
+    """groups, down-sampling, up + down, per-axis / asymmetric / negative padding, flip_filter, separable filters."""
+    G = golden('conv2d_resample_ext')
+    k = case['key']
+    y = O.conv2d_resample(G.t(k + '_x'), G.t(k + '_w'), f=G.t('f::' + case['filter']), up=case['up'], down=case['down'], padding=case['padding'],
+                          groups=case['groups'], flip_weight=case['flip_weight'], flip_filter=case['flip_filter'])
+    ref = G.t(k + '_y')
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    assert rel_err(y, ref) <= {'float32': 2e-6, 'float64': 1e-12}[case['dtype']]
+
+
 @pytest.mark.parametrize('case', _cases('modulated_conv2d'), ids=lambda c: f"{c['key']}-{c['dtype']}")
 def test_modulated_conv2d(case):
     G = golden('modulated_conv2d')

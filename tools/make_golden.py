@@ -275,6 +275,36 @@ def gen_conv2d_resample():
     save('conv2d_resample', arrays, dict(cases=cases))
 
 
+def gen_conv2d_resample_ext():
+    """conv2d_resample beyond the decoder's subset: groups, down-sampling, up + down, per-axis / asymmetric padding, flip_filter with an
+    asymmetric filter, separable 1-D filters (torch_utils/ops/conv2d_resample.py:95-141), fp32 and fp64."""
+    arrays, cases = {}, []
+    g = rng(15)
+    filters = {'f4': ref_upfirdn2d.setup_filter([1, 3, 3, 1]), 'fasym': ref_upfirdn2d.setup_filter([1, 2, 4, 3]),
+               'fsep8': ref_upfirdn2d.setup_filter([1, 2, 3, 5, 5, 3, 2, 1])}
+    assert filters['fsep8'].ndim == 1
+    idx = 0
+    for dtype in (torch.float32, torch.float64):
+        for (n, i, o, h, k, up, down, pad, flipw, groups, flipf, fname) in [
+            (2, 4, 6, 9, 3, 1, 2, 1, True, 2, False, 'f4'), (2, 4, 6, 8, 3, 2, 1, 1, False, 2, False, 'f4'),
+            (1, 3, 2, 8, 3, 2, 2, 1, True, 1, False, 'f4'), (1, 3, 2, 8, 3, 1, 1, [1, 2], True, 1, False, 'f4'),
+            (1, 3, 2, 8, 3, 2, 1, [1, 0, 2, 1], True, 1, True, 'fasym'), (1, 4, 4, 8, 1, 1, 2, 0, True, 4, False, 'f4'),
+            (2, 3, 5, 10, 3, 1, 2, 1, True, 1, True, 'fsep8'), (2, 3, 5, 6, 3, 2, 1, 1, True, 1, False, 'fsep8'),
+            (1, 4, 2, 7, 1, 2, 1, 0, False, 2, False, 'fasym'), (1, 2, 3, 9, 3, 1, 1, [0, -1, 2, 0], False, 1, False, 'f4'),
+        ]:
+            x = randn(g, n, i, h, h, dtype=dtype)
+            w = randn(g, o, i // groups, k, k, dtype=dtype)
+            y = ref_c2r.conv2d_resample(x, w, f=filters[fname], up=up, down=down, padding=pad, groups=groups, flip_weight=flipw, flip_filter=flipf)
+            kk = f'e{idx}'
+            idx += 1
+            arrays[kk + '_x'], arrays[kk + '_w'], arrays[kk + '_y'] = x, w, y
+            cases.append(dict(key=kk, up=up, down=down, padding=pad, flip_weight=flipw, groups=groups, flip_filter=flipf, filter=fname,
+                              dtype=str(dtype).split('.')[-1]))
+    for k_, v in filters.items():
+        arrays['f::' + k_] = v
+    save('conv2d_resample_ext', arrays, dict(cases=cases))
+
+
 DECODER_KW = dict(c_dim=0, w_dim=32, img_resolution=64, img_channels=3, z_resolution=8, z_dim=16,
                   concat_z_block_indices=[0, 1], concat_z_mapped_dims=[32, 32], how_to_process_concat_z='unshuffle',
                   activation_for_concat_z='lrelu', attn_block_indices=[0], attn_depths=[1], use_self_attn=True,
@@ -353,10 +383,15 @@ def gen_decoder_convnext():
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:            # python tools/make_golden.py gen_conv2d_resample_ext  -> only that fixture
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     gen_bias_act()
     gen_upfirdn2d()
     gen_filtered_lrelu()
     gen_modconv()
     gen_conv2d_resample()
+    gen_conv2d_resample_ext()
     gen_decoder()
     gen_decoder_convnext()

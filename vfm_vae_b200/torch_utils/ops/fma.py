@@ -1,5 +1,6 @@
 """a * b + c with broadcasting-aware gradients.  Mirror of torch_utils/ops/fma.py:15 (only reached on the reference's
-unfused modconv branch, which this package never takes; kept so callers importing it keep working)."""
+unfused modconv branch, which this package never takes; kept so callers importing it keep working).  Tested on CPU
+(tests/test_fma_cpu.py, incl. gradcheck) and on the device (tests/test_ops_gpu.py)."""
 import torch
 
 
@@ -8,15 +9,13 @@ def fma(a, b, c):
 
 
 def _reduce_to(g, shape):
-    """Sum a gradient over the dimensions that were broadcast to reach g.shape from `shape`."""
+    """Sum a gradient over the dimensions that were broadcast to reach g.shape from `shape` (leading dimensions that `shape` lacks,
+    and size-1 dimensions of `shape` that g expanded)."""
     lead = g.ndim - len(shape)
-    dims = [i for i in range(g.ndim) if g.shape[i] > 1 and (i < lead or shape[i - lead] == 1)]
+    dims = [i for i in range(g.ndim) if i < lead or (shape[i - lead] == 1 and g.shape[i] > 1)]
     if dims:
         g = g.sum(dim=dims, keepdim=True)
-    if lead:
-        g = g.reshape(-1, *g.shape[lead + 1:])
-    assert tuple(g.shape) == tuple(shape)
-    return g
+    return g.reshape(shape)
 
 
 class _Fma(torch.autograd.Function):

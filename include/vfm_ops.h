@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 5
+#define VFM_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -382,6 +382,22 @@ typedef struct {
     double   nan, posinf, neginf;
 } vfm_grad_finalize_params;
 VFM_API int vfm_grad_finalize(const vfm_grad_finalize_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Decode I/O path: decoder output -> the bytes a PNG encoder takes, in one pass.  Replaces, bit for bit,
+ *     images = ((images + 1) / 2).clamp(0, 1)            tools/decode/decode_latents_to_images.py:92  (tools/reconstruct likewise)
+ *     to_pil_image(img.clamp(0, 1))                      safe_save, :20-24  == img.mul(255).byte() transposed to HWC (truncation)
+ * y[n,h,w,c] = (uint8) trunc( clamp((x[n,c,h,w] + pre_add) / pre_div, 0, 1) * scale ),  evaluated in fp32 in exactly that order
+ * (reference values: pre_add 1, pre_div 2, scale 255).  x: contiguous NCHW, fp16 or fp32; y: contiguous NHWC uint8; C in {1, 3, 4}.
+ */
+typedef struct {
+    const void* x;          /* [N,C,H,W] */
+    uint8_t*    y;          /* [N,H,W,C] out */
+    int32_t     dtype;      /* vfm_dtype of x */
+    int32_t     batch, channels, height, width;
+    double      pre_add, pre_div, scale;
+} vfm_image_to_u8_params;
+VFM_API int vfm_image_to_u8(const vfm_image_to_u8_params* p, void* stream);
 
 /* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);

@@ -102,6 +102,11 @@ class GradFinalizeParams(C.Structure):
                 ('neginf', _f64)]
 
 
+class ImageToU8Params(C.Structure):
+    _fields_ = [('x', _vp), ('y', _vp), ('dtype', _i32), ('batch', _i32), ('channels', _i32), ('height', _i32), ('width', _i32),
+                ('pre_add', _f64), ('pre_div', _f64), ('scale', _f64)]
+
+
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
@@ -135,6 +140,7 @@ SYMBOLS = {
     'vfm_pixel_shuffle2': (C.c_int, [C.POINTER(PixelShuffle2Params), _vp]),
     'vfm_depthwise_wgrad': (C.c_int, [C.POINTER(DepthwiseWgradParams), _vp]),
     'vfm_grad_finalize': (C.c_int, [C.POINTER(GradFinalizeParams), _vp]),
+    'vfm_image_to_u8': (C.c_int, [C.POINTER(ImageToU8Params), _vp]),
 }
 
 _lib = None
@@ -155,8 +161,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 5:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 5)')
+    if lib.vfm_abi_version() != 6:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 6)')
     _lib = lib
     return lib
 

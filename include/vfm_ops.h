@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 6
+#define VFM_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -261,6 +261,11 @@ typedef struct {
     const float* x_scale;        /* [N,I] fp32 or NULL */
     const float* x_shift;        /* [N,I] fp32 or NULL (requires x_scale) */
     int32_t      ep_res_affine;
+    /* Training: != 0 asks the tcgen05 path to leave its activation operand -- x * s' as NHWC fp16 (hi [+ lo] for fp32 tensors), scaled by ONE
+     * power of two for the whole batch -- intact in the workspace, so that the backward can feed it to the weight gradient instead of
+     * re-reading and re-laying x (vfm_modconv_forward_operand / vfm_modconv_bwd_params::saved_operand).  The caller keeps the workspace
+     * alive until the backward has run.  Ignored by the other paths and together with x_scale. */
+    int32_t      keep_operand;
 } vfm_modconv_fwd_params;
 
 typedef struct {
@@ -278,6 +283,10 @@ typedef struct {
     float*       dnoise;   /* fp32, shape per noise_mode, out, or NULL */
     void*        workspace;
     size_t       workspace_bytes;
+    /* Optional: the forward's activation operand, as returned by vfm_modconv_forward_operand after a forward with keep_operand != 0 on the
+     * same x / styles (NULL = recompute it from x).  Skips one read of x and one write + read of its NHWC copy per layer. */
+    const void*  saved_operand;
+    const void*  saved_operand_lo;   /* fp32 tensors: the lo half of the split */
 } vfm_modconv_bwd_params;
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -405,6 +414,9 @@ VFM_API int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream);
 VFM_API int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream);
 /* 1 if the tcgen05/TMEM implicit-GEMM path will be used for this descriptor, 0 if the generic SIMT kernel. */
 VFM_API int vfm_modconv_uses_tensor_cores(const vfm_modconv_desc* d);
+/* Where a forward with keep_operand != 0 left its activation operand inside `workspace` (the pointer given to that forward):
+ * *hi (and *lo for fp32 tensors, else NULL), or both NULL when the path taken for this descriptor keeps none.  Pure address arithmetic. */
+VFM_API int vfm_modconv_forward_operand(const vfm_modconv_desc* d, void* workspace, size_t workspace_bytes, const void** hi, const void** lo);
 
 #ifdef __cplusplus
 }

@@ -544,6 +544,36 @@ def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
     _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['fp16', 'fp32'])
+@pytest.mark.parametrize('up', [1, 2])
+def test_kept_forward_operand_gives_the_same_weight_gradient(dtype, up):
+    """Training keeps the forward's NHWC operand for the weight gradient (keep_forward_operand): same gradients as re-laying x in the backward
+    (up to the fp32 atomics of the split-K weight gradient), with styles > 1 so that the power-of-two operand scale is not 1."""
+    V = _ops()
+    from vfm_vae_b200.torch_utils.ops import modulated_conv2d as M
+    g = torch.Generator().manual_seed(40)
+    N, I, O_, H = 3, 256, 128, 16
+    x = torch.randn(N, I, H, H, generator=g).to(dtype).to(DEV)
+    w = torch.randn(O_, I, 3, 3, generator=g).to(DEV)
+    st = (torch.randn(N, I, generator=g) * 3 + 1).to(DEV)
+    f = O.setup_filter([1, 3, 3, 1]).to(DEV) if up == 2 else None
+    dy = None
+    res = {}
+    for keep in (True, False):
+        M.keep_forward_operand = keep
+        try:
+            leaves = [x.clone().requires_grad_(True), w.clone().requires_grad_(True), st.clone().requires_grad_(True)]
+            y = V.modulated_conv2d(leaves[0], leaves[1], leaves[2], up=up, padding=1, resample_filter=f, demodulate=(dtype == torch.float16), flip_weight=(up == 1))
+            if dy is None:
+                dy = torch.randn(y.shape, generator=g).to(dtype).to(DEV)
+            res[keep] = (y, torch.autograd.grad(y, leaves, dy))
+        finally:
+            M.keep_forward_operand = True
+    assert torch.equal(res[True][0], res[False][0])
+    for a, b, name in zip(res[True][1], res[False][1], ['dx', 'dw', 'ds']):
+        assert rel_err(a, b) <= 2e-6, name
+
+
 def test_tensor_core_path_is_taken_for_decoder_shapes():
     """The hot decoder layers must be routed to the tcgen05 kernel (and the odd shapes must not)."""
     from vfm_vae_b200.plugins import modconv_plugin as P

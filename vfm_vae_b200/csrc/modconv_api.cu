@@ -25,10 +25,11 @@ size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction);
 // stage-1 contraction: x -> z (== y for up=1; noise only added when up == 1)
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
                       const float* noise, int64_t noise_sn, const Epilogue& ep, const float* x_scale, const float* x_shift,
-                      void* ws, size_t ws_bytes, cudaStream_t stream);
+                      void* ws, size_t ws_bytes, cudaStream_t stream, int keep_operand);
+void tc_forward_operand(const vfm_modconv_desc& d, void* ws, size_t ws_bytes, const void** hi, const void** lo);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
-                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream);
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo);
 
 static int validate(const vfm_modconv_desc& d) {
     VFM_CHECK_ARG(d.dtype == VFM_F16 || d.dtype == VFM_F32 || d.dtype == VFM_F64, "modulated_conv2d: unsupported dtype %d", d.dtype);
@@ -99,6 +100,22 @@ extern "C" int vfm_modconv_uses_tensor_cores(const vfm_modconv_desc* d) {
     return use_tc(*d) ? 1 : 0;
 }
 
+// the forward's workspace layout up to the tensor-core section (must mirror vfm_modconv_forward)
+extern "C" int vfm_modconv_forward_operand(const vfm_modconv_desc* dp, void* workspace, size_t workspace_bytes, const void** hi, const void** lo) {
+    VFM_CHECK_ARG(dp && hi && lo, "modconv_forward_operand: NULL argument");
+    *hi = *lo = nullptr;
+    const vfm_modconv_desc& d = *dp;
+    if (!workspace || !use_tc(d) || (use_pw(d))) return VFM_OK;
+    Carver cv(workspace, workspace_bytes);
+    Coefs k; carve_coefs(cv, d, k);
+    Stage1 s = make_stage1(d);
+    if (d.up == 2) cv.take<char>((size_t)d.batch * d.out_channels * s.zh * (size_t)((s.zw + 15) & ~15) * esize(d.dtype));
+    cv.off = (cv.off + 255) & ~(size_t)255;
+    if (cv.off >= workspace_bytes) return VFM_OK;
+    tc_forward_operand(d, (char*)workspace + cv.off, workspace_bytes - cv.off, hi, lo);
+    return VFM_OK;
+}
+
 extern "C" size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction) {
     if (!d) return 0;
     size_t g = generic_workspace(*d, direction);
@@ -156,7 +173,7 @@ extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = tc_stage1_forward(d, s, p->x, p->weight, k, z, zpitch, s1_noise, noise_sn, s1_ep, p->x_scale, p->x_shift,
-                               (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+                               (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream, p->keep_operand);
         if (st) return st;
     } else {
         ConvArgs a;
@@ -236,7 +253,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = tc_stage1_backward(d, s, dzp, d.up == 2 ? dz_pitch : 0, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
-                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);
+                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream, p->saved_operand, p->saved_operand_lo);
         if (st) return st;
     } else {
         if (p->dx) {

@@ -1037,8 +1037,11 @@ __global__ void __launch_bounds__(256) weight_prep_mod1x1_kernel(const float* __
 // per-sample power-of-two normalisation of the activation scale so that |x * scale| stays far from the fp16 limit:
 //   a_scale[n,i] = in_scale[n,i] * c2[n],  o_scale[n,o] = out_scale[n,o] / c2[n],  c2 = 2^-ceil(log2(max_i |in_scale|)) if that max > 1
 //   with an input affine map x -> x * xa + xb:  a_scale *= xa,  a_shift[n,i] = in_scale * c2 * xb
+//   c2_global != NULL: ONE power of two for the whole batch (*c2_global, from wgrad_scalars_kernel) instead of the per-sample one, which
+//   makes the scaled operand exactly what the weight gradient needs (training: the forward's operand is kept for the backward)
 __global__ void scale_prep_kernel(const float* __restrict__ in_scale, const float* __restrict__ out_scale, float* a_scale, float* o_scale, int Cin, int Cout,
-                                  const float* __restrict__ xa = nullptr, const float* __restrict__ xb = nullptr, float* a_shift = nullptr) {
+                                  const float* __restrict__ xa = nullptr, const float* __restrict__ xb = nullptr, float* a_shift = nullptr,
+                                  const float* __restrict__ c2_global = nullptr) {
     __shared__ float red[32];
     __shared__ float s_c2;
     const int n = blockIdx.x;
@@ -1051,7 +1054,7 @@ __global__ void scale_prep_kernel(const float* __restrict__ in_scale, const floa
     if (threadIdx.x == 0) {
         float mm = 0.f;
         for (int k = 0; k < (int)(blockDim.x + 31) / 32; k++) mm = fmaxf(mm, red[k]);
-        s_c2 = (mm > 1.f && isfinite(mm)) ? exp2f(-ceilf(log2f(mm))) : 1.f;
+        s_c2 = c2_global ? *c2_global : ((mm > 1.f && isfinite(mm)) ? exp2f(-ceilf(log2f(mm))) : 1.f);
     }
     __syncthreads();
     const float c2 = s_c2, c2i = 1.f / s_c2;
@@ -1358,9 +1361,20 @@ size_t tc_workspace_bytes(const vfm_modconv_desc& d, int direction) {
     return cv.off + 512;
 }
 
+// where tc_stage1_forward(keep_operand) leaves x * s' * c2g (NHWC fp16 hi / lo) inside its workspace; NULL for the direct-NCHW 1x1 path
+void tc_forward_operand(const vfm_modconv_desc& d, void* ws, size_t ws_bytes, const void** hi, const void** lo) {
+    *hi = *lo = nullptr;
+    if (mnp_candidate(d)) return;
+    Carver cv(ws, ws_bytes);
+    TcWorkspace w;
+    carve_tc(cv, d, make_stage1(d), 0, w);
+    if (!cv.ok()) return;
+    *hi = w.act; *lo = w.act_lo;
+}
+
 int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x, const float* weight, const Coefs& k, void* z, int zpitch,
                       const float* noise, int64_t noise_sn, const Epilogue& ep, const float* x_scale, const float* x_shift,
-                      void* ws, size_t ws_bytes, cudaStream_t stream) {
+                      void* ws, size_t ws_bytes, cudaStream_t stream, int keep_operand) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
@@ -1386,7 +1400,14 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
         return run_tc_conv(false, false, op, a, 1, stream, true);
     }
     // A = x * s' * c2, B = W * a, epilogue scale = d / c2
-    scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O, x_scale, x_shift, x_scale ? w.a_shift : nullptr);
+    const float* c2_global = nullptr;
+    if (keep_operand && !x_scale) {
+        // the operand survives for the weight gradient: one power of two for the whole batch (what run_tc_wgrad's own pre-pass would use)
+        wgrad_scalars_kernel<<<1, 256, 0, stream>>>(k.iscale, N * I, w.gs, 0);
+        int st1 = launch_status("modconv wgrad_scalars_kernel"); if (st1) return st1;
+        c2_global = w.gs + 2;
+    }
+    scale_prep_kernel<<<N, 256, 0, stream>>>(k.iscale, k.d, w.a_scale, w.o_scale, I, O, x_scale, x_shift, x_scale ? w.a_shift : nullptr, c2_global);
     int st = launch_status("modconv scale_prep_kernel"); if (st) return st;
     st = run_prepass(d.dtype, f32, x, w.a_scale, nullptr, w.act, w.act_lo, N, I, d.in_h * d.in_w, stream, x_scale ? w.a_shift : nullptr); if (st) return st;
     st = run_weight_prep(weight, k.a, w.wt, w.wt_lo, O, I, KK, s.taps, 0, stream); if (st) return st;
@@ -1424,7 +1445,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
 }
 
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
-                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo) {
     const bool f32 = is_f32(d);
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
@@ -1467,7 +1488,12 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         // B operand: x * s' * c2g NHWC; result scale a[o] / (gk * c2g)
         wgrad_scalars_kernel<<<1, 256, 0, stream>>>(k.iscale, N * I, w.gs, gs ? 1 : 0);
         st = launch_status("modconv wgrad_scalars_kernel"); if (st) return st;
-        st = run_prepass(d.dtype, f32, x, k.iscale, w.gs + 2, w.xt, w.xt_lo, N, I, d.in_h * d.in_w, stream); if (st) return st;
+        if (saved_xt && (!f32 || saved_xt_lo)) {
+            // the forward kept exactly this tensor (same iscale, same c2g): no second pass over x
+            w.xt = (__half*)saved_xt; w.xt_lo = (__half*)saved_xt_lo;
+        } else {
+            st = run_prepass(d.dtype, f32, x, k.iscale, w.gs + 2, w.xt, w.xt_lo, N, I, d.in_h * d.in_w, stream); if (st) return st;
+        }
         st = run_tc_wgrad(f32, d, s, w, k.a, w.gs + 3, dweight, stream); if (st) return st;
     }
     return VFM_OK;

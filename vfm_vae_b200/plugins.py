@@ -377,8 +377,11 @@ class _ModconvPlugin:
 
     @staticmethod
     def forward(x, weight, styles, noise, up, padding, resample_filter, demodulate, flip_weight, force_generic=False, epilogue=None,
-                x_affine=None):
-        """-> (y [N,O,Hout,Wout] in x.dtype, dcoefs [N,O] fp32).
+                x_affine=None, keep_operand=False):
+        """-> (y [N,O,Hout,Wout] in x.dtype, dcoefs [N,O] fp32)   [, saved] with ``keep_operand``.
+
+        ``keep_operand`` (training): the tcgen05 path leaves its NHWC activation operand in the workspace; the third return value is then
+        ``(workspace tensor, hi pointer, lo pointer)`` to hand to ``backward(saved_operand=...)`` (or None when the path keeps none).
 
         ``x_affine`` (inference only): (scale, shift) fp32 [N,I] from ``group_norm_affine``: the conv sees x*scale+shift; with
         ``epilogue['residual_affine']`` the same map is applied to the epilogue's residual (which then is the raw x).
@@ -423,18 +426,24 @@ class _ModconvPlugin:
                        for t in (xs, xb)), 'x_affine must be two contiguous fp32 [N,I] tensors')
             keep += [xs, xb]
             p.x_scale, p.x_shift = _ptr(xs), _ptr(xb)
+        p.keep_operand = int(bool(keep_operand))
         with torch.cuda.device(x.device):
             st = lib.vfm_modconv_forward(C.byref(p), _stream(x))
         del keep
         if (epilogue is not None or x_affine is not None) and st == _lib.VFM_ERR_NO_KERNEL:
             return None
         _lib.check(st, 'modulated_conv2d')
+        if keep_operand:
+            hi, lo = C.c_void_p(), C.c_void_p()
+            _lib.check(lib.vfm_modconv_forward_operand(C.byref(d), _ptr(ws), nbytes, C.byref(hi), C.byref(lo)), 'modconv_forward_operand')
+            return y, dcoefs, ((ws, hi.value, lo.value) if hi.value else None)
         return y, dcoefs
 
     @staticmethod
     def backward(dy, x, y, weight, styles, noise, dcoefs, up, padding, resample_filter, demodulate, flip_weight,
-                 need_dx=True, need_dweight=True, need_dstyles=True, need_dnoise=False, force_generic=False):
-        """-> (dx or None, dweight fp32 or None, dstyles fp32 or None, dnoise fp32 or None)"""
+                 need_dx=True, need_dweight=True, need_dstyles=True, need_dnoise=False, force_generic=False, saved_operand=None):
+        """-> (dx or None, dweight fp32 or None, dstyles fp32 or None, dnoise fp32 or None).  ``saved_operand``: what ``forward(keep_operand=True)``
+        returned for the same x / styles (its workspace must still be alive and untouched)."""
         _ModconvPlugin._common_checks(x, weight, styles, noise, up, resample_filter)
         d = _ModconvPlugin._desc(x, weight, up, padding, demodulate, flip_weight, noise, resample_filter, force_generic)
         _check(dy.is_contiguous() and dy.dtype == x.dtype and tuple(dy.shape) == (d.batch, d.out_channels, d.out_h, d.out_w),
@@ -453,6 +462,8 @@ class _ModconvPlugin:
         p.dy, p.x, p.y, p.weight, p.styles, p.noise, p.dcoefs = _ptr(dy), _ptr(x), _ptr(y), _ptr(weight), _ptr(styles), _ptr(noise), _ptr(dcoefs)
         p.dx, p.dweight, p.dstyles, p.dnoise = _ptr(dx), _ptr(dweight), _ptr(dstyles), _ptr(dnoise)
         p.workspace, p.workspace_bytes = _ptr(ws), nbytes
+        if saved_operand is not None:
+            p.saved_operand, p.saved_operand_lo = saved_operand[1], saved_operand[2]
         with torch.cuda.device(x.device):
             _lib.check(lib.vfm_modconv_backward(C.byref(p), _stream(x)), 'modulated_conv2d backward')
         return dx, dweight, dstyles, dnoise

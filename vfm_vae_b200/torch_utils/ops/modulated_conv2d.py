@@ -19,6 +19,11 @@ _plugin = None
 #: set True (tests only) to run every call through the generic SIMT kernel instead of the tcgen05 path
 force_generic = False
 
+#: training: keep the forward's NHWC activation operand (x * s', fp16) alive for the weight gradient instead of re-laying x in the backward:
+#: one read of x and one write + read of its NHWC copy less per layer, for N*H*W*C*2 bytes of extra live memory per layer (~10 GB for the
+#: f16d32 decoder at batch 64).  Set False to trade the time back for the memory.
+keep_forward_operand = True
+
 
 def _init():
     global _plugin
@@ -55,7 +60,10 @@ class _ModulatedConv2d(torch.autograd.Function):
             oh = x.shape[2] * up + 2 * padding - (kh - 1)
             ow = x.shape[3] * up + 2 * padding - (weight.shape[3] - 1)
         n32 = _noise_canon(noise.detach() if noise is not None else None, n, oh, ow)
-        y, dcoefs = _plugin.forward(xc, w32, s32, n32, up, padding, f32, demodulate, flip_weight, force_generic)
+        keep = bool(keep_forward_operand and ctx.needs_input_grad[1] and not force_generic)
+        out = _plugin.forward(xc, w32, s32, n32, up, padding, f32, demodulate, flip_weight, force_generic, keep_operand=keep)
+        y, dcoefs = out[0], out[1]
+        ctx.saved_operand = out[2] if keep else None           # (workspace tensor, hi, lo): the tensor reference keeps the bytes alive
         ctx.save_for_backward(xc, w32, s32, n32 if n32 is not None else torch.empty([0]), dcoefs,
                               y if demodulate else torch.empty([0]), f32 if f32 is not None else torch.empty([0]))
         ctx.cfg = (up, padding, demodulate, flip_weight)
@@ -74,7 +82,9 @@ class _ModulatedConv2d(torch.autograd.Function):
         need = ctx.needs_input_grad
         dx, dw, ds, dn = _plugin.backward(dy.contiguous(), xc, y, w32, s32, n32, dcoefs, up, padding, f32, demodulate, flip_weight,
                                           need_dx=need[0], need_dweight=need[1], need_dstyles=need[2],
-                                          need_dnoise=(need[3] and n32 is not None), force_generic=force_generic)
+                                          need_dnoise=(need[3] and n32 is not None), force_generic=force_generic,
+                                          saved_operand=ctx.saved_operand)
+        ctx.saved_operand = None
         xd, wd, sd, nd = ctx.in_dtypes
         if dx is not None and not need[0]:
             dx = None

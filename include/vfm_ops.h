@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 7
+#define VFM_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -287,6 +287,16 @@ typedef struct {
      * same x / styles (NULL = recompute it from x).  Skips one read of x and one write + read of its NHWC copy per layer. */
     const void*  saved_operand;
     const void*  saved_operand_lo;   /* fp32 tensors: the lo half of the split */
+    /* Training with the fused layer epilogue (forward ran with ep_enable != 0, no residual): `dy` and `y` then are the gradient / value of
+     * the ACTIVATED output, y = clamp(act(conv + noise + ep_bias) * ep_gain, +-ep_clamp), and the backward of that bias_act
+     * (torch_utils/ops/bias_act.py:158-179) is folded into the one pass over dy that the demodulation and noise reductions make anyway.
+     * dbias_no receives sum_p of the pre-activation gradient per (sample, channel); the caller sums it over the batch.
+     * ep_act 1 (linear) or 3 (lrelu); needs fp16 / fp32, >= 2048 output pixels (a multiple of 8), else VFM_ERR_NO_KERNEL. */
+    int32_t      ep_enable;
+    int32_t      ep_act;
+    double       ep_alpha, ep_gain, ep_clamp;
+    const void*  ep_bias;            /* [O], dtype of x, or NULL */
+    float*       dbias_no;           /* [N,O] fp32 out, or NULL */
 } vfm_modconv_bwd_params;
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -408,8 +418,11 @@ typedef struct {
 } vfm_image_to_u8_params;
 VFM_API int vfm_image_to_u8(const vfm_image_to_u8_params* p, void* stream);
 
-/* direction: 0 = forward, 1 = backward.  Returns bytes (0 is a valid answer). */
+/* direction: 0 = forward, 1 = backward, 2 = backward with the fused layer epilogue (vfm_modconv_bwd_params::ep_enable).  Returns bytes
+ * (0 is a valid answer). */
 VFM_API size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction);
+/* 1 if vfm_modconv_backward can take ep_enable != 0 for this descriptor (fused training layer), else 0. */
+VFM_API int vfm_modconv_fused_backward_supported(const vfm_modconv_desc* d);
 VFM_API int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream);
 VFM_API int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* stream);
 /* 1 if the tcgen05/TMEM implicit-GEMM path will be used for this descriptor, 0 if the generic SIMT kernel. */

@@ -574,6 +574,66 @@ def test_kept_forward_operand_gives_the_same_weight_gradient(dtype, up):
         assert rel_err(a, b) <= 2e-6, name
 
 
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['fp16', 'fp32'])
+@pytest.mark.parametrize('cfg', [
+    dict(N=2, I=128, O_=128, H=64, up=1, noise='const', clamp=256.0, gain=1.0),
+    dict(N=2, I=256, O_=128, H=48, up=1, noise='random', clamp=1.5, gain=math.sqrt(2)),       # a clamp that bites: the gradient mask
+    dict(N=2, I=256, O_=128, H=32, up=2, noise='const', clamp=2.0, gain=math.sqrt(2)),        # epilogue in the blur, backward through it
+    dict(N=1, I=128, O_=256, H=64, up=1, noise=None, clamp=None, gain=1.0),
+], ids=lambda c: f"I{c['I']}O{c['O_']}H{c['H']}up{c['up']}{c['noise']}")
+def test_fused_training_layer_vs_oracle(cfg, dtype):
+    """modulated conv + noise + bias_act as ONE autograd node (training): forward and every gradient (x, weight, styles, bias, noise) against the
+    oracle's composition of the two reference ops, and against this package's own unfused composition."""
+    V = _ops()
+    from vfm_vae_b200.torch_utils.ops.modulated_conv2d import fused_synthesis_layer_train
+    g = torch.Generator().manual_seed(50)
+    N, I, O_, H, up = cfg['N'], cfg['I'], cfg['O_'], cfg['H'], cfg['up']
+    xq = torch.randn(N, I, H, H, generator=g).to(dtype).float()
+    w = torch.randn(O_, I, 3, 3, generator=g)
+    st = torch.randn(N, I, generator=g) + 1
+    b = (torch.randn(O_, generator=g) * 0.3).to(dtype).float()
+    f = O.setup_filter([1, 3, 3, 1]) if up == 2 else None
+    noise = None
+    if cfg['noise'] == 'const':
+        noise = torch.randn(H * up, H * up, generator=g) * 0.3
+    elif cfg['noise'] == 'random':
+        noise = torch.randn(N, 1, H * up, H * up, generator=g) * 0.3
+    lv = [xq, w, st, b] + ([noise] if noise is not None else [])
+    ref = [t.clone().double().requires_grad_(True) for t in lv]
+    yr = O.modulated_conv2d(ref[0], ref[1], ref[2], noise=(ref[4] if noise is not None else None), up=up, padding=1,
+                            resample_filter=(f.double() if f is not None else None), flip_weight=(up == 1))
+    yr = O.bias_act(yr, ref[3], act='lrelu', gain=cfg['gain'], clamp=cfg['clamp'])
+    dyq = torch.randn(yr.shape, generator=g).to(dtype).float()
+    gr = torch.autograd.grad(yr, ref, dyq.double())
+    dev = [xq.to(DEV, dtype).requires_grad_(True)] + [t.to(DEV).requires_grad_(True) for t in lv[1:]]
+    y = fused_synthesis_layer_train(dev[0], dev[1], dev[2], dev[3], noise=(dev[4] if noise is not None else None), up=up, padding=1,
+                                    resample_filter=(f.to(DEV) if f is not None else None), flip_weight=(up == 1), act='lrelu', gain=cfg['gain'], clamp=cfg['clamp'])
+    assert y is not None, 'expected the fused training kernel for this shape'
+    gg = torch.autograd.grad(y, dev, dyq.to(DEV, dtype))
+    tol = TOL[str(dtype).split('.')[-1]]
+    names = ['dx', 'dweight', 'dstyles', 'dbias', 'dnoise']
+    if dtype == torch.float16:
+        # fp16: the lrelu branch / clamp mask of an element is decided from the stored fp16 y, as in the reference kernels: elements within one
+        # fp16 ulp of 0 or +-clamp may take the other branch than the fp64 oracle; compare dx where the oracle's y is clear of both
+        yv = yr.detach().abs()
+        clear = (yv > 4e-3 * yv.max())
+        if cfg['clamp'] is not None:
+            clear &= ((yv - cfg['clamp']).abs() > 4e-3 * cfg['clamp'])
+        assert clear.float().mean() > 0.98
+    assert rel_err(y, yr) <= tol, 'y'
+    for a, b_, name in zip(gg, gr, names):
+        assert rel_err(a, b_) <= (tol if dtype == torch.float32 else 4e-3), name       # fp16 grads: flipped-branch elements included, see above
+    # and the unfused composition of this package (same kernels underneath): bias_act on the modulated conv
+    dev2 = [t.detach().clone().requires_grad_(True) for t in dev]
+    y2 = V.modulated_conv2d(dev2[0], dev2[1], dev2[2], noise=(dev2[4] if noise is not None else None), up=up, padding=1,
+                            resample_filter=(f.to(DEV) if f is not None else None), flip_weight=(up == 1))
+    y2 = V.bias_act.bias_act(y2, dev2[3].to(dtype), act='lrelu', gain=cfg['gain'], clamp=cfg['clamp'])
+    g2 = torch.autograd.grad(y2, dev2, dyq.to(DEV, dtype))
+    assert rel_err(y, y2) <= (1e-6 if dtype == torch.float32 else 1e-3)
+    for a, b_, name in zip(gg, g2, names):
+        assert rel_err(a, b_) <= (2e-5 if dtype == torch.float32 else 4e-3), name
+
+
 def test_tensor_core_path_is_taken_for_decoder_shapes():
     """The hot decoder layers must be routed to the tcgen05 kernel (and the odd shapes must not)."""
     from vfm_vae_b200.plugins import modconv_plugin as P

@@ -110,7 +110,8 @@ class ImageToU8Params(C.Structure):
 class ModconvBwdParams(C.Structure):
     _fields_ = [('d', ModconvDesc), ('dy', _vp), ('x', _vp), ('y', _vp), ('weight', _vp), ('styles', _vp),
                 ('noise', _vp), ('dcoefs', _vp), ('dx', _vp), ('dweight', _vp), ('dstyles', _vp), ('dnoise', _vp),
-                ('workspace', _vp), ('workspace_bytes', _sz), ('saved_operand', _vp), ('saved_operand_lo', _vp)]
+                ('workspace', _vp), ('workspace_bytes', _sz), ('saved_operand', _vp), ('saved_operand_lo', _vp),
+                ('ep_enable', _i32), ('ep_act', _i32), ('ep_alpha', _f64), ('ep_gain', _f64), ('ep_clamp', _f64), ('ep_bias', _vp), ('dbias_no', _vp)]
 
 
 class KernelStat(C.Structure):
@@ -132,6 +133,7 @@ SYMBOLS = {
     'vfm_modconv_forward': (C.c_int, [C.POINTER(ModconvFwdParams), _vp]),
     'vfm_modconv_backward': (C.c_int, [C.POINTER(ModconvBwdParams), _vp]),
     'vfm_modconv_uses_tensor_cores': (C.c_int, [C.POINTER(ModconvDesc)]),
+    'vfm_modconv_fused_backward_supported': (C.c_int, [C.POINTER(ModconvDesc)]),
     'vfm_modconv_forward_operand': (C.c_int, [C.POINTER(ModconvDesc), _vp, _sz, C.POINTER(_vp), C.POINTER(_vp)]),
     'vfm_group_norm_affine': (C.c_int, [C.POINTER(GroupNormAffineParams), _vp]),
     'vfm_group_norm_forward': (C.c_int, [C.POINTER(GroupNormParams), _vp]),
@@ -162,8 +164,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 7:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 7)')
+    if lib.vfm_abi_version() != 8:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 8)')
     _lib = lib
     return lib
 

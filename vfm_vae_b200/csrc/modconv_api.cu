@@ -16,6 +16,9 @@ int run_gsum(int dtype, const void* dy, const void* y, const float* noise, int64
 int run_dnoise(int dtype, const void* dy, int N, int O, int HW, int per_sample, float* dnoise, cudaStream_t stream);
 int run_gsum_dnoise(int dtype, const void* dy, const void* y, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
                     float* g, float* dnoise, int dnoise_per_sample, cudaStream_t stream);
+bool act_grad_fused_supported(int dtype, int O, int HW, const void* dy, const void* y, const void* dz);
+int run_act_grad_gsum_dnoise(int dtype, const void* dy, const void* y, const void* bias, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
+                             float gain, float alpha, float clamp, int act, void* dz, float* g, float* gz, float* dnoise, int dnoise_per_sample, cudaStream_t stream);
 int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream);
 int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, const float* dcoefs, const float* iscale, const float* wsq, int N, int O, int I, int demod, cudaStream_t stream);
 
@@ -118,10 +121,19 @@ extern "C" int vfm_modconv_forward_operand(const vfm_modconv_desc* dp, void* wor
 
 extern "C" size_t vfm_modconv_workspace_bytes(const vfm_modconv_desc* d, int direction) {
     if (!d) return 0;
-    size_t g = generic_workspace(*d, direction);
-    if (use_tc(*d)) g += tc_workspace_bytes(*d, direction);
-    if (use_pw(*d)) g += pw_workspace_bytes(*d, direction);
+    const int dir = direction == 2 ? 1 : direction;
+    size_t g = generic_workspace(*d, dir);
+    if (use_tc(*d)) g += tc_workspace_bytes(*d, dir);
+    if (use_pw(*d)) g += pw_workspace_bytes(*d, dir);
+    // fused-epilogue backward: the pre-activation gradient dz [N,O,Hout,Wout] lives in the workspace
+    if (direction == 2) g += (size_t)d->batch * d->out_channels * d->out_h * d->out_w * esize(d->dtype) + 512;
     return g;
+}
+
+extern "C" int vfm_modconv_fused_backward_supported(const vfm_modconv_desc* d) {
+    if (!d) return 0;
+    const int HW = d->out_h * d->out_w;
+    return ((d->dtype == VFM_F16 || d->dtype == VFM_F32) && HW % 8 == 0 && HW >= 2048 && (size_t)d->out_channels * 2 * sizeof(float) <= 48 * 1024) ? 1 : 0;
 }
 
 extern "C" int vfm_modconv_forward(const vfm_modconv_fwd_params* p, void* stream_) {
@@ -200,8 +212,13 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     VFM_CHECK_ARG(!d.demodulate || p->y, "modulated_conv2d backward: y (forward output) is required when demodulate is on");
     VFM_CHECK_ARG(!p->dstyles || p->dx, "modulated_conv2d backward: dstyles needs dx to be computed as well");
     VFM_CHECK_ARG(!p->dnoise || d.noise_mode != VFM_NOISE_NONE, "modulated_conv2d backward: dnoise requested without noise");
-    size_t need = vfm_modconv_workspace_bytes(&d, 1);
+    size_t need = vfm_modconv_workspace_bytes(&d, p->ep_enable ? 2 : 1);
     if (!p->workspace || p->workspace_bytes < need) { set_error("modulated_conv2d backward: workspace too small (%zu < %zu)", p->workspace_bytes, need); return VFM_ERR_WORKSPACE; }
+    if (p->ep_enable) {
+        VFM_CHECK_ARG(p->ep_act == 1 || p->ep_act == 3, "modulated_conv2d backward: the fused epilogue gradient supports linear and lrelu only");
+        VFM_CHECK_ARG(p->ep_gain > 0 && p->y, "modulated_conv2d backward: the fused epilogue gradient needs ep_gain > 0 and the activated output y");
+        if (!vfm_modconv_fused_backward_supported(&d)) { set_error("modulated_conv2d backward: no fused epilogue gradient for this descriptor"); return VFM_ERR_NO_KERNEL; }
+    }
 
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(p->workspace, p->workspace_bytes);
@@ -218,7 +235,18 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
 
     const int HWo = d.out_h * d.out_w;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)HWo : 0;
-    {
+    const void* dy_pre = p->dy;                 // gradient w.r.t. the conv output (before bias / activation)
+    if (p->ep_enable) {
+        // one pass: activation gradient -> dz (workspace), g, per-sample bias gradient, dnoise
+        void* dzp_act = cv.take<char>((size_t)N * O * HWo * esize(d.dtype));
+        const bool need_g = d.demodulate && (p->dweight || p->dstyles);
+        const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
+        if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
+        st = run_act_grad_gsum_dnoise(d.dtype, p->dy, p->y, p->ep_bias, p->noise, noise_sn, p->dcoefs, N, O, HWo, (float)p->ep_gain, (float)p->ep_alpha,
+                                      (float)p->ep_clamp, p->ep_act, dzp_act, need_g ? g : nullptr, p->dbias_no, p->dnoise, per_sample, stream);
+        if (st) return st;
+        dy_pre = dzp_act;
+    } else {
         const bool need_g = d.demodulate && (p->dweight || p->dstyles);
         const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
         if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
@@ -234,10 +262,10 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     }
 
     // gradient w.r.t. the stage-1 output
-    const void* dzp = p->dy;
+    const void* dzp = dy_pre;
     if (d.up == 2) {
         // backward of upfirdn2d (torch_utils/ops/upfirdn2d.py:251-269): swap up/down, flip the filter, same gain
-        st = call_upfirdn(d.dtype, p->dy, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
+        st = call_upfirdn(d.dtype, dy_pre, dz, d.resample_filter, d.fw, d.fh, 1, s.r_up, s.rb_px0, s.rb_py0, 1, (float)(d.up * d.up),
                           N, O, d.out_h, d.out_w, s.zh, s.zw, nullptr, 0, stream, 0, nullptr, dz_pitch);
         if (st) return st;
         dzp = dz;
@@ -245,7 +273,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     if (p->dstyles) VFM_CUDA_OK(cudaMemsetAsync(dsum, 0, sizeof(float) * (size_t)N * I, stream));
     if (p->dweight) VFM_CUDA_OK(cudaMemsetAsync(p->dweight, 0, sizeof(float) * (size_t)O * I * KK, stream));
 
-    if (use_pw(d) && aligned16(p->x) && aligned16(p->dy) && (!p->dx || aligned16(p->dx))) {
+    if (use_pw(d) && aligned16(p->x) && aligned16(dy_pre) && (!p->dx || aligned16(p->dx))) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = pw_stage1_backward(d, dzp, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
                                 (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream);

@@ -416,6 +416,85 @@ __global__ void __launch_bounds__(128) gsum_dnoise_kernel(const T* __restrict__ 
     }
 }
 
+// Training with the fused layer epilogue (y_act = clamp(gain * lrelu(conv * d + noise + b), +-clamp) written by the forward, nothing else
+// kept): the backward of bias_act (torch_utils/ops/bias_act.py:158-179) folded into the same single pass over the incoming gradient:
+//   dz       = dy_act * gain * (y_act > 0 ? 1 : alpha) * [|y_act| < clamp]           -> written out (the gradient w.r.t. the conv output)
+//   g[n,o]  += (1/d) * sum_p dz * (y_act / (gain * slope) - b[o] - noise)             (the pre-activation value recovered from y_act; where
+//                                                                                       the clamp saturated, dz = 0 and the term vanishes)
+//   gz[n,o] += sum_p dz   (bias gradient per sample)          dnoise[(n,)p] += sum_o dz
+// instead of bias_act_grad (2 reads + 1 write) followed by gsum_dnoise (2 reads): 2 reads + 1 write in total.
+template <class T>
+__global__ void __launch_bounds__(128) act_grad_gsum_dnoise_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ bias,
+                                                                   const float* __restrict__ noise, int64_t noise_sn, const float* __restrict__ dcoefs, int O, int HW,
+                                                                   float gain, float alpha, float clamp, int act, T* __restrict__ dz, float* g, float* gz,
+                                                                   float* dnoise, int64_t dnoise_sn) {
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int NV = 8 / V;
+    extern __shared__ float s_red[];                     // [2][O]: g and gz partials of this CTA
+    float* s_g = s_red;
+    float* s_z = s_red + O;
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * 1024 + threadIdx.x * 8;
+    const bool live = p0 < HW;
+    for (int o = threadIdx.x; o < 2 * O; o += blockDim.x) s_red[o] = 0.f;
+    __syncthreads();
+    float nz[8], dn[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { nz[i] = (noise && live) ? noise[(size_t)n * noise_sn + p0 + i] : 0.f; dn[i] = 0.f; }
+    const size_t base = (size_t)n * O * HW + p0;
+    const int lane = threadIdx.x & 31;
+    const float g_pos = gain, g_neg = (act == 3) ? gain * alpha : gain;
+    const float r_pos = 1.f / g_pos, r_neg = 1.f / g_neg;
+    for (int o0 = 0; o0 < O; o0 += 4) {
+        uint4 a[4][NV], b[4][NV];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const bool ok = live && o0 + k < O;
+                a[k][q] = ok ? ldg_stream(dy + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+                b[k][q] = ok ? ldg_stream(y + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float bo = (bias && o0 + k < O) ? to_acc(bias[o0 + k]) : 0.f;
+            float part = 0.f, zsum = 0.f;
+#pragma unroll
+            for (int q = 0; q < NV; q++) {
+                const T* av = (const T*)&a[k][q];
+                const T* bv = (const T*)&b[k][q];
+                struct alignas(16) { T e[V]; } out;
+#pragma unroll
+                for (int e = 0; e < V; e++) {
+                    const float ya = to_acc(bv[e]);
+                    const bool pos = ya > 0.f;
+                    float d = to_acc(av[e]) * (pos ? g_pos : g_neg);
+                    if (clamp >= 0.f && !(fabsf(ya) < clamp)) d = 0.f;
+                    const T dq = from_acc<T, float>(d);
+                    out.e[e] = dq;
+                    d = to_acc(dq);                              // downstream kernels see the rounded value: keep the reductions consistent with it
+                    dn[q * V + e] += d;
+                    zsum += d;
+                    part = fmaf(d, ya * (pos ? r_pos : r_neg) - bo - nz[q * V + e], part);
+                }
+                if (live && o0 + k < O) stg_stream(dz + base + (size_t)(o0 + k) * HW + q * V, *(const uint4*)&out);
+            }
+            part = warp_sum(part);
+            zsum = warp_sum(zsum);
+            if (lane == 0 && o0 + k < O) { atomicAdd(&s_g[o0 + k], part); atomicAdd(&s_z[o0 + k], zsum); }
+        }
+    }
+    if (dnoise && live) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) atomicAdd(&dnoise[(size_t)n * dnoise_sn + p0 + i], dn[i]);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+        if (g) atomicAdd(&g[(size_t)n * O + o], s_g[o] / dcoefs[(size_t)n * O + o]);
+        if (gz) atomicAdd(&gz[(size_t)n * O + o], s_z[o]);
+    }
+}
+
 // dW[o,i,k] = M[o,i,k] - a[o]^2 W[o,i,k] sum_n h[n,o] s'[n,i]^2,  h = g d^3          (thread per (o,i))
 __global__ void dw_fix_kernel(float* dw, const float* __restrict__ w, const float* __restrict__ a, const float* __restrict__ g,
                               const float* __restrict__ dcoefs, const float* __restrict__ iscale, int N, int O, int I, int KK) {
@@ -485,6 +564,28 @@ int run_gsum_dnoise(int dtype, const void* dy, const void* y, const float* noise
     else
         gsum_dnoise_kernel<float><<<grid, 128, O * sizeof(float), stream>>>((const float*)dy, g ? (const float*)y : nullptr, g ? noise : nullptr, noise_sn, dcoefs, O, HW, g, dnoise, dsn);
     return launch_status("modconv gsum_dnoise_kernel");
+}
+// fused backward of the layer epilogue (see act_grad_gsum_dnoise_kernel); g / gz are zero-initialised here, dnoise by the caller
+bool act_grad_fused_supported(int dtype, int O, int HW, const void* dy, const void* y, const void* dz) {
+    return (dtype == VFM_F16 || dtype == VFM_F32) && HW % 8 == 0 && HW >= 2048 && aligned16(dy) && aligned16(y) && aligned16(dz) && (size_t)O * 2 * sizeof(float) <= 48 * 1024;
+}
+int run_act_grad_gsum_dnoise(int dtype, const void* dy, const void* y, const void* bias, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
+                             float gain, float alpha, float clamp, int act, void* dz, float* g, float* gz, float* dnoise, int dnoise_per_sample, cudaStream_t stream) {
+    if (!act_grad_fused_supported(dtype, O, HW, dy, y, dz)) { set_error("modulated_conv2d backward: the fused epilogue gradient needs >= 2048 output pixels (a multiple of 8) and 16-byte aligned tensors"); return VFM_ERR_NO_KERNEL; }
+    if (g) VFM_CUDA_OK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)N * O, stream));
+    if (gz) VFM_CUDA_OK(cudaMemsetAsync(gz, 0, sizeof(float) * (size_t)N * O, stream));
+    dim3 grid(ceil_div(HW, 1024), N);
+    const double es = dtype == VFM_F16 ? 2.0 : 4.0;
+    KernelTimer timer("modconv_act_grad_gsum", stream, 0.0, (double)N * O * HW * es * 3.0, "o%dhw%d", O, HW);
+    const int64_t dsn = dnoise_per_sample ? HW : 0;
+    const size_t smem = (size_t)O * 2 * sizeof(float);
+    if (dtype == VFM_F16)
+        act_grad_gsum_dnoise_kernel<__half><<<grid, 128, smem, stream>>>((const __half*)dy, (const __half*)y, (const __half*)bias, noise, noise_sn, dcoefs, O, HW, gain, alpha, clamp, act,
+                                                                         (__half*)dz, g, gz, dnoise, dsn);
+    else
+        act_grad_gsum_dnoise_kernel<float><<<grid, 128, smem, stream>>>((const float*)dy, (const float*)y, (const float*)bias, noise, noise_sn, dcoefs, O, HW, gain, alpha, clamp, act,
+                                                                        (float*)dz, g, gz, dnoise, dsn);
+    return launch_status("modconv act_grad_gsum_dnoise_kernel");
 }
 int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream) {
     dw_fix_kernel<<<ceil_div(O * I, 256), 256, 0, stream>>>(dw, w, a, g, dcoefs, iscale, N, O, I, KK);

@@ -27,8 +27,10 @@ import torch.nn.functional as F
 
 def default_ops():
     from .torch_utils.ops import bias_act, upfirdn2d
-    from .torch_utils.ops.modulated_conv2d import modulated_conv2d, fused_modconv_bias_act, modulated_pointwise_conv2d, fused_convnext_mlp
-    return SimpleNamespace(fused_layer=fused_modconv_bias_act, bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
+    from .torch_utils.ops.modulated_conv2d import (modulated_conv2d, fused_modconv_bias_act, modulated_pointwise_conv2d, fused_convnext_mlp,
+                                                   fused_synthesis_layer_train)
+    return SimpleNamespace(fused_layer=fused_modconv_bias_act, fused_layer_train=None if os.environ.get('VFM_NO_FUSED_TRAIN') else fused_synthesis_layer_train,
+                           bias_act=bias_act.bias_act, def_gain=lambda act: bias_act.activation_funcs[act].def_gain,
                            setup_filter=upfirdn2d.setup_filter, upsample2d=upfirdn2d.upsample2d, blur2d_replicate=upfirdn2d.blur2d_replicate,
                            depthwise_conv2d=upfirdn2d.depthwise_conv2d, pixel_shuffle2=upfirdn2d.pixel_shuffle2,
                            modulated_conv2d=modulated_conv2d, modulated_pointwise_conv2d=modulated_pointwise_conv2d,
@@ -316,10 +318,18 @@ class SynthesisLayer(nn.Module):
                       residual=x if self.residual else None, gamma=self.gamma if self.residual else None, res_scale=float(np.sqrt(2)))
             if y is not None:
                 return y
-        y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                                      resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
-        y = y.to(dtype)
-        y = self.ops.bias_act(y, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+        y = None
+        fused_train = getattr(self.ops, 'fused_layer_train', None)
+        if fused_train is not None and torch.is_grad_enabled() and self.activation in ('linear', 'lrelu') and x.is_cuda:
+            # training: conv + noise + bias_act as ONE autograd node (only the activated output is written and kept; the bias_act gradient is
+            # folded into the backward's single pass over dy); None where the kernels do not fuse the shape
+            y = fused_train(x, self.weight, styles, self.bias, noise=noise, up=self.up, padding=self.padding, resample_filter=self.resample_filter,
+                            flip_weight=(self.up == 1), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
+        if y is None:
+            y = self.ops.modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                          resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+            y = y.to(dtype)
+            y = self.ops.bias_act(y, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=act_clamp)
         if self.residual:
             if y.is_cuda:
                 from .torch_utils.ops import layer_scale as _ls         # CUDA only: never reached by the CPU (oracle) runs

@@ -356,6 +356,12 @@ class _ModconvPlugin:
         return bool(_lib.load().vfm_modconv_uses_tensor_cores(C.byref(d)))
 
     @staticmethod
+    def fused_backward_supported(x, weight, up=1, padding=0, demodulate=True, flip_weight=True, noise=None, resample_filter=None):
+        """Can ``backward(epilogue=...)`` (fused training layer) take this call?"""
+        d = _ModconvPlugin._desc(x, weight, up, padding, demodulate, flip_weight, noise, resample_filter, False)
+        return bool(_lib.load().vfm_modconv_fused_backward_supported(C.byref(d)))
+
+    @staticmethod
     def group_norm_affine(x, weight, bias, num_groups, eps=1e-5):
         """GroupNorm statistics of x [N,C,H,W] as the per-(sample, channel) affine map (scale, shift), both fp32 [N,C]:
         group_norm(x) == x * scale[:, :, None, None] + shift[:, :, None, None]  (nn.GroupNorm evaluated in fp32)."""
@@ -441,9 +447,12 @@ class _ModconvPlugin:
 
     @staticmethod
     def backward(dy, x, y, weight, styles, noise, dcoefs, up, padding, resample_filter, demodulate, flip_weight,
-                 need_dx=True, need_dweight=True, need_dstyles=True, need_dnoise=False, force_generic=False, saved_operand=None):
-        """-> (dx or None, dweight fp32 or None, dstyles fp32 or None, dnoise fp32 or None).  ``saved_operand``: what ``forward(keep_operand=True)``
-        returned for the same x / styles (its workspace must still be alive and untouched)."""
+                 need_dx=True, need_dweight=True, need_dstyles=True, need_dnoise=False, force_generic=False, saved_operand=None, epilogue=None):
+        """-> (dx or None, dweight fp32 or None, dstyles fp32 or None, dnoise fp32 or None)   [, dbias_no fp32 [N,O]] with ``epilogue``.
+
+        ``saved_operand``: what ``forward(keep_operand=True)`` returned for the same x / styles (its workspace must still be alive and untouched).
+        ``epilogue`` (fused training layer): dict(act, alpha, gain, clamp, bias) of the forward's fused epilogue; ``dy`` / ``y`` then refer to the
+        ACTIVATED output and the bias_act backward is folded into the kernels (the fifth return value is the per-sample bias gradient)."""
         _ModconvPlugin._common_checks(x, weight, styles, noise, up, resample_filter)
         d = _ModconvPlugin._desc(x, weight, up, padding, demodulate, flip_weight, noise, resample_filter, force_generic)
         _check(dy.is_contiguous() and dy.dtype == x.dtype and tuple(dy.shape) == (d.batch, d.out_channels, d.out_h, d.out_w),
@@ -455,7 +464,7 @@ class _ModconvPlugin:
         dweight = torch.empty_like(weight) if need_dweight else None
         dstyles = torch.empty_like(styles) if need_dstyles else None
         dnoise = torch.empty_like(noise) if (need_dnoise and noise is not None) else None
-        nbytes = lib.vfm_modconv_workspace_bytes(C.byref(d), 1)
+        nbytes = lib.vfm_modconv_workspace_bytes(C.byref(d), 2 if epilogue is not None else 1)
         ws = torch.empty([nbytes], dtype=torch.uint8, device=x.device)
         p = _lib.ModconvBwdParams()
         p.d = d
@@ -464,8 +473,22 @@ class _ModconvPlugin:
         p.workspace, p.workspace_bytes = _ptr(ws), nbytes
         if saved_operand is not None:
             p.saved_operand, p.saved_operand_lo = saved_operand[1], saved_operand[2]
+        dbias = ebias = None
+        if epilogue is not None:
+            ebias = epilogue.get('bias')
+            _check(ebias is None or (ebias.dtype == x.dtype and ebias.is_contiguous() and ebias.numel() == d.out_channels), 'epilogue bias must be [O] in the dtype of x')
+            _check(y is not None and y.is_contiguous() and y.shape == dy.shape and y.dtype == x.dtype, 'the fused backward needs the activated output y')
+            dbias = torch.empty([d.batch, d.out_channels], dtype=torch.float32, device=x.device)
+            p.ep_enable = 1
+            p.ep_act = {'linear': 1, 'lrelu': 3}[epilogue.get('act', 'linear')]
+            p.ep_alpha, p.ep_gain = float(epilogue.get('alpha', 0.2)), float(epilogue.get('gain', 1.0))
+            clamp = epilogue.get('clamp')
+            p.ep_clamp = float(clamp) if clamp is not None else -1.0
+            p.ep_bias, p.dbias_no = _ptr(ebias), _ptr(dbias)
         with torch.cuda.device(x.device):
             _lib.check(lib.vfm_modconv_backward(C.byref(p), _stream(x)), 'modulated_conv2d backward')
+        if epilogue is not None:
+            return dx, dweight, dstyles, dnoise, dbias
         return dx, dweight, dstyles, dnoise
 
 

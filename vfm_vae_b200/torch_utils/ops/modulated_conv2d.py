@@ -93,16 +93,92 @@ class _ModulatedConv2d(torch.autograd.Function):
         if ds is not None:
             ds = ds.to(sd)
         if dn is not None:
-            # undo the broadcast of _noise_canon
-            shape = ctx.noise_shape
-            full = dn if dn.dim() == 4 else dn[None, None]
-            while full.dim() > len(shape):
-                full = full.sum(0)
-            for i, sz in enumerate(shape):
-                if sz == 1 and full.shape[i] != 1:
-                    full = full.sum(i, keepdim=True)
-            dn = full.reshape(shape).to(nd)
+            dn = _undo_noise_broadcast(dn, ctx.noise_shape, nd)
         return dx, dw, ds, dn, None, None, None, None, None
+
+
+def _undo_noise_broadcast(dn, shape, dtype):
+    """gradient of the canonical [H,W] / [N,1,H,W] noise -> the shape the caller passed"""
+    full = dn if dn.dim() == 4 else dn[None, None]
+    while full.dim() > len(shape):
+        full = full.sum(0)
+    for i, sz in enumerate(shape):
+        if sz == 1 and full.shape[i] != 1:
+            full = full.sum(i, keepdim=True)
+    return full.reshape(shape).to(dtype)
+
+
+class _FusedModconvBiasAct(torch.autograd.Function):
+    """One legacy synthesis layer for TRAINING: modulated conv + noise + bias_act (networks/generator.py:264-270) as one autograd node.
+    Forward = the conv (blur for up=2) kernel with the bias / lrelu / gain / clamp epilogue: only the activated output is written and kept.
+    Backward = the bias_act gradient folded into the single pass over the incoming gradient that the demodulation / noise reductions make
+    anyway (csrc/modconv_generic.cu act_grad_gsum_dnoise_kernel), then the usual data / weight gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, styles, bias, noise, up, padding, resample_filter, flip_weight, act, alpha, gain, clamp):
+        n = x.shape[0]
+        xc = x.contiguous()
+        w32 = weight.detach().to(torch.float32).contiguous()
+        s32 = styles.detach().to(torch.float32).contiguous()
+        f32 = resample_filter.to(device=x.device, dtype=torch.float32).contiguous() if (up > 1 and resample_filter is not None) else None
+        kh, kw = weight.shape[2], weight.shape[3]
+        oh = x.shape[2] * up + 2 * padding - (kh - 1)
+        ow = x.shape[3] * up + 2 * padding - (kw - 1)
+        n32 = _noise_canon(noise.detach() if noise is not None else None, n, oh, ow)
+        b = bias.detach().to(x.dtype).contiguous() if bias is not None else None
+        ep = dict(act=act, alpha=alpha, gain=gain, clamp=clamp, bias=b)
+        keep = bool(keep_forward_operand and ctx.needs_input_grad[1])
+        out = _plugin.forward(xc, w32, s32, n32, up, padding, f32, True, flip_weight, False, epilogue=ep, keep_operand=keep)
+        if out is None:
+            raise RuntimeError('fused synthesis layer: no kernel fuses this call (checked by the caller)')
+        y, dcoefs = out[0], out[1]
+        ctx.saved_operand = out[2] if keep else None
+        ctx.save_for_backward(xc, w32, s32, n32 if n32 is not None else torch.empty([0]), dcoefs, y, f32 if f32 is not None else torch.empty([0]),
+                              b if b is not None else torch.empty([0]))
+        ctx.cfg = (up, padding, flip_weight, act, alpha, gain, clamp)
+        ctx.in_dtypes = (weight.dtype, styles.dtype, bias.dtype if bias is not None else None, noise.dtype if noise is not None else None)
+        ctx.noise_shape = tuple(noise.shape) if noise is not None else None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        xc, w32, s32, n32, dcoefs, y, f32, b = ctx.saved_tensors
+        up, padding, flip_weight, act, alpha, gain, clamp = ctx.cfg
+        n32 = n32 if n32.numel() else None
+        f32 = f32 if f32.numel() else None
+        b = b if b.numel() else None
+        need = ctx.needs_input_grad
+        dx, dw, ds, dn, db_no = _plugin.backward(dy.contiguous(), xc, y, w32, s32, n32, dcoefs, up, padding, f32, True, flip_weight,
+                                                 need_dx=need[0], need_dweight=need[1], need_dstyles=need[2], need_dnoise=(need[4] and n32 is not None),
+                                                 saved_operand=ctx.saved_operand, epilogue=dict(act=act, alpha=alpha, gain=gain, clamp=clamp, bias=b))
+        ctx.saved_operand = None
+        wd, sd, bd, nd = ctx.in_dtypes
+        dx = dx if need[0] else None
+        dw = dw.to(wd) if dw is not None else None
+        ds = ds.to(sd) if ds is not None else None
+        db = db_no.sum(0).to(bd) if (need[3] and bd is not None) else None
+        dn = _undo_noise_broadcast(dn, ctx.noise_shape, nd) if dn is not None else None
+        return dx, dw, ds, db, dn, None, None, None, None, None, None, None, None
+
+
+def fused_synthesis_layer_train(x, weight, styles, bias, noise=None, up=1, padding=0, resample_filter=None, flip_weight=True, act='lrelu', alpha=0.2,
+                                gain=1.0, clamp=None):
+    """Training-time fusion of ``bias_act(modulated_conv2d(x, weight, styles, noise, up, ...), bias, act, gain, clamp)`` (demodulated 3x3 layers of
+    the legacy decoder) with full first-order autograd for x, weight, styles, bias and noise.  Returns None when the kernels cannot fuse the
+    call (the caller then composes the two ops as the reference does): needs CUDA fp16 / fp32, the tcgen05 path, act in {linear, lrelu},
+    gain > 0 and >= 2048 output pixels."""
+    if x.device.type != 'cuda' or act not in ('linear', 'lrelu') or not gain > 0 or x.dtype not in (torch.float16, torch.float32) or force_generic:
+        return None
+    _init()
+    xs = x.detach()
+    w32 = weight.detach().to(torch.float32)
+    f32 = resample_filter.to(device=x.device, dtype=torch.float32).contiguous() if (up > 1 and resample_filter is not None) else None
+    kw = dict(up=int(up), padding=int(padding), demodulate=True, flip_weight=bool(flip_weight), resample_filter=f32)
+    if not (_plugin.uses_tensor_cores(xs, w32, **kw) and _plugin.fused_backward_supported(xs, w32, **kw)):
+        return None
+    return _FusedModconvBiasAct.apply(x, weight, styles, bias, noise, int(up), int(padding), resample_filter, bool(flip_weight), act, float(alpha),
+                                      float(gain), None if clamp is None else float(clamp))
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,

@@ -445,24 +445,28 @@ __global__ void __launch_bounds__(128) act_grad_gsum_dnoise_kernel(const T* __re
     const int lane = threadIdx.x & 31;
     const float g_pos = gain, g_neg = (act == 3) ? gain * alpha : gain;
     const float r_pos = 1.f / g_pos, r_neg = 1.f / g_neg;
-    for (int o0 = 0; o0 < O; o0 += 4) {
-        uint4 a[4][NV], b[4][NV];
+    // software pipeline over groups of 4 channels: the loads of group k+1 are issued before group k is consumed
+    uint4 a[2][4][NV], b[2][4][NV];
+    auto fetch = [&](int o0, int slot) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
 #pragma unroll
             for (int q = 0; q < NV; q++) {
                 const bool ok = live && o0 + k < O;
-                a[k][q] = ok ? ldg_stream(dy + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
-                b[k][q] = ok ? ldg_stream(y + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+                a[slot][k][q] = ok ? ldg_stream(dy + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
+                b[slot][k][q] = ok ? ldg_stream(y + base + (size_t)(o0 + k) * HW + q * V) : make_uint4(0, 0, 0, 0);
             }
+    };
+    auto consume = [&](int o0, int slot) {
+        float red[8];                                        // [part of channel 0..3 | zsum of channel 0..3]
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const float bo = (bias && o0 + k < O) ? to_acc(bias[o0 + k]) : 0.f;
             float part = 0.f, zsum = 0.f;
 #pragma unroll
             for (int q = 0; q < NV; q++) {
-                const T* av = (const T*)&a[k][q];
-                const T* bv = (const T*)&b[k][q];
+                const T* av = (const T*)&a[slot][k][q];
+                const T* bv = (const T*)&b[slot][k][q];
                 struct alignas(16) { T e[V]; } out;
 #pragma unroll
                 for (int e = 0; e < V; e++) {
@@ -479,10 +483,39 @@ __global__ void __launch_bounds__(128) act_grad_gsum_dnoise_kernel(const T* __re
                 }
                 if (live && o0 + k < O) stg_stream(dz + base + (size_t)(o0 + k) * HW + q * V, *(const uint4*)&out);
             }
-            part = warp_sum(part);
-            zsum = warp_sum(zsum);
-            if (lane == 0 && o0 + k < O) { atomicAdd(&s_g[o0 + k], part); atomicAdd(&s_z[o0 + k], zsum); }
+            red[k] = part; red[4 + k] = zsum;
         }
+        // 8 sums over the warp with 9 shuffles instead of 40: halve the value set while halving the lane set (bits 16, 8, 4), then two
+        // plain butterfly steps; lane L ends up with the total of value index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+        float v4[4], v2[2], v1;
+        {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float send = hi ? red[i] : red[4 + i]; const float keep = hi ? red[4 + i] : red[i]; v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+        }
+        {
+            const bool hi = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 2; i++) { const float send = hi ? v4[i] : v4[2 + i]; const float keep = hi ? v4[2 + i] : v4[i]; v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+        }
+        {
+            const bool hi = lane & 4;
+            const float send = hi ? v2[0] : v2[1]; const float keep = hi ? v2[1] : v2[0];
+            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        if ((lane & 3) == 0) {
+            const int k = ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (o0 + k < O) atomicAdd(((lane & 16) ? s_z : s_g) + o0 + k, v1);
+        }
+    };
+    fetch(0, 0);
+    for (int o0 = 0; o0 < O; o0 += 8) {
+        if (o0 + 4 < O) fetch(o0 + 4, 1);
+        consume(o0, 0);
+        if (o0 + 8 < O) fetch(o0 + 8, 0);
+        if (o0 + 4 < O) consume(o0 + 4, 1);
     }
     if (dnoise && live) {
 #pragma unroll

@@ -140,16 +140,15 @@ __global__ void __launch_bounds__(512) gn_bwd_reduce_kernel(const T* __restrict_
         float a1 = 0.f, a2 = 0.f;
         if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
             const int64_t nvec = HW / V;
-            constexpr int UN = 4;                    // 2 x UN independent 16-byte loads in flight per thread
-            for (int64_t v0 = threadIdx.x; v0 < nvec; v0 += (int64_t)blockDim.x * UN) {
-                uint4 ud[UN], ux[UN];
+            for (int64_t v0 = threadIdx.x; v0 < nvec; v0 += (int64_t)blockDim.x * 2) {
+                uint4 ud[2], ux[2];
 #pragma unroll
-                for (int u = 0; u < UN; u++) {
+                for (int u = 0; u < 2; u++) {
                     const int64_t v = v0 + (int64_t)u * blockDim.x;
                     if (v < nvec) { ud[u] = ldg_stream((const uint4*)dyp + v); ux[u] = ldg_stream((const uint4*)xp + v); }
                 }
 #pragma unroll
-                for (int u = 0; u < UN; u++) {
+                for (int u = 0; u < 2; u++) {
                     if (v0 + (int64_t)u * blockDim.x >= nvec) continue;
                     const T* ed = (const T*)&ud[u];
                     const T* ex = (const T*)&ux[u];

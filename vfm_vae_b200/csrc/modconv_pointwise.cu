@@ -37,24 +37,15 @@ __global__ void __launch_bounds__(256) pw_fwd_kernel(const T* __restrict__ x, co
         for (int v = 0; v < VEC; v++) acc[o][v] = 0.f;
     const T* xp = x + (size_t)n * C * HW + p0;
     struct alignas(16) Vec { T e[VEC]; };
-    // the op is one read of x: keep CB independent 16-byte loads (one per channel plane) in flight per thread -- a loop that loads and
-    // consumes one plane at a time leaves the kernel latency-bound at a third of the HBM rate
-    constexpr int CB = 8;
-    for (int c0 = 0; c0 < C; c0 += CB) {
-        uint4 raw[CB];
+#pragma unroll 4
+    for (int c = 0; c < C; c++) {
+        Vec xv;
+        *(uint4*)&xv = ldg_stream((const uint4*)(xp + (size_t)c * HW));
+        const float4 wv = *(const float4*)&s_w[c * OMAX];
 #pragma unroll
-        for (int j = 0; j < CB; j++) raw[j] = (c0 + j < C) ? ldg_stream((const uint4*)(xp + (size_t)(c0 + j) * HW)) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < CB; j++) {
-            const int c = (c0 + j < C) ? c0 + j : C - 1;
-            const float4 wv = (c0 + j < C) ? *(const float4*)&s_w[c * OMAX] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const T* xe = (const T*)&raw[j];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                const float xf = to_acc(xe[v]);
-                acc[0][v] = fmaf(wv.x, xf, acc[0][v]); acc[1][v] = fmaf(wv.y, xf, acc[1][v]);
-                acc[2][v] = fmaf(wv.z, xf, acc[2][v]); acc[3][v] = fmaf(wv.w, xf, acc[3][v]);
-            }
+        for (int v = 0; v < VEC; v++) {
+            const float xf = to_acc(xv.e[v]);
+            acc[0][v] += wv.x * xf; acc[1][v] += wv.y * xf; acc[2][v] += wv.z * xf; acc[3][v] += wv.w * xf;
         }
     }
     for (int o = 0; o < O; o++) {
@@ -114,28 +105,16 @@ __global__ void __launch_bounds__(256) pw_corr_kernel(const T* __restrict__ dy, 
     const T* dyp = dy + (size_t)n * O * HW;
     struct alignas(16) Vec { T e[VEC]; };
     float acc[OMAX] = {0.f, 0.f, 0.f, 0.f};
-    // PB chunks of the x plane (HBM) and of the <= 4 dy planes (L2: every channel block re-reads them) in flight per thread
-    constexpr int PB = 4;
-    const int step = blockDim.x * VEC;
-    for (int pb = threadIdx.x * VEC; pb < HW; pb += step * PB) {
-        uint4 xr[PB], dr[PB][OMAX];
+    for (int p0 = threadIdx.x * VEC; p0 < HW; p0 += blockDim.x * VEC) {
+        Vec xv;
+        *(uint4*)&xv = ldg_stream((const uint4*)(xp + p0));
 #pragma unroll
-        for (int j = 0; j < PB; j++) {
-            const int p0 = pb + j * step;
-            const bool ok = p0 < HW;
-            xr[j] = ok ? ldg_stream((const uint4*)(xp + p0)) : make_uint4(0, 0, 0, 0);
+        for (int o = 0; o < OMAX; o++) {
+            if (o >= O) break;
+            Vec dv;
+            *(uint4*)&dv = *(const uint4*)(dyp + (size_t)o * HW + p0);     // re-read per channel block: stays in L2
 #pragma unroll
-            for (int o = 0; o < OMAX; o++) dr[j][o] = (ok && o < O) ? *(const uint4*)(dyp + (size_t)o * HW + p0) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int j = 0; j < PB; j++) {
-            const T* xe = (const T*)&xr[j];
-#pragma unroll
-            for (int o = 0; o < OMAX; o++) {
-                const T* de = (const T*)&dr[j][o];
-#pragma unroll
-                for (int v = 0; v < VEC; v++) acc[o] = fmaf(to_acc(xe[v]), to_acc(de[v]), acc[o]);
-            }
+            for (int v = 0; v < VEC; v++) acc[o] += to_acc(xv.e[v]) * to_acc(dv.e[v]);
         }
     }
     for (int o = 0; o < O; o++) {

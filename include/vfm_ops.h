@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 8
+#define VFM_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -183,6 +183,10 @@ typedef struct {
     int32_t      s_w_bytes, s_h;   /* sign tensor row length in bytes and height */
     int32_t      s_ofs_x, s_ofs_y; /* offset between upsampled coordinates and sign coordinates */
     int32_t      s_w_active;       /* active width in ELEMENTS (write: yw*down-(down-1)+fd_w-1; read: s_w_bytes*4) */
+    /* Extension (NULL = off): fp32 [C], ACCUMULATED into (pass zeros): y_sum[c] += sum over n, h, w of the stored output.  In the backward
+     * pass (the same op with up/down swapped, filtered_lrelu.py:252-263) the output is dx, so this is the bias gradient
+     * db = dx.sum([0,2,3]) of filtered_lrelu.py:266 without a second pass over dx. */
+    float*       y_sum;
 } vfm_filtered_lrelu_params;
 
 VFM_API int vfm_filtered_lrelu(const vfm_filtered_lrelu_params* p, void* stream);

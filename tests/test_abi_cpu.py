@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vfm_abi_version() == 8
+    assert lib.vfm_abi_version() == 9
     assert _lib.last_error() == ''
 
 

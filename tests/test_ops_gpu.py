@@ -449,6 +449,30 @@ def test_filtered_lrelu_composed_fallback():
     assert rel_err(dx, dxr) <= 2e-5
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [dict(up=2, down=2, taps=12, pad=[10, 11, 10, 11]), dict(up=1, down=2, taps=8, pad=[3, 4, 3, 4]),
+                                 dict(up=2, down=1, taps=5, pad=2, two_d=True)], ids=lambda c: f"up{c['up']}down{c['down']}t{c['taps']}")
+def test_filtered_lrelu_fused_bias_gradient(cfg, dtype):
+    """db comes out of the backward kernel itself (y_sum accumulation) -- it must equal dx.sum([0, 2, 3]) (reference filtered_lrelu.py:266);
+    under create_graph the wrapper switches to the differentiable reduction and second-order gradients flow."""
+    V = _ops()
+    g = torch.Generator().manual_seed(60)
+    x = torch.randn(3, 6, 24, 20, generator=g).to(dtype).to(DEV).requires_grad_(True)
+    b = (torch.randn(6, generator=g) * 0.5).to(dtype).to(DEV).requires_grad_(True)
+    f1 = O.setup_filter(list(range(1, cfg['taps'] + 1)))
+    f = (torch.outer(f1, f1) if cfg.get('two_d') and f1.ndim == 1 else f1).to(DEV)
+    y = V.filtered_lrelu.filtered_lrelu(x, f, f, b, up=cfg['up'], down=cfg['down'], padding=cfg['pad'], clamp=0.8)
+    dy = torch.randn(y.shape, generator=g).to(dtype).to(DEV)
+    dx, db = torch.autograd.grad(y, [x, b], dy, retain_graph=True)
+    want = dx.float().sum([0, 2, 3])
+    assert db.dtype == b.dtype and rel_err(db, want) <= (1e-5 if dtype == torch.float32 else 1e-3)
+    if dtype == torch.float32:
+        dx2, db2 = torch.autograd.grad(y, [x, b], dy, create_graph=True)
+        assert rel_err(db2, want) <= 1e-5 and db2.requires_grad
+        (gx2,) = torch.autograd.grad(dx2.square().sum() + db2.sum(), [x], allow_unused=True)      # double backward runs (lrelu is piecewise linear: zero or finite)
+        assert gx2 is None or torch.isfinite(gx2).all()
+
+
 # --------------------------------------------------------------------------------------------- modulated_conv2d
 
 @pytest.mark.parametrize('case', _cases('modulated_conv2d'), ids=lambda c: f"{c['key']}-{c['dtype']}")

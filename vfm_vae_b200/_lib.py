@@ -47,7 +47,7 @@ class FilteredLreluParams(C.Structure):
                 ('y_w', _i32), ('y_h', _i32),
                 ('y_stride_w', _i64), ('y_stride_h', _i64), ('y_stride_c', _i64), ('y_stride_n', _i64),
                 ('b_stride', _i64), ('s_w_bytes', _i32), ('s_h', _i32), ('s_ofs_x', _i32), ('s_ofs_y', _i32),
-                ('s_w_active', _i32)]
+                ('s_w_active', _i32), ('y_sum', _vp)]
 
 
 class FilteredLreluActParams(C.Structure):
@@ -164,8 +164,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 8:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 8)')
+    if lib.vfm_abi_version() != 9:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 9)')
     _lib = lib
     return lib
 

@@ -32,12 +32,29 @@ struct FlrArgs {
     int64_t ysw, ysh, ysc, ysn;
     int64_t b_stride;
     int s_w_bytes, s_h, s_ofs_x, s_ofs_y, s_w_active;
+    float* ysum;             // optional [channels] fp32: += sum of the (rounded) outputs of each plane: the fused bias gradient of the backward pass
     // tiling (host-computed)
     int tow, toh;            // output tile
     int tuw, tuh;            // upsampled tile (tuw multiple of 4)
     int tiw, tih;            // input tile
     int tiles_x, tiles_y;
 };
+
+// sum of a per-thread partial over the 256-thread CTA -> one atomicAdd into ysum[c] (fused db = dx.sum([0,2,3]) of the backward pass,
+// reference filtered_lrelu.py:266).  Called by every thread of the CTA after its last store.
+__device__ __forceinline__ void flr_accumulate_ysum(float* ysum, int c, float part) {
+    __shared__ float s_part[8];
+    part = warp_sum(part);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += s_part[w];
+        atomicAdd(&ysum[c], t);
+    }
+}
 
 // SIGN: 0 = none, 1 = write, 2 = read
 template <class T, int SIGN>
@@ -59,6 +76,7 @@ __global__ void __launch_bounds__(256) filtered_lrelu_kernel(FlrArgs p) {
     const int tile_x = (int)(bid % p.tiles_x); bid /= p.tiles_x;
     const int tile_y = (int)(bid % p.tiles_y); bid /= p.tiles_y;
     const int c = (int)(bid % p.channels), n = (int)(bid / p.channels);
+    float ysum_part = 0.f;                 // this thread's share of sum(y) over the plane (p.ysum)
     const int64_t plane = (int64_t)n * p.channels + c;
 
     // ---- taps as correlation taps (flip == 0 means true convolution -> reverse) ----
@@ -191,7 +209,9 @@ __global__ void __launch_bounds__(256) filtered_lrelu_kernel(FlrArgs p) {
             const float* col = s_dx + (roy * p.down) * p.tow + rox;
             float acc = 0.f;
             for (int t = 0; t < fdh; t++) acc += s_fd[t] * col[t * p.tow];
-            yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = from_acc<T, float>(acc);
+            const T q = from_acc<T, float>(acc);
+            yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = q;
+            ysum_part += to_acc(q);
         }
     } else {
         for (int i = tid; i < p.toh * p.tow; i += nthr) {
@@ -202,9 +222,12 @@ __global__ void __launch_bounds__(256) filtered_lrelu_kernel(FlrArgs p) {
             float acc = 0.f;
             for (int ty = 0; ty < fdh; ty++)
                 for (int tx = 0; tx < p.fd_w; tx++) acc += s_fd[ty * p.fd_w + tx] * base[ty * p.tuw + tx];
-            yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = from_acc<T, float>(acc);
+            const T q = from_acc<T, float>(acc);
+            yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = q;
+            ysum_part += to_acc(q);
         }
     }
+    if (p.ysum) flr_accumulate_ysum(p.ysum, c, ysum_part);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -268,6 +291,7 @@ __global__ void __launch_bounds__(256) flr_sep_kernel(FlrArgs p) {
     const int tile_x = (int)(bid % p.tiles_x); bid /= p.tiles_x;
     const int tile_y = (int)(bid % p.tiles_y); bid /= p.tiles_y;
     const int c = (int)(bid % p.channels), n = (int)(bid / p.channels);
+    float ysum_part = 0.f;                 // this thread's share of sum(y) over the plane (p.ysum)
     const int64_t plane = (int64_t)n * p.channels + c;
 
     // correlation taps (flip == 0 means true convolution -> reversed), zero-extended to the padded counts
@@ -419,11 +443,12 @@ __global__ void __launch_bounds__(256) flr_sep_kernel(FlrArgs p) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     const int ox = ox0 + 4 * g4 + k;
-                    if (ox < p.y_w) yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = from_acc<T, float>(o[k]);
+                    if (ox < p.y_w) { const T q = from_acc<T, float>(o[k]); yp[(int64_t)oy * p.ysh + (int64_t)ox * p.ysw] = q; ysum_part += to_acc(q); }
                 }
             }
         }
     }
+    if (p.ysum) flr_accumulate_ysum(p.ysum, c, ysum_part);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -569,6 +594,7 @@ extern "C" int vfm_filtered_lrelu(const vfm_filtered_lrelu_params* p, void* stre
     a.ysw = p->y_stride_w; a.ysh = p->y_stride_h; a.ysc = p->y_stride_c; a.ysn = p->y_stride_n;
     a.b_stride = p->b_stride;
     a.s_w_bytes = p->s_w_bytes; a.s_h = p->s_h; a.s_ofs_x = p->s_ofs_x; a.s_ofs_y = p->s_ofs_y; a.s_w_active = p->s_w_active;
+    a.ysum = p->y_sum;
 
     {
         const int sign = p->write_signs ? 1 : (p->read_signs ? 2 : 0);

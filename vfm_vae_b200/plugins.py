@@ -199,7 +199,9 @@ class _Upfirdn2dPlugin:
 
 class _FilteredLreluPlugin:
     @staticmethod
-    def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns):
+    def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filters, writeSigns, y_sum=None):
+        """``y_sum`` (extension): optional zero-initialised fp32 [C] tensor that receives the per-channel sum of the output (the fused bias
+        gradient when this call is the backward pass)."""
         _check(x.is_cuda, 'x must reside on CUDA device')
         _check(fu.device == x.device and fd.device == x.device and b.device == x.device, 'all input tensors must reside on the same device')
         _check(fu.dtype == torch.float32 and fd.dtype == torch.float32, 'fu and fd must be float32')
@@ -266,6 +268,10 @@ class _FilteredLreluPlugin:
         p.s_w_bytes, p.s_h = (s.size(3), s.size(2)) if (read_signs or writeSigns) else (0, 0)
         p.s_ofs_x, p.s_ofs_y = int(sx), int(sy)
         p.s_w_active = int(sw_active)
+        if y_sum is not None:
+            _check(y_sum.dtype == torch.float32 and y_sum.is_contiguous() and y_sum.device == x.device and y_sum.numel() == x.size(1),
+                   'y_sum must be a contiguous float32 [C] tensor on the device of x')
+            p.y_sum = _ptr(y_sum)
         with torch.cuda.device(x.device):
             st = lib.vfm_filtered_lrelu(C.byref(p), _stream(x))
         if st == _lib.VFM_ERR_NO_KERNEL:

@@ -467,10 +467,12 @@ def test_filtered_lrelu_fused_bias_gradient(cfg, dtype):
     want = dx.float().sum([0, 2, 3])
     assert db.dtype == b.dtype and rel_err(db, want) <= (1e-5 if dtype == torch.float32 else 1e-3)
     if dtype == torch.float32:
-        dx2, db2 = torch.autograd.grad(y, [x, b], dy, create_graph=True)
+        # higher-order use (create_graph): db is then the differentiable reduction of dx and gradients flow back to the incoming dy
+        dy2 = dy.clone().requires_grad_(True)
+        dx2, db2 = torch.autograd.grad(y, [x, b], dy2, create_graph=True)
         assert rel_err(db2, want) <= 1e-5 and db2.requires_grad
-        (gx2,) = torch.autograd.grad(dx2.square().sum() + db2.sum(), [x], allow_unused=True)      # double backward runs (lrelu is piecewise linear: zero or finite)
-        assert gx2 is None or torch.isfinite(gx2).all()
+        (g_dy,) = torch.autograd.grad(db2.sum(), [dy2])
+        assert g_dy.shape == dy.shape and torch.isfinite(g_dy).all() and g_dy.abs().max() > 0
 
 
 # --------------------------------------------------------------------------------------------- modulated_conv2d

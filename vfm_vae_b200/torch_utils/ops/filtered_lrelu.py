@@ -107,7 +107,7 @@ class _FilteredLRelu(torch.autograd.Function):
             so = _plugin.filtered_lrelu_act_(y, si, sofs[0], sofs[1], op.gain, op.slope, op.clamp, writing)
             y = upfirdn2d.upfirdn2d(x=y, f=fd, down=op.down, flip_filter=op.flip)
             if want_sum:
-                y_sum = y.sum([0, 2, 3], dtype=torch.float32)
+                y_sum = y.sum([0, 2, 3])                     # in y's own dtype: fp64 inputs take this route and keep their precision
         ctx.save_for_backward(fu, fd, signs if reading else so)
         ctx.op, ctx.sofs = op, sofs
         ctx.x_hw, ctx.y_hw = tuple(x.shape[2:]), tuple(y.shape[2:])

@@ -26,6 +26,7 @@ ap.add_argument('--batch', type=int, default=64)
 ap.add_argument('--mode', default='fwd')
 ap.add_argument('--dtype', default='f16')
 ap.add_argument('--iters', type=int, default=3)
+ap.add_argument('--warm', type=int, default=2, help='untimed warm-up runs (0 for ncu captures)')
 a = ap.parse_args()
 dev = 'cuda'
 dt = torch.float16 if a.dtype == 'f16' else torch.float32
@@ -58,7 +59,7 @@ def run():
     return torch.autograd.grad(y, [xg, wg, sg], torch.ones_like(y))
 
 
-for _ in range(2):
+for _ in range(a.warm):
     run()
 ts = []
 for _ in range(a.iters):

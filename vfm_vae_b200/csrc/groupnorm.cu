@@ -130,44 +130,54 @@ __global__ void __launch_bounds__(512) gn_bwd_reduce_kernel(const T* __restrict_
     const int n = blockIdx.x / groups, g = blockIdx.x - n * groups;
     const int cpg = C / groups;
     const float mu = mean[blockIdx.x], rs = rstd[blockIdx.x];
-    __shared__ float red[2][32];
-    __shared__ float s_c1[64], s_c2[64];           // cpg <= 64 (checked on the host)
+    // The 16 warps form `teams` = min(cpg, 16) teams of TS warps; a team owns the channels c = team (mod teams) and reduces them with
+    // shuffles only, so no CTA barrier sits between channels: the layers with many channels per group and few pixels (8x8 .. 32x32)
+    // reduce up to 16 channels at once instead of one after the other with two barriers each.
+    __shared__ float s_part[2][64][16];            // [sum dy | sum dy*(x-mu)][channel][warp of the team]; cpg <= 64 (checked on the host)
+    __shared__ float s_c1[64], s_c2[64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = 0; c < cpg; c++) {
-        const int ch = g * cpg + c;
-        const T* dyp = dy + ((int64_t)n * C + ch) * HW;
-        const T* xp = x + ((int64_t)n * C + ch) * HW;
-        float a1 = 0.f, a2 = 0.f;
-        if ((HW % V) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) {
-            const int64_t nvec = HW / V;
-            for (int64_t v0 = threadIdx.x; v0 < nvec; v0 += (int64_t)blockDim.x * 2) {
-                uint4 ud[2], ux[2];
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int teams = cpg < nwarps ? cpg : nwarps;
+    const int TS = nwarps / teams;
+    const int team = warp / TS, wt = warp - team * TS;
+    const bool vec_ok = (HW % V) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0;
+    if (team < teams) {
+        for (int c = team; c < cpg; c += teams) {
+            const int ch = g * cpg + c;
+            const T* dyp = dy + ((int64_t)n * C + ch) * HW;
+            const T* xp = x + ((int64_t)n * C + ch) * HW;
+            float a1 = 0.f, a2 = 0.f;
+            if (vec_ok) {
+                const int nvec = (int)(HW / V);          // a plane has < 2^31 vectors
+                const int step = TS * 32;
+                for (int v0 = wt * 32 + lane; v0 < nvec; v0 += step * 2) {
+                    uint4 ud[2], ux[2];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const int64_t v = v0 + (int64_t)u * blockDim.x;
-                    if (v < nvec) { ud[u] = ldg_stream((const uint4*)dyp + v); ux[u] = ldg_stream((const uint4*)xp + v); }
+                    for (int u = 0; u < 2; u++) {
+                        const int v = v0 + u * step;
+                        if (v < nvec) { ud[u] = ldg_stream((const uint4*)dyp + v); ux[u] = ldg_stream((const uint4*)xp + v); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (v0 + u * step >= nvec) continue;
+                        const T* ed = (const T*)&ud[u];
+                        const T* ex = (const T*)&ux[u];
+#pragma unroll
+                        for (int k = 0; k < V; k++) { const float d = to_acc(ed[k]); a1 += d; a2 = fmaf(d, to_acc(ex[k]) - mu, a2); }
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    if (v0 + (int64_t)u * blockDim.x >= nvec) continue;
-                    const T* ed = (const T*)&ud[u];
-                    const T* ex = (const T*)&ux[u];
-#pragma unroll
-                    for (int k = 0; k < V; k++) { const float d = to_acc(ed[k]); a1 += d; a2 = fmaf(d, to_acc(ex[k]) - mu, a2); }
-                }
+            } else {
+                for (int64_t i = wt * 32 + lane; i < HW; i += (int64_t)TS * 32) { const float d = to_acc(dyp[i]); a1 += d; a2 = fmaf(d, to_acc(xp[i]) - mu, a2); }
             }
-        } else {
-            for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) { const float d = to_acc(dyp[i]); a1 += d; a2 = fmaf(d, to_acc(xp[i]) - mu, a2); }
+            a1 = warp_sum(a1); a2 = warp_sum(a2);
+            if (lane == 0) { s_part[0][c][wt] = a1; s_part[1][c][wt] = a2; }
         }
-        a1 = warp_sum(a1); a2 = warp_sum(a2);
-        __syncthreads();
-        if (lane == 0) { red[0][warp] = a1; red[1][warp] = a2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t1 = 0.f, t2 = 0.f;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { t1 += red[0][w]; t2 += red[1][w]; }
-            s_c1[c] = t1; s_c2[c] = t2 * rs;          // sum dy,  sum dy * xhat
-        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cpg; c += blockDim.x) {
+        float t1 = 0.f, t2 = 0.f;
+        for (int w = 0; w < TS; w++) { t1 += s_part[0][c][w]; t2 += s_part[1][c][w]; }
+        s_c1[c] = t1; s_c2[c] = t2 * rs;              // sum dy,  sum dy * xhat
     }
     __syncthreads();
     float s1 = 0.f, s2 = 0.f;

@@ -543,18 +543,30 @@ __global__ void dw_fix_kernel(float* dw, const float* __restrict__ w, const floa
     for (int k = 0; k < KK; k++) dw[(size_t)idx * KK + k] -= aa * w[(size_t)idx * KK + k] * t;
 }
 
-// ds[n,i] = c[n] * (dsum[n,i] - s'[n,i] sum_o h[n,o] wsq[o,i])                          (thread per (n,i))
-__global__ void ds_fix_kernel(float* ds, const float* __restrict__ dsum, const float* __restrict__ c, const float* __restrict__ g,
-                              const float* __restrict__ dcoefs, const float* __restrict__ iscale, const float* __restrict__ wsq,
-                              int N, int O, int I, int demodulate) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * I) return;
-    int n = idx / I, i = idx - n * I;
+// ds[n,i] = c[n] * (dsum[n,i] - s'[n,i] sum_o h[n,o] wsq[o,i])
+// CTA = 32 input channels of one sample x 8 slices of the output channels (summed through shared memory): a thread per (n,i) walking
+// all O channels alone was a chain of O dependent-latency rounds on 128 CTAs (46 us per call in the ncu launch list).
+__global__ void __launch_bounds__(256) ds_fix_kernel(float* ds, const float* __restrict__ dsum, const float* __restrict__ c, const float* __restrict__ g,
+                                                     const float* __restrict__ dcoefs, const float* __restrict__ iscale, const float* __restrict__ wsq,
+                                                     int N, int O, int I, int demodulate) {
+    __shared__ float part[8][32];
+    const int il = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int bpn = (I + 31) / 32;
+    const int n = blockIdx.x / bpn, i = (blockIdx.x - n * bpn) * 32 + il;
     float t = 0.f;
-    if (demodulate) {
-        for (int o = 0; o < O; o++) { float d = dcoefs[n * O + o]; t += g[n * O + o] * d * d * d * wsq[(size_t)o * I + i]; }
+    if (demodulate && i < I) {
+#pragma unroll 4
+        for (int o = sl; o < O; o += 8) { const float d = dcoefs[n * O + o]; t += g[n * O + o] * d * d * d * wsq[(size_t)o * I + i]; }
     }
-    ds[idx] = c[n] * (dsum[idx] - iscale[idx] * t);
+    part[sl][il] = t;
+    __syncthreads();
+    if (sl == 0 && i < I) {
+        t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += part[k][il];
+        const int idx = n * I + i;
+        ds[idx] = c[n] * (dsum[idx] - iscale[idx] * t);
+    }
 }
 
 template <class T>
@@ -625,7 +637,7 @@ int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const 
     return launch_status("modconv dw_fix_kernel");
 }
 int run_ds_fix(float* ds, const float* dsum, const float* c, const float* g, const float* dcoefs, const float* iscale, const float* wsq, int N, int O, int I, int demod, cudaStream_t stream) {
-    ds_fix_kernel<<<ceil_div(N * I, 256), 256, 0, stream>>>(ds, dsum, c, g, dcoefs, iscale, wsq, N, O, I, demod);
+    ds_fix_kernel<<<N * ceil_div(I, 32), 256, 0, stream>>>(ds, dsum, c, g, dcoefs, iscale, wsq, N, O, I, demod);
     return launch_status("modconv ds_fix_kernel");
 }
 

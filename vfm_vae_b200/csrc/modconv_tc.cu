@@ -1,28 +1,49 @@
 // Modulated conv on the 5th-generation tensor cores: implicit GEMM with tcgen05.mma, accumulators in TMEM, operands
 // staged by TMA.  sm_100a only.
 //
-//   M = 128 output pixels (a tw x th x tn patch of the NHWC activation tensor),  N = 128 output channels,
-//   K = taps x Cin, walked as (tap, 64-channel chunk).
-//
-// * A operand: the activation already multiplied by the per-sample styles and transposed to NHWC fp16 by a pre-pass
-//   (nhwc_prepass_kernel).  One TMA box [64 ch, tw, th, tn] per (tap, chunk); the tap shift is a coordinate offset and
-//   the zero padding halo is TMA out-of-bounds fill -- no im2col buffer, no per-sample [N,O,I,k,k] weights.
-// * B operand: the shared weights re-laid out as [tap][Cout][Cin] fp16 (K-major), one TMA box [64, 128, 1].
-// * both land in shared memory in the canonical 128-byte-swizzled K-major layout that tcgen05 smem descriptors read.
-// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue
-//   (tcgen05.ld 32 lanes x 16 columns, demodulation d[n,o] and noise applied in fp32, NCHW store).  3-stage full/empty
-//   mbarrier ring; tcgen05.commit releases smem stages and publishes the accumulator.
-// * up=2 (transposed conv, stride 2) runs as 4 sub-pixel phases of the same kernel (blockIdx.z): each phase is a
-//   stride-1 conv over the input grid with the taps of matching parity, written to every other output pixel.
-// * the data gradient is the same kernel (activation = d*dz, weights transposed) with an epilogue that scales by the
-//   styles and reduces sum_p x*dxpre into dstyles with warp shuffles; for up=2 its A boxes are element-strided TMA boxes.
-// * fp32 tensors use a 2-term fp16 split of both operands (x = hi + lo/2048): three MMAs per K step
+// conv_tc_kernel (forward and data gradient), one persistent CTA of 320 threads per SM:
+//   M = 128 output CHANNELS (UMMA A operand = a weight tile),  N = NPIX = 256 PIXELS (UMMA B operand = a tw x th x tn
+//   patch of the NHWC activation; 128 pixels for the paired up=2 phases and the fp32 split),  K = taps x Cin, walked
+//   as (tap, 64-channel chunk).  The accumulator therefore has one channel per TMEM lane and the pixels along the
+//   columns: an epilogue thread owns one output channel and runs of 16 consecutive pixels.
+// * A operand: the shared weights re-laid out as [tap][Cout][Cin] fp16 (K-major, weight_prep_kernel), one TMA box
+//   [64, 128, 1] per (tap, chunk); the data gradient uses the transposed layout [tap][Cin][Cout].
+// * B operand: the activation multiplied by the per-sample styles (and an optional GroupNorm affine map) and transposed
+//   to NHWC fp16 by a pre-pass (nhwc_prepass_kernel).  One TMA box [64 ch, tw, th, tn] per (tap, chunk): the tap shift
+//   is a coordinate offset, the zero-padding halo is TMA out-of-bounds fill -- no im2col buffer and no per-sample
+//   [N,O,I,k,k] weights (the 604 MB tensor of networks/generator.py:73-99).  1x1 convs on fp16 NCHW rows of a multiple
+//   of 64 pixels (MNP) skip the pre-pass: MN-major boxes [64 pixels, 64 channels] straight from the NCHW tensor and
+//   per-sample weights that carry the modulation.
+// * both operands land in shared memory in the canonical 128-byte-swizzled layout that tcgen05 smem descriptors read;
+//   a ring of 192 KB / stage bytes stages (4 x 48 KB for fp16 at NPIX = 256) with full/empty mbarriers.
+// * warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator (all 512 columns) + single-thread MMA
+//   issuer, warps 2-9 = epilogue (two warps per TMEM lane group, one per half of the pixel columns).  The
+//   accumulators are double-buffered in TMEM (tfull/tempty mbarriers): the epilogue of item i runs under the MMAs of
+//   item i+1; tcgen05.commit releases smem stages and publishes accumulators.
+// * epilogue: tcgen05.ld 32 lanes x 16 columns (next step's load in flight), demodulation d[n,o], noise (staged per
+//   tile in shared memory), optional fused bias / lrelu|GELU / gain / clamp / layer-scaled residual (inference),
+//   256-bit NCHW stores; side inputs (residual, or x for the dstyles reduction) prefetched in a rolling window.
+// * up=2 (transposed conv, stride 2; PAIR): 4 sub-pixel phases, each a stride-1 conv over the input grid with the taps
+//   of matching parity.  An item computes the two horizontal phases of one row parity into two accumulators and the
+//   epilogue interleaves them, so stores to the (2H+1) x (2W+1) intermediate are contiguous vectors.
+// * the data gradient (DGRAD) is the same kernel (B operand = d*dz, weights transposed) with an epilogue that scales by
+//   the styles and accumulates sum_p x*dxpre -> dstyles as a private register sum (one atomic per channel and sample);
+//   for up=2 its B boxes are element-strided TMA boxes (stride 2).
+// * fp32 tensors (SPLIT) use a 2-term fp16 split of both operands (x = hi + lo/2048): three MMAs per K step
 //   (hi*hi -> acc0; hi*lo + lo*hi -> acc1), recombined in the epilogue as acc0 + acc1/2048.  That carries ~22 mantissa
 //   bits per operand -- enough for the 1e-5 fp32 parity gate, which single-pass TF32 (10 bits) cannot meet -- at 3x the
-//   fp16 cost instead of the 6x of 3xTF32.
+//   fp16 cost instead of the 6x of 3xTF32.  Range: the styles are normalised per sample (max |s'| <= 1, a power-of-two
+//   c2 undone in the epilogue) and the incoming GRADIENTS are brought into fp16 range by a device-computed power of two
+//   (amax_kernel -> gscale); forward ACTIVATIONS are not rescaled (that would cost one more pass over x), so an fp32
+//   forward needs |x * s'| < 65504 and loses mantissa below ~1e-4 of that -- true for the decoder's O(1) activations
+//   (GroupNorm / lrelu-clamped layers), documented in INTEGRATION.md as the supported range.
+//
+// wgrad_tc_kernel (weight gradient): M = 128 output channels x N = 256 columns = two (tap, 128 input channel) blocks,
+// K = pixels; both operands are MN-major TMA boxes [64 pixels, 64 channels] of the same NHWC tensors; split-K over
+// pixel tiles with fp32 red.add into dweight.
 //
 // Numerics: fp16 operands, fp32 accumulation, fp32 epilogue.  The reference's fp16 pre-normalisation
-// (networks/generator.py:66-68) maps to: A = x * s' (styles normalised per sample), B = W * a[o] (weights normalised per
+// (networks/generator.py:66-68) maps to: B = x * s' (styles normalised per sample), A = W * a[o] (weights normalised per
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
@@ -902,10 +923,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 }
 
 // gs[2] = c2g (power of two keeping |x * s'| in fp16 range for every sample), gs[3] = 1 / (gk * c2g)
-__global__ void wgrad_scalars_kernel(const float* __restrict__ iscale, int n_el, float* gs, int has_gk) {
+// One CTA (the result is a single scalar the next kernels read): 1024 threads x four independent 16-byte loads per round, so the
+// N*I <= ~50 K styles take 3 rounds of memory latency -- the former 256-thread scalar loop was 128+ dependent rounds (77 us per call,
+// 89 calls per training step: 3.4 % of the step in the ncu launch list).
+__global__ void __launch_bounds__(1024) wgrad_scalars_kernel(const float* __restrict__ iscale, int n_el, float* gs, int has_gk) {
     __shared__ float red[32];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < n_el; i += blockDim.x) m = fmaxf(m, fabsf(iscale[i]));
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    const int nv = ((reinterpret_cast<uintptr_t>(iscale) & 15u) == 0) ? n_el >> 2 : 0;
+    const float4* iv = (const float4*)iscale;
+    int i = threadIdx.x;
+    for (; i + 3 * (int)blockDim.x < nv; i += 4 * blockDim.x) {
+        const float4 a = iv[i], b = iv[i + blockDim.x], c = iv[i + 2 * blockDim.x], d = iv[i + 3 * blockDim.x];
+        m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+        m1 = fmaxf(m1, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        m2 = fmaxf(m2, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))));
+        m3 = fmaxf(m3, fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
+    }
+    for (; i < nv; i += blockDim.x) { const float4 a = iv[i]; m0 = fmaxf(m0, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)))); }
+    for (int j = 4 * nv + threadIdx.x; j < n_el; j += blockDim.x) m1 = fmaxf(m1, fabsf(iscale[j]));
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -1071,6 +1107,19 @@ template <class TIn>
 __global__ void __launch_bounds__(256) amax_kernel(const TIn* __restrict__ x, const float* __restrict__ scale, int C, int HW, size_t total, unsigned int* amax_bits,
                                                    int W, int pitch) {
     float m = 0.f;
+    if (pitch == W && (HW & 3) == 0 && total < (1ull << 31) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && sizeof(TIn) == 4) {
+        // dense fp32 planes: 16-byte loads, one 32-bit division per vector, two vectors in flight
+        const unsigned nv = (unsigned)(total >> 2), step = gridDim.x * blockDim.x;
+        const float4* xv = (const float4*)x;
+        for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += 2 * step) {
+            const float4 a = xv[v];
+            const bool two = v + step < nv;
+            const float4 b = two ? xv[v + step] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float sa = scale[(v * 4u) / (unsigned)HW], sb = two ? scale[((v + step) * 4u) / (unsigned)HW] : 0.f;
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))) * fabsf(sa));
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))) * fabsf(sb));
+        }
+    } else
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t plane = i / HW;
         size_t off = i;
@@ -1403,7 +1452,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     const float* c2_global = nullptr;
     if (keep_operand && !x_scale) {
         // the operand survives for the weight gradient: one power of two for the whole batch (what run_tc_wgrad's own pre-pass would use)
-        wgrad_scalars_kernel<<<1, 256, 0, stream>>>(k.iscale, N * I, w.gs, 0);
+        wgrad_scalars_kernel<<<1, 1024, 0, stream>>>(k.iscale, N * I, w.gs, 0);
         int st1 = launch_status("modconv wgrad_scalars_kernel"); if (st1) return st1;
         c2_global = w.gs + 2;
     }
@@ -1486,7 +1535,7 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
     }
     if (dweight) {
         // B operand: x * s' * c2g NHWC; result scale a[o] / (gk * c2g)
-        wgrad_scalars_kernel<<<1, 256, 0, stream>>>(k.iscale, N * I, w.gs, gs ? 1 : 0);
+        wgrad_scalars_kernel<<<1, 1024, 0, stream>>>(k.iscale, N * I, w.gs, gs ? 1 : 0);
         st = launch_status("modconv wgrad_scalars_kernel"); if (st) return st;
         if (saved_xt && (!f32 || saved_xt_lo)) {
             // the forward kept exactly this tensor (same iscale, same c2g): no second pass over x

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 9
+#define VFM_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define VFM_API __attribute__((visibility("default")))
@@ -373,6 +373,24 @@ typedef struct {
     int32_t     inverse;      /* != 0: PixelUnshuffle(2) (the backward): x is the [batch, out_channels, 2 in_h, 2 in_w] tensor, y the 4-plane one */
 } vfm_pixel_shuffle2_params;
 VFM_API int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stream);
+
+/* Border rows / columns of the data gradient of  y = conv2d(pad(x, k/2, mode='replicate'), f[k,k], groups=C)  (the fixed blur behind
+ * the pixel-shuffle upsampler, networks/utils/convnext_utils.py:250-255):
+ *   dx[jy,jx] = sum_{iy,ix} dy[iy,ix] * sum_{ty,tx} f[ty,tx] [clamp(iy+ty-k/2) == jy] [clamp(ix+tx-k/2) == jx]
+ * Away from the border this is the zero-padded "same" stencil over dy (one vfm_upfirdn2d pass, flip = 0); on the outermost row / column
+ * of every plane the clamped taps fold back, and this call OVERWRITES those 2W + 2(H-2) elements of dx with the complete sums
+ * (range sums of f from a summed-area table).  dy, dx contiguous [planes, h, w] of `dtype` (fp16 / fp32), f fp32 [k,k], k in {3, 5},
+ * h, w >= k.  Replaces the four thin conv_transpose2d calls + slice arithmetic a host-side fold needs. */
+typedef struct {
+    const void*  dy;
+    void*        dx;
+    const float* f;
+    int32_t      dtype;
+    int32_t      k;
+    int64_t      planes;
+    int32_t      h, w;
+} vfm_replicate_blur_edges_params;
+VFM_API int vfm_replicate_blur_edges(const vfm_replicate_blur_edges_params* p, void* stream);
 
 /* Weight and bias gradient of the depthwise k x k conv (k = 3, 5, 7; "same" zero padding; see vfm_upfirdn2d_params::f_stride_c for
  * the forward; the data gradient is the forward with flip = 0):

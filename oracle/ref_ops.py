@@ -405,3 +405,32 @@ def synthesis_layer(x, weight, bias, styles, noise, up, resample_filter, act_gai
     y = modulated_conv2d(x, weight, styles, noise=noise, up=up, padding=weight.shape[-1] // 2,
                          resample_filter=resample_filter, flip_weight=(up == 1))
     return bias_act(y, bias.to(y.dtype), act='lrelu', gain=act_gain, clamp=act_clamp)
+
+
+def replicate_blur_edges(dy, f, dx):
+    """CPU model of ``vfm_replicate_blur_edges`` (include/vfm_ops.h): the border rows / columns of the data gradient of
+    ``conv2d(pad(x, k//2, mode='replicate'), f, groups=C)`` (networks/utils/convnext_utils.py:250-255), written into ``dx`` [N,C,H,W]
+    (whose interior the caller has filled with the zero-padded stencil over ``dy``).  For output j and input i of one axis the taps
+    that land on j after clamping form a range -- [0, p-i] on the first row / column, [n-1+p-i, k-1] on the last, the single tap j-i+p
+    elsewhere -- so each weight is a range sum of ``f``.  Plain loops over the 2W + 2(H-2) border elements: small cases only."""
+    k = f.shape[0]
+    p = k // 2
+    h, w = dy.shape[2:]
+
+    def taps(j, i, n):
+        if j == 0:
+            return range(0, min(k - 1, p - i) + 1)
+        if j == n - 1:
+            return range(max(0, n - 1 + p - i), k)
+        t = j - i + p
+        return range(t, t + 1) if 0 <= t < k else range(0)
+
+    border = [(0, x) for x in range(w)] + [(h - 1, x) for x in range(w)] + [(y, x) for y in range(1, h - 1) for x in (0, w - 1)]
+    for jy, jx in border:
+        acc = torch.zeros(dy.shape[:2], dtype=dy.dtype)
+        for iy in range(max(0, jy - p), min(h, jy + p + 1)):
+            for ix in range(max(0, jx - p), min(w, jx + p + 1)):
+                wgt = sum(float(f[ty, tx]) for ty in taps(jy, iy, h) for tx in taps(jx, ix, w))
+                acc = acc + wgt * dy[:, :, iy, ix]
+        dx[:, :, jy, jx] = acc
+    return dx

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SYMBOLS) == declared
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vfm_abi_version() == 9
+    assert lib.vfm_abi_version() == 10
     assert _lib.last_error() == ''
 
 
@@ -38,7 +38,7 @@ def test_struct_layout_matches_header(tmp_path):
         'vfm_filtered_lrelu_params': _lib.FilteredLreluParams, 'vfm_filtered_lrelu_act_params': _lib.FilteredLreluActParams,
         'vfm_modconv_desc': _lib.ModconvDesc, 'vfm_modconv_fwd_params': _lib.ModconvFwdParams,
         'vfm_modconv_bwd_params': _lib.ModconvBwdParams, 'vfm_group_norm_affine_params': _lib.GroupNormAffineParams, 'vfm_group_norm_params': _lib.GroupNormParams, 'vfm_rows_params': _lib.RowsParams,
-        'vfm_pixel_shuffle2_params': _lib.PixelShuffle2Params, 'vfm_depthwise_wgrad_params': _lib.DepthwiseWgradParams,
+        'vfm_pixel_shuffle2_params': _lib.PixelShuffle2Params, 'vfm_replicate_blur_edges_params': _lib.ReplicateBlurEdgesParams, 'vfm_depthwise_wgrad_params': _lib.DepthwiseWgradParams,
         'vfm_grad_finalize_params': _lib.GradFinalizeParams, 'vfm_image_to_u8_params': _lib.ImageToU8Params,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vfm_ops.h"', 'int main(void){']

@@ -570,6 +570,17 @@ def test_modulated_conv2d_vs_oracle(cfg, dtype, generic):
     _modconv_vs_oracle(dtype=dtype, generic=generic, **cfg)
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
+@pytest.mark.parametrize('cfg', [dict(N=2, I=512, H=8, W=8), dict(N=3, I=512, H=16, W=16), dict(N=2, I=256, H=32, W=32), dict(N=2, I=200, H=8, W=8),
+                                 dict(N=1, I=128, H=12, W=8), dict(N=2, I=128, H=64, W=64), dict(N=70, I=64, H=32, W=32)],
+                         ids=lambda c: f"N{c['N']}I{c['I']}H{c['H']}W{c['W']}")
+def test_torgb_pointwise_shapes(cfg, dtype):
+    """ToRGB (1x1, 3 outputs, no demodulation, networks/generator.py:284-312) at the small-image / many-channel shapes of the decoder's first
+    blocks: the forward splits the channels over slices of a CTA there (2 .. 16 slices, partial last pixel group, channel counts that are
+    not a multiple of the slice count), the backward correlation runs one warp per channel."""
+    _modconv_vs_oracle(O_=3, k=1, up=1, demod=False, dtype=dtype, noise_kind=None, generic=False, **cfg)
+
+
 @pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['fp16', 'fp32'])
 @pytest.mark.parametrize('up', [1, 2])
 def test_kept_forward_operand_gives_the_same_weight_gradient(dtype, up):
@@ -897,7 +908,10 @@ def test_fused_convnext_mlp(cfg, dtype):
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
 @pytest.mark.parametrize('cfg', [dict(shape=(2, 128, 16, 16), groups=32), dict(shape=(3, 32, 7, 5), groups=8), dict(shape=(1, 512, 8, 8), groups=32),
-                                 dict(shape=(2, 64, 64, 64), groups=16)], ids=lambda c: 'x'.join(map(str, c['shape'])))
+                                 dict(shape=(2, 64, 64, 64), groups=16),
+                                 # backward reduce in warp teams: more channels per group than warps (24, 20), a team count that does not divide 16 (3)
+                                 dict(shape=(1, 768, 8, 8), groups=32), dict(shape=(1, 640, 16, 16), groups=32), dict(shape=(2, 96, 12, 12), groups=32)],
+                         ids=lambda c: 'x'.join(map(str, c['shape'])))
 def test_group_norm32_forward_backward(cfg, dtype):
     """GroupNorm32 (fp32 statistics, output in x.dtype) forward and gradients against torch.nn.functional.group_norm in fp64."""
     from vfm_vae_b200.torch_utils.ops.group_norm import group_norm32

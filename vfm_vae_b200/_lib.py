@@ -92,6 +92,10 @@ class PixelShuffle2Params(C.Structure):
     _fields_ = [('x', _vp), ('y', _vp), ('dtype', _i32), ('batch', _i32), ('out_channels', _i32), ('in_h', _i32), ('in_w', _i32), ('inverse', _i32)]
 
 
+class ReplicateBlurEdgesParams(C.Structure):
+    _fields_ = [('dy', _vp), ('dx', _vp), ('f', _vp), ('dtype', _i32), ('k', _i32), ('planes', C.c_int64), ('h', _i32), ('w', _i32)]
+
+
 class DepthwiseWgradParams(C.Structure):
     _fields_ = [('x', _vp), ('dy', _vp), ('dweight', _vp), ('dbias', _vp), ('dtype', _i32), ('batch', _i32), ('channels', _i32), ('h', _i32),
                 ('w', _i32), ('k', _i32)]
@@ -141,6 +145,7 @@ SYMBOLS = {
     'vfm_rows_affine': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_rows_dot': (C.c_int, [C.POINTER(RowsParams), _vp]),
     'vfm_pixel_shuffle2': (C.c_int, [C.POINTER(PixelShuffle2Params), _vp]),
+    'vfm_replicate_blur_edges': (C.c_int, [C.POINTER(ReplicateBlurEdgesParams), _vp]),
     'vfm_depthwise_wgrad': (C.c_int, [C.POINTER(DepthwiseWgradParams), _vp]),
     'vfm_grad_finalize': (C.c_int, [C.POINTER(GradFinalizeParams), _vp]),
     'vfm_image_to_u8': (C.c_int, [C.POINTER(ImageToU8Params), _vp]),
@@ -164,8 +169,8 @@ def load():
         fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 9:
-        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 9)')
+    if lib.vfm_abi_version() != 10:
+        raise RuntimeError(f'vfm_vae_b200: ABI version mismatch ({lib.vfm_abi_version()} != 10)')
     _lib = lib
     return lib
 

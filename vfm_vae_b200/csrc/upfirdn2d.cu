@@ -977,8 +977,85 @@ __global__ void __launch_bounds__(128) dw_wgrad_kernel(const T* __restrict__ x, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Border of the data gradient of the replicate-padded fixed blur (see vfm_replicate_blur_edges in vfm_ops.h).  One thread per border
+// element of a plane: 2W (first / last row) + 2(H-2) (first / last column of the rows in between).  For output j and a contributing dy
+// position i = j + a of one axis, the taps that land on j after clamping form a RANGE that depends only on the class of j (first /
+// interior / last) and on a: the single tap p - a in the interior, [0, p - a] on the first row / column (a >= 0), [p - a, k-1] on the
+// last (a <= 0).  The CTA builds the table G[cy][a][cx][b] = sum of f over the two ranges once (3k x 3k entries) and every thread then
+// does (2p+1)^2 guarded loads and FMAs.  Replaces four grouped conv_transpose2d calls (0.4 ms each in cuDNN for [64,128,2,256] slices)
+// plus ~20 slice kernels of a host-side fold.
+template <class T, int K>
+__global__ void __launch_bounds__(256) replicate_blur_edges_kernel(const T* __restrict__ dy, T* __restrict__ dx, const float* __restrict__ f, int64_t planes, int H, int W) {
+    constexpr int P = K / 2;
+    __shared__ float G[3 * K][3 * K];              // [class_y * K + (a + P)][class_x * K + (b + P)]
+    auto range = [](int cls, int a, int& lo, int& hi) {     // tap range of one axis; empty when lo > hi
+        if (cls == 1) { lo = hi = P - a; }
+        else if (cls == 0) { lo = 0; hi = (a >= 0) ? P - a : -1; }
+        else { lo = (a <= 0) ? P - a : K; hi = K - 1; }
+        lo = max(lo, 0); hi = min(hi, K - 1);
+    };
+    for (int i = threadIdx.x; i < 9 * K * K; i += blockDim.x) {
+        const int r = i / (3 * K), c = i - r * (3 * K);
+        int ty0, ty1, tx0, tx1;
+        range(r / K, r % K - P, ty0, ty1);
+        range(c / K, c % K - P, tx0, tx1);
+        float sum = 0.f;
+        for (int t = ty0; t <= ty1; t++) for (int u = tx0; u <= tx1; u++) sum += f[t * K + u];
+        G[r][c] = sum;
+    }
+    __syncthreads();
+    const int border = 2 * W + 2 * (H - 2);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= planes * border) return;
+    const int64_t plane = idx / border;
+    int e = (int)(idx - plane * border), jy, jx;
+    if (e < W) { jy = 0; jx = e; }
+    else if (e < 2 * W) { jy = H - 1; jx = e - W; }
+    else { e -= 2 * W; jy = 1 + (e >> 1); jx = (e & 1) ? W - 1 : 0; }
+    const int cy = (jy == 0) ? 0 : (jy == H - 1 ? 2 : 1), cx = (jx == 0) ? 0 : (jx == W - 1 ? 2 : 1);
+    const T* dp = dy + plane * (int64_t)H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = -P; a <= P; a++) {
+        const int iy = jy + a;
+        if (iy < 0 || iy >= H) continue;
+        const float* grow = &G[cy * K + a + P][cx * K + P];
+        const T* drow = dp + (int64_t)iy * W + jx;
+#pragma unroll
+        for (int b = -P; b <= P; b++) {
+            const int ix = jx + b;
+            if (ix < 0 || ix >= W) continue;
+            acc = fmaf(grow[b], to_acc(drow[b]), acc);
+        }
+    }
+    dx[plane * (int64_t)H * W + (int64_t)jy * W + jx] = from_acc<T, float>(acc);
+}
+
 }  // namespace
 }  // namespace vfm
+
+extern "C" int vfm_replicate_blur_edges(const vfm_replicate_blur_edges_params* p, void* stream_) {
+    using namespace vfm;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    VFM_CHECK_ARG(p != nullptr && p->dy && p->dx && p->f, "replicate_blur_edges: NULL argument");
+    VFM_CHECK_ARG(p->dtype == VFM_F16 || p->dtype == VFM_F32, "replicate_blur_edges: fp16 / fp32 only");
+    VFM_CHECK_ARG(p->k == 3 || p->k == 5, "replicate_blur_edges: k must be 3 or 5 (got %d)", p->k);
+    VFM_CHECK_ARG(p->planes >= 1 && p->h >= p->k && p->w >= p->k, "replicate_blur_edges: planes must be at least k x k");
+    const int64_t total = p->planes * (2 * (int64_t)p->w + 2 * ((int64_t)p->h - 2));
+    VFM_CHECK_ARG(ceil_div64(total, 256) <= 0x7fffffffLL, "replicate_blur_edges: grid too large");
+    const unsigned blocks = (unsigned)ceil_div64(total, 256);
+    const int es = p->dtype == VFM_F16 ? 2 : 4;
+    KernelTimer timer("replicate_blur_edges", stream, 0.0, (double)total * es * 2.0, "h%dw%d", p->h, p->w);
+    if (p->dtype == VFM_F16) {
+        if (p->k == 3) replicate_blur_edges_kernel<__half, 3><<<blocks, 256, 0, stream>>>((const __half*)p->dy, (__half*)p->dx, p->f, p->planes, p->h, p->w);
+        else replicate_blur_edges_kernel<__half, 5><<<blocks, 256, 0, stream>>>((const __half*)p->dy, (__half*)p->dx, p->f, p->planes, p->h, p->w);
+    } else {
+        if (p->k == 3) replicate_blur_edges_kernel<float, 3><<<blocks, 256, 0, stream>>>((const float*)p->dy, (float*)p->dx, p->f, p->planes, p->h, p->w);
+        else replicate_blur_edges_kernel<float, 5><<<blocks, 256, 0, stream>>>((const float*)p->dy, (float*)p->dx, p->f, p->planes, p->h, p->w);
+    }
+    return launch_status("replicate_blur_edges_kernel");
+}
 
 extern "C" int vfm_pixel_shuffle2(const vfm_pixel_shuffle2_params* p, void* stream_) {
     using namespace vfm;

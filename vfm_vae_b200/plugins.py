@@ -133,6 +133,21 @@ class _Upfirdn2dPlugin:
         return y
 
     @staticmethod
+    def replicate_blur_edges(dy, dx, f):
+        """Overwrites the border rows / columns of ``dx`` (the zero-padded stencil pass over ``dy``) with the data gradient of the
+        replicate-padded blur (extension; ``vfm_replicate_blur_edges``).  In place; returns ``dx``."""
+        _check(dy.is_cuda and dy.dim() == 4 and dy.is_contiguous() and dx.is_contiguous() and dx.shape == dy.shape and dx.dtype == dy.dtype,
+               'replicate_blur_edges: dy / dx must be contiguous NCHW CUDA tensors of the same shape and dtype')
+        _check(f.dtype == torch.float32 and f.is_contiguous() and f.dim() == 2 and f.shape[0] == f.shape[1] and f.device == dy.device,
+               'replicate_blur_edges: f must be a contiguous float32 [k,k] tensor on the device of dy')
+        p = _lib.ReplicateBlurEdgesParams()
+        p.dy, p.dx, p.f, p.dtype, p.k = _ptr(dy), _ptr(dx), _ptr(f), _dtype_code(dy, 'replicate_blur_edges'), f.shape[0]
+        p.planes, p.h, p.w = dy.shape[0] * dy.shape[1], dy.shape[2], dy.shape[3]
+        with torch.cuda.device(dy.device):
+            _lib.check(_lib.load().vfm_replicate_blur_edges(C.byref(p), _stream(dy)), 'replicate_blur_edges')
+        return dx
+
+    @staticmethod
     def depthwise_wgrad(x, dy, k, want_bias=True):
         """-> (dweight [C,k,k] fp32, dbias [C] fp32 | None) of the depthwise k x k conv (extension), or None where no kernel applies."""
         _check(x.is_cuda and x.dim() == 4 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and dy.dtype == x.dtype,

@@ -149,34 +149,10 @@ def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl='cuda'
     return upfirdn2d(x, f, down=down, padding=p, flip_filter=flip_filter, gain=gain, impl=impl)
 
 
-def replicate_blur_adjoint(dy, fw, core):
-    """Gradient w.r.t. x of ``y = F.conv2d(F.pad(x, (p,p,p,p), mode='replicate'), fw, groups=C)`` (fw [C,1,k,k], k odd, p = k//2).
-
-    With Z = the adjoint of the valid correlation on the padded domain (size (H+2p) x (W+2p)), dx is Z's interior plus Z's p pad rows /
-    columns folded back onto the edge row / column they replicate.  ``core`` = Z[p:H+p, p:W+p] (the data gradient of the zero-padded
-    "same" conv: one pass of the stencil kernel on the GPU) is supplied by the caller and updated in place; the four border strips of Z
-    only depend on the outermost p rows / columns of dy and are computed here from those thin slices (fp32, a few MB)."""
-    import torch.nn.functional as F
-    c, k = dy.shape[1], fw.shape[-1]
-    p = k // 2
-    h, w = dy.shape[2:]
-    w32 = fw.to(torch.float32)
-    ct = lambda a: F.conv_transpose2d(a.to(torch.float32), w32, groups=c)       # noqa: E731  exact adjoint of the valid correlation
-    dx = core
-    top, bot = ct(dy[:, :, :p, :]), ct(dy[:, :, h - p:, :])                        # rows [0,p) resp. the last p rows of Z, all W+2p columns
-    dx[:, :, 0, :] += top[:, :, :p, p:w + p].sum(2).to(dx.dtype)
-    dx[:, :, h - 1, :] += bot[:, :, -p:, p:w + p].sum(2).to(dx.dtype)
-    for strip, col, sl in ((ct(dy[:, :, :, :p]), 0, slice(0, p)), (ct(dy[:, :, :, w - p:]), w - 1, slice(-p, None))):
-        cols = strip[:, :, p:h + p, sl].clone()                                    # Z[:, pad columns] with its own pad rows folded first
-        cols[:, :, 0] += strip[:, :, :p, sl].sum(2)
-        cols[:, :, h - 1] += strip[:, :, h + p:, sl].sum(2)
-        dx[:, :, :, col] += cols.sum(3).to(dx.dtype)
-    return dx
-
-
 class _ReplicateBlur(torch.autograd.Function):
     """replicate-pad + fixed depthwise blur (k = 3, 5) as one pass of the streaming kernel; backward = one pass of the zero-padded
-    stencil kernel over dy + the edge folding of ``replicate_blur_adjoint``."""
+    stencil kernel over dy (exact away from the border) + ``vfm_replicate_blur_edges``, which rewrites the outermost row / column of every
+    plane with the sums that include the taps the clamp folds back onto them."""
 
     @staticmethod
     def forward(ctx, x, f32):
@@ -191,8 +167,8 @@ class _ReplicateBlur(torch.autograd.Function):
         k, c = f32.shape[0], dy.shape[1]
         dy = dy.contiguous()
         fc = f32[None].repeat(c, 1, 1)
-        core = _dw_call(dy, fc, k, False)
-        return replicate_blur_adjoint(dy, fc[:, None], core), None
+        dx = _dw_call(dy, fc, k, False)
+        return _plugin.replicate_blur_edges(dy, dx, f32), None
 
 
 def blur2d_replicate(x, f, padding):

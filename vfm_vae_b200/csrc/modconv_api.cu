@@ -32,12 +32,7 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
 void tc_forward_operand(const vfm_modconv_desc& d, void* ws, size_t ws_bytes, const void** hi, const void** lo);
 // gradients of the stage-1 contraction given dz: dx (+ dsum) and the main part of dweight
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
-                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo,
-                       bool act_ready = false);
-void* tc_backward_act_buffer(const vfm_modconv_desc& d, const Stage1& s, void* ws, size_t ws_bytes);
-bool act_grad_nhwc_supported(int dtype, int O, int HW, const void* dy, const void* y);
-int run_act_grad_nhwc(const void* dy, const void* y, const void* bias, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
-                      float gain, float alpha, float clamp, int act, void* act_out, float* g, float* gz, float* dnoise, int dnoise_per_sample, cudaStream_t stream);
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo);
 
 static int validate(const vfm_modconv_desc& d) {
     VFM_CHECK_ARG(d.dtype == VFM_F16 || d.dtype == VFM_F32 || d.dtype == VFM_F64, "modulated_conv2d: unsupported dtype %d", d.dtype);
@@ -241,34 +236,17 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     const int HWo = d.out_h * d.out_w;
     const int64_t noise_sn = (d.noise_mode == VFM_NOISE_N1HW) ? (int64_t)HWo : 0;
     const void* dy_pre = p->dy;                 // gradient w.r.t. the conv output (before bias / activation)
-    bool act_ready = false;                     // the activation-gradient pass has already written the tcgen05 backward's NHWC operand
     if (p->ep_enable) {
-        const bool need_g = d.demodulate && (p->dweight || p->dstyles);
-        const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
-        if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
-        // stride-1 fp16 layers on the tensor-core path: dz is only ever read as the NHWC operand d * dz of the two gradient GEMMs, so the
-        // activation-gradient pass writes that operand directly (no NCHW dz, no pre-pass over it)
-        if (d.up == 1 && use_tc(d) && !use_pw(d) && act_grad_nhwc_supported(d.dtype, O, HWo, p->dy, p->y)) {
-            const size_t tc_off = (cv.off + 255) & ~(size_t)255;
-            void* act_buf = tc_backward_act_buffer(d, s, (char*)p->workspace + tc_off, p->workspace_bytes - tc_off);
-            if (act_buf) {
-                st = run_act_grad_nhwc(p->dy, p->y, p->ep_bias, p->noise, noise_sn, p->dcoefs, N, O, HWo, (float)p->ep_gain, (float)p->ep_alpha, (float)p->ep_clamp,
-                                       p->ep_act, act_buf, need_g ? g : nullptr, p->dbias_no, p->dnoise, per_sample, stream);
-                if (st) return st;
-                act_ready = true;
-            }
-        }
-    }
-    if (p->ep_enable && !act_ready) {
         // one pass: activation gradient -> dz (workspace), g, per-sample bias gradient, dnoise
         void* dzp_act = cv.take<char>((size_t)N * O * HWo * esize(d.dtype));
         const bool need_g = d.demodulate && (p->dweight || p->dstyles);
         const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
+        if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
         st = run_act_grad_gsum_dnoise(d.dtype, p->dy, p->y, p->ep_bias, p->noise, noise_sn, p->dcoefs, N, O, HWo, (float)p->ep_gain, (float)p->ep_alpha,
                                       (float)p->ep_clamp, p->ep_act, dzp_act, need_g ? g : nullptr, p->dbias_no, p->dnoise, per_sample, stream);
         if (st) return st;
         dy_pre = dzp_act;
-    } else if (!p->ep_enable) {
+    } else {
         const bool need_g = d.demodulate && (p->dweight || p->dstyles);
         const int per_sample = (d.noise_mode == VFM_NOISE_N1HW);
         if (p->dnoise) VFM_CUDA_OK(cudaMemsetAsync(p->dnoise, 0, sizeof(float) * (size_t)HWo * (per_sample ? N : 1), stream));
@@ -303,7 +281,7 @@ extern "C" int vfm_modconv_backward(const vfm_modconv_bwd_params* p, void* strea
     } else if (use_tc(d)) {
         cv.off = (cv.off + 255) & ~(size_t)255;
         st = tc_stage1_backward(d, s, dzp, d.up == 2 ? dz_pitch : 0, p->x, p->weight, k, p->dx, p->dstyles ? dsum : nullptr, p->dweight,
-                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream, p->saved_operand, p->saved_operand_lo, act_ready);
+                                (char*)p->workspace + cv.off, p->workspace_bytes - cv.off, stream, p->saved_operand, p->saved_operand_lo);
         if (st) return st;
     } else {
         if (p->dx) {

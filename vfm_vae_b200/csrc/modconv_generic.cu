@@ -530,131 +530,6 @@ __global__ void __launch_bounds__(128) act_grad_gsum_dnoise_kernel(const T* __re
     }
 }
 
-// The same pass when the gradient feeds the tcgen05 backward of a stride-1 fp16 layer: dz is consumed only as the NHWC operand
-// (d[n,o] * dz) of the data / weight gradient GEMMs, so this variant writes THAT tensor (through the 64 x 64 shared-memory transpose of
-// nhwc_prepass_kernel, same roundings: dz to fp16, then d * dz to fp16) and the NCHW dz never exists -- one write and one read of the
-// layer's output-sized tensor less than act_grad_gsum_dnoise_kernel + nhwc_prepass_kernel (5 -> 3 tensor passes).
-// CTA: 256 threads; thread (pg = tid & 7, cl0 = tid >> 3) owns pixels 8 pg .. 8 pg + 7 and channels cl0, cl0 + 32 of every 64 x 64 tile.
-// It walks `ptiles` pixel tiles (outer) x NCT channel tiles (inner): the dnoise sums of a pixel tile live in registers across the
-// channel tiles, the per-channel partials of g / gz in registers across the pixel tiles (one atomic per (CTA, channel) at the end).
-template <int NCT>
-__global__ void __launch_bounds__(256, 2) act_grad_nhwc_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ bias,
-                                                            const float* __restrict__ noise, int64_t noise_sn, const float* __restrict__ dcoefs, int O, int HW,
-                                                            float gain, float alpha, float clamp, int act, __half* __restrict__ act_out, float* g, float* gz,
-                                                            float* dnoise, int64_t dnoise_sn, int ptiles) {
-    __shared__ __half s[64][66];                         // [pixel][channel], 33-word pitch: conflict-free transposed stores
-    __shared__ float s_dn[64];
-    const int n = blockIdx.y, tid = threadIdx.x;
-    const int pg = tid & 7, cl0 = tid >> 3;
-    const int cbase = blockIdx.z * NCT * 64;
-    const float g_pos = gain, g_neg = (act == 3) ? gain * alpha : gain;
-    const float r_pos = 1.f / g_pos, r_neg = 1.f / g_neg;
-    float part[NCT][2], zs[NCT][2], bo[NCT][2], dco[NCT][2];
-#pragma unroll
-    for (int ct = 0; ct < NCT; ct++)
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int c = cbase + ct * 64 + cl0 + 32 * i;
-            part[ct][i] = zs[ct][i] = 0.f;
-            bo[ct][i] = bias ? __half2float(bias[c]) : 0.f;
-            dco[ct][i] = dcoefs[(size_t)n * O + c];
-        }
-    union V8 { uint4 u; __half2 h[4]; };
-    V8 a[2], b[2], an[2], bn[2];                         // this step's dy / y vectors and the next step's (in flight during the transpose)
-    auto fetch = [&](int p0, int ct, V8* av, V8* bv) {
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const size_t off = ((size_t)n * O + cbase + ct * 64 + cl0 + 32 * i) * HW + p0 + 8 * pg;
-            av[i].u = ldg_stream(dy + off);
-            bv[i].u = ldg_stream(y + off);
-        }
-    };
-    const int p_first = blockIdx.x * ptiles * 64;
-    if (p_first < HW) fetch(p_first, 0, a, b);
-    for (int pt = 0; pt < ptiles; pt++) {
-        const int p0 = p_first + pt * 64;
-        if (p0 >= HW) break;                             // uniform over the CTA (HW % 64 == 0: tiles are complete)
-        float nz[8], dn[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) { nz[e] = noise ? noise[(size_t)n * noise_sn + p0 + 8 * pg + e] : 0.f; dn[e] = 0.f; }
-        if (dnoise && tid < 64) s_dn[tid] = 0.f;
-#pragma unroll
-        for (int ct = 0; ct < NCT; ct++) {
-            const int c0 = cbase + ct * 64;
-            // next step: the next channel tile of this pixel tile, else the first channel tile of the next pixel tile
-            const bool has_next = (ct + 1 < NCT) || (pt + 1 < ptiles && p0 + 64 < HW);
-            if (has_next) fetch(ct + 1 < NCT ? p0 : p0 + 64, ct + 1 < NCT ? ct + 1 : 0, an, bn);
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int cl = cl0 + 32 * i;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float2 dv = __half22float2(a[i].h[k]), yv = __half22float2(b[i].h[k]);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int e = 2 * k + h;
-                        const float ya = h ? yv.y : yv.x;
-                        const bool pos = ya > 0.f;
-                        float d = (h ? dv.y : dv.x) * (pos ? g_pos : g_neg);
-                        if (clamp >= 0.f && !(fabsf(ya) < clamp)) d = 0.f;
-                        const __half dq = __float2half_rn(d);
-                        d = __half2float(dq);                    // what act_grad_gsum_dnoise_kernel stores and its consumers read
-                        dn[e] += d;
-                        zs[ct][i] += d;
-                        part[ct][i] = fmaf(d, ya * (pos ? r_pos : r_neg) - bo[ct][i] - nz[e], part[ct][i]);
-                        s[8 * pg + e][cl] = __float2half_rn(d * dco[ct][i]);
-                    }
-                }
-            }
-            __syncthreads();
-            {
-                const int cv = tid & 7, pl0 = tid >> 3;  // 8 threads x 8 channels (16 bytes) per pixel, 32 pixels per pass
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int pl = pl0 + i * 32;
-                    union { uint4 u; uint32_t w[4]; } pk;
-                    const uint32_t* src = (const uint32_t*)&s[pl][cv * 8];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) pk.w[k] = src[k];
-                    *(uint4*)(act_out + ((size_t)n * HW + p0 + pl) * O + c0 + cv * 8) = pk.u;
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 2; i++) { a[i].u = an[i].u; b[i].u = bn[i].u; }
-        }
-        if (dnoise) {
-            // lanes with the same pg (lane & 7) hold the same pixels: fold the 4 channel rows of the warp, then the 8 warps through shared memory
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                dn[e] += __shfl_xor_sync(0xffffffffu, dn[e], 8);
-                dn[e] += __shfl_xor_sync(0xffffffffu, dn[e], 16);
-            }
-            if ((tid & 31) < 8) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) atomicAdd(&s_dn[8 * pg + e], dn[e]);
-            }
-            __syncthreads();
-            if (tid < 64) atomicAdd(&dnoise[(size_t)n * dnoise_sn + p0 + tid], s_dn[tid]);
-            __syncthreads();
-        }
-    }
-    // the 8 lanes pg = 0..7 of a channel: fold, one atomic per (CTA, channel)
-#pragma unroll
-    for (int ct = 0; ct < NCT; ct++)
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            float a = part[ct][i], z = zs[ct][i];
-#pragma unroll
-            for (int m = 1; m < 8; m <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); z += __shfl_xor_sync(0xffffffffu, z, m); }
-            if (pg == 0) {
-                const size_t idx = (size_t)n * O + cbase + ct * 64 + cl0 + 32 * i;
-                if (g) atomicAdd(&g[idx], a / dco[ct][i]);
-                if (gz) atomicAdd(&gz[idx], z);
-            }
-        }
-}
-
 // dW[o,i,k] = M[o,i,k] - a[o]^2 W[o,i,k] sum_n h[n,o] s'[n,i]^2,  h = g d^3          (thread per (o,i))
 __global__ void dw_fix_kernel(float* dw, const float* __restrict__ w, const float* __restrict__ a, const float* __restrict__ g,
                               const float* __restrict__ dcoefs, const float* __restrict__ iscale, int N, int O, int I, int KK) {
@@ -770,28 +645,6 @@ int run_act_grad_gsum_dnoise(int dtype, const void* dy, const void* y, const voi
         act_grad_gsum_dnoise_kernel<float><<<grid, 128, smem, stream>>>((const float*)dy, (const float*)y, (const float*)bias, noise, noise_sn, dcoefs, O, HW, gain, alpha, clamp, act,
                                                                         (float*)dz, g, gz, dnoise, dsn, ops);
     return launch_status("modconv act_grad_gsum_dnoise_kernel");
-}
-// act_grad_nhwc_kernel: fp16, O % 128 == 0, HW % 64 == 0.  g / gz zero-initialised here, dnoise by the caller.
-bool act_grad_nhwc_supported(int dtype, int O, int HW, const void* dy, const void* y) {
-    return dtype == VFM_F16 && O % 128 == 0 && HW % 64 == 0 && HW >= 2048 && aligned16(dy) && aligned16(y);
-}
-int run_act_grad_nhwc(const void* dy, const void* y, const void* bias, const float* noise, int64_t noise_sn, const float* dcoefs, int N, int O, int HW,
-                      float gain, float alpha, float clamp, int act, void* act_out, float* g, float* gz, float* dnoise, int dnoise_per_sample, cudaStream_t stream) {
-    if (!act_grad_nhwc_supported(VFM_F16, O, HW, dy, y) || !aligned16(act_out) || N > 65535) { set_error("modulated_conv2d backward: no NHWC activation-gradient kernel for this layer"); return VFM_ERR_NO_KERNEL; }
-    if (g) VFM_CUDA_OK(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)N * O, stream));
-    if (gz) VFM_CUDA_OK(cudaMemsetAsync(gz, 0, sizeof(float) * (size_t)N * O, stream));
-    // a CTA takes 2 channel tiles (128 channels) x 16 pixel tiles (1024 pixels), or 4 pixel tiles when that leaves fewer than 4 CTAs per SM
-    const int ctiles = O / 64, nct = 2;
-    int ptiles = 16;
-    if ((long long)ceil_div(HW, 64 * ptiles) * N * (ctiles / nct) < 4LL * kNumSMs) ptiles = 4;
-    dim3 grid(ceil_div(HW, 64 * ptiles), N, ctiles / nct);
-    KernelTimer timer("modconv_act_grad_nhwc", stream, 0.0, (double)N * O * HW * 2.0 * 3.0, "o%dhw%d", O, HW);
-    const int64_t dsn = dnoise_per_sample ? HW : 0;
-#define VFM_LAUNCH_AGN(NCT) act_grad_nhwc_kernel<NCT><<<grid, 256, 0, stream>>>((const __half*)dy, (const __half*)y, (const __half*)bias, noise, noise_sn, dcoefs, O, HW, \
-                                                                              gain, alpha, clamp, act, (__half*)act_out, g, gz, dnoise, dsn, ptiles)
-    VFM_LAUNCH_AGN(2);
-#undef VFM_LAUNCH_AGN
-    return launch_status("modconv act_grad_nhwc_kernel");
 }
 int run_dw_fix(float* dw, const float* w, const float* a, const float* g, const float* dcoefs, const float* iscale, int N, int O, int I, int KK, cudaStream_t stream) {
     dw_fix_kernel<<<ceil_div(O * I, 256), 256, 0, stream>>>(dw, w, a, g, dcoefs, iscale, N, O, I, KK);

@@ -1493,20 +1493,9 @@ int tc_stage1_forward(const vfm_modconv_desc& d, const Stage1& s, const void* x,
     return run_tc_conv(f32, false, op, a, nph, stream);
 }
 
-// where tc_stage1_backward expects the NHWC (d * dz) operand inside its workspace: a producer that writes it there (act_grad_nhwc_kernel) passes
-// act_ready = true and no dz
-void* tc_backward_act_buffer(const vfm_modconv_desc& d, const Stage1& s, void* ws, size_t ws_bytes) {
-    Carver cv(ws, ws_bytes);
-    TcWorkspace w;
-    carve_tc(cv, d, s, 1, w);
-    return cv.ok() ? (void*)w.act : nullptr;
-}
-
 int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* dz, int dz_pitch, const void* x, const float* weight, const Coefs& k,
-                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo,
-                       bool act_ready) {
+                       void* dx, float* dsum, float* dweight, void* ws, size_t ws_bytes, cudaStream_t stream, const void* saved_xt, const void* saved_xt_lo) {
     const bool f32 = is_f32(d);
-    if (act_ready && f32) { set_error("modulated_conv2d backward: a pre-built gradient operand is fp16 only"); return VFM_ERR_INVALID; }
     const int N = d.batch, I = d.in_channels, O = d.out_channels, KK = d.kh * d.kw;
     Carver cv(ws, ws_bytes);
     TcWorkspace w;
@@ -1527,7 +1516,7 @@ int tc_stage1_backward(const vfm_modconv_desc& d, const Stage1& s, const void* d
         st = launch_status("modconv gscale_kernel"); if (st) return st;
         gs = w.gs;
     }
-    if (!act_ready) { st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream, nullptr, s.zw, dz_pitch > 0 ? dz_pitch : s.zw); if (st) return st; }
+    st = run_prepass(d.dtype, f32, dz, k.d, gs, w.act, w.act_lo, N, O, s.zh * s.zw, stream, nullptr, s.zw, dz_pitch > 0 ? dz_pitch : s.zw); if (st) return st;
     if (dx) {
         // dxpre[n,i,p] = sum_{o,t} (a*W)[o,i,widx(t)] * (d*dz)[n,o,z(p,t)];  dx = s' * dxpre;  dsum = sum_p x * dxpre
         TapTable dt; int sn, sd;

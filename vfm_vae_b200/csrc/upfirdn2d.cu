@@ -1010,23 +1010,46 @@ __global__ void __launch_bounds__(256) replicate_blur_edges_kernel(const T* __re
     if (idx >= planes * border) return;
     const int64_t plane = idx / border;
     int e = (int)(idx - plane * border), jy, jx;
+    const bool e_col = e >= 2 * W;
     if (e < W) { jy = 0; jx = e; }
     else if (e < 2 * W) { jy = H - 1; jx = e - W; }
     else { e -= 2 * W; jy = 1 + (e >> 1); jx = (e & 1) ? W - 1 : 0; }
     const int cy = (jy == 0) ? 0 : (jy == H - 1 ? 2 : 1), cx = (jx == 0) ? 0 : (jx == W - 1 ? 2 : 1);
     const T* dp = dy + plane * (int64_t)H * W;
     float acc = 0.f;
+    if (e_col && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15u) == 0) {
+        // first / last column: adjacent lanes sit in different rows, so every scalar load of a warp touches 32 sectors (the kernel was bound
+        // by exactly that: 15 loads x 32 sectors per warp).  The <= 3 columns a row contributes lie inside one aligned group of 4: one 8- /
+        // 16-byte load per row instead of three scalar ones
+        const int cb = (jx == 0) ? 0 : W - 4;
 #pragma unroll
-    for (int a = -P; a <= P; a++) {
-        const int iy = jy + a;
-        if (iy < 0 || iy >= H) continue;
-        const float* grow = &G[cy * K + a + P][cx * K + P];
-        const T* drow = dp + (int64_t)iy * W + jx;
+        for (int a = -P; a <= P; a++) {
+            const int iy = jy + a;
+            if (iy < 0 || iy >= H) continue;
+            const float* grow = &G[cy * K + a + P][cx * K + P];
+            struct alignas(4 * sizeof(T)) { T v[4]; } q;
+            q = *reinterpret_cast<const decltype(q)*>(dp + (int64_t)iy * W + cb);
 #pragma unroll
-        for (int b = -P; b <= P; b++) {
-            const int ix = jx + b;
-            if (ix < 0 || ix >= W) continue;
-            acc = fmaf(grow[b], to_acc(drow[b]), acc);
+            for (int b = -P; b <= P; b++) {
+                const int ix = jx + b;
+                if (ix < 0 || ix >= W) continue;
+                const int o = ix - cb;            // 0..3
+                acc = fmaf(grow[b], to_acc(o == 0 ? q.v[0] : o == 1 ? q.v[1] : o == 2 ? q.v[2] : q.v[3]), acc);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = -P; a <= P; a++) {
+            const int iy = jy + a;
+            if (iy < 0 || iy >= H) continue;
+            const float* grow = &G[cy * K + a + P][cx * K + P];
+            const T* drow = dp + (int64_t)iy * W + jx;
+#pragma unroll
+            for (int b = -P; b <= P; b++) {
+                const int ix = jx + b;
+                if (ix < 0 || ix >= W) continue;
+                acc = fmaf(grow[b], to_acc(drow[b]), acc);
+            }
         }
     }
     dx[plane * (int64_t)H * W + (int64_t)jy * W + jx] = from_acc<T, float>(acc);

@@ -779,13 +779,17 @@ struct WgTcArgs {
 //   sd == 1: the tap shift is applied to the x operand (B), the dz tile (A) is the same for every tap, so the two blocks may
 //            belong to different taps -- also 128-channel layers get N = 256 (shared-memory and L2 traffic per MMA drop by 25%);
 //   sd == 2: the shift / stride 2 sits on the dz operand, both blocks share the tap and cover 256 input channels.
-template <bool SPLIT>
+// MB = 2 (fp16, O % 256 == 0): the CTA owns TWO 128-channel row blocks (two A tiles, two accumulators = all 512 TMEM columns) that share the B
+// tile: 64 KB of operands per 1024 tensor-pipe cycles instead of 48 KB per 512 -- the kernel is bound by operand delivery from L2 (ncu:
+// tensor pipe 55-58 % with MB = 1, profiles/r02_ncu_full_bwd_*.md), so a third less traffic per MMA is the lever; 3 stages of 64 KB.
+template <bool SPLIT, int MB>
 __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, WgTcArgs p) {
-    constexpr int A_OP = WOP_BYTES, B_OP = 2 * WOP_BYTES;                    // 16 KB + 32 KB
+    static_assert(MB == 1 || !SPLIT, "two row blocks need the TMEM columns the split accumulators use");
+    constexpr int A_OP = MB * WOP_BYTES, B_OP = 2 * WOP_BYTES;               // 16 (32) KB + 32 KB
     constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_OP + B_OP);
-    constexpr int NST = (192 * 1024) / STAGE_BYTES;                          // 4 (fp16) / 2 (split)
-    constexpr int TMEM_COLS = SPLIT ? 512 : 256;
+    constexpr int NST = (192 * 1024) / STAGE_BYTES;                          // 4 (fp16) / 3 (fp16, MB = 2) / 2 (split)
+    constexpr int TMEM_COLS = (SPLIT || MB == 2) ? 512 : 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = (uint64_t*)(smem + NST * STAGE_BYTES);
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // job -> output-channel block and column blocks
-    const int o0 = (blockIdx.x / p.jobs_per_o) * 128;
+    const int o0 = (blockIdx.x / p.jobs_per_o) * (128 * MB);
     const int jc = blockIdx.x % p.jobs_per_o;
     const int ks = blockIdx.y;
     int btap[2], bi0[2], nb;
@@ -846,8 +850,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                 // sd == 1: tiles walk the dz grid, x is read at (z - tap_a);  sd == 2: tiles walk the x grid, dz at (q*2 + tap_a)
                 const int aw = (p.sd == 1) ? w0 : w0 * p.sd + p.tap_ax[btap[0]], ah = (p.sd == 1) ? h0 : h0 * p.sd + p.tap_ay[btap[0]];
                 uint8_t* sa = smem + s * STAGE_BYTES;
-                tma_load_4d(sa, &tmA, &full_bar[s], o0, aw, ah, n0);
-                tma_load_4d(sa + WBOX_BYTES, &tmA, &full_bar[s], o0 + 64, aw, ah, n0);
+#pragma unroll
+                for (int m = 0; m < MB; m++) {
+                    tma_load_4d(sa + m * WOP_BYTES, &tmA, &full_bar[s], o0 + m * 128, aw, ah, n0);
+                    tma_load_4d(sa + m * WOP_BYTES + WBOX_BYTES, &tmA, &full_bar[s], o0 + m * 128 + 64, aw, ah, n0);
+                }
                 if (SPLIT) {
                     tma_load_4d(sa + A_OP + B_OP, &tmAlo, &full_bar[s], o0, aw, ah, n0);
                     tma_load_4d(sa + A_OP + B_OP + WBOX_BYTES, &tmAlo, &full_bar[s], o0 + 64, aw, ah, n0);
@@ -882,6 +889,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                     const uint64_t ko = (uint64_t)((k * 16 * 128) >> 4);     // 16 pixel rows of 128 bytes
                     const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
                     umma_f16(tmem_base, adesc + ko, bdesc + ko, idesc, first);
+                    if (MB == 2) umma_f16(tmem_base + 256, make_mnmajor_sw128_desc(sa + WOP_BYTES, WBOX_BYTES) + ko, bdesc + ko, idesc, first);
                     if (SPLIT) {
                         umma_f16(tmem_base + 256, adesc + ko, bdesc_lo + ko, idesc, first);
                         umma_f16(tmem_base + 256, adesc_lo + ko, bdesc + ko, idesc, 1u);
@@ -893,16 +901,18 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
         }
     } else {
         const int lg = warp & 3;
-        const int o = o0 + lg * 32 + lane;
-        const float rs = p.rowscale[o] * (p.gscale ? *p.gscale : 1.f);
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        for (int j = 0; j < nb; j++) {
+#pragma unroll 1
+        for (int mj = 0; mj < MB * nb; mj++) {
+            const int m = mj / nb, j = mj - m * nb;
+            const int o = o0 + m * 128 + lg * 32 + lane;
+            const float rs = p.rowscale[o] * (p.gscale ? *p.gscale : 1.f);
             float* dst = p.dw + ((size_t)o * p.I + bi0[j]) * p.KK + p.tap_widx[btap[j]];
 #pragma unroll 1
             for (int q = 0; q < 128 / 16; q++) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(j * 128 + q * 16), v);
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(m * 256 + j * 128 + q * 16), v);
                 if (SPLIT) {
                     float v1[16];
                     tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + j * 128 + q * 16), v1);
@@ -1364,7 +1374,8 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     const int tiles = a.tiles_w * a.tiles_h * a.tiles_n;
     a.ib = I / 128;
     a.jobs_per_o = (s.sd == 1) ? ceil_div(a.ntaps * a.ib, 2) : a.ntaps * ceil_div(a.ib, 2);
-    const int jobs = (O / 128) * a.jobs_per_o;
+    const int mb = (!f32 && O % 256 == 0) ? 2 : 1;          // row blocks (of 128 output channels) per CTA
+    const int jobs = (O / (128 * mb)) * a.jobs_per_o;
     a.ksplit = max(1, min(tiles, (2 * kNumSMs + jobs / 2) / jobs));
     CUtensorMap maps[4];
     uint64_t adims[4] = {(uint64_t)O, (uint64_t)s.zw, (uint64_t)s.zh, (uint64_t)N};
@@ -1382,11 +1393,14 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     const double flops = 2.0 * N * d.in_h * d.in_w * (double)O * I * a.ntaps;
     KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0, "i%do%dh%ds%d", I, O, d.in_h, s.sd);
     if (f32) {
-        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wgrad_tc_kernel<true><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_tc_kernel<true, 1><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    } else if (mb == 2) {
+        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_tc_kernel<false, 2><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     } else {
-        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wgrad_tc_kernel<false><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+        VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_tc_kernel<false, 1><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     }
     return launch_status("modconv wgrad_tc_kernel");
 }

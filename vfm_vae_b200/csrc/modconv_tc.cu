@@ -759,6 +759,19 @@ constexpr int WK = 64;                      // pixels per K block
 constexpr int WBOX_BYTES = WK * 128;        // one [64 px][64 ch] box = 8 KB
 constexpr int WOP_BYTES = 2 * WBOX_BYTES;   // 128 channels
 
+// 16-byte vector reduction (sm_90+): one L2 atomic request for four fp32 sums.  The split-K epilogue of the weight gradient is bound by
+// the L2's atomic rate (~125 scalar atomics per ns chip-wide measured: 148 CTAs x 32 K atomics = 40 us per wave), so it accumulates into a
+// [tap][O][I] scratch whose rows are contiguous along the input channels an epilogue thread holds, with a quarter of the requests.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// dweight[o][i][k] = scratch[k][o][i]
+__global__ void __launch_bounds__(256) dw_scatter_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int OI, int KK) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= OI) return;
+    for (int k = 0; k < KK; k++) dw[(size_t)idx * KK + k] = scratch[(size_t)k * OI + idx];
+}
+
 struct WgTcArgs {
     int tw, th, tn;              // pixel tile (tw*th*tn == 64)
     int tiles_w, tiles_h, tiles_n;
@@ -769,7 +782,7 @@ struct WgTcArgs {
     int O, I, KK;
     int ib;                      // I / 128
     int jobs_per_o;              // column-block pairs per 128 output channels
-    float* dw;                   // [O][I][KK] fp32, accumulated with atomics
+    float* dw;                   // [KK][O][I] fp32 scratch (workspace), accumulated with 16-byte vector reductions; dw_scatter_kernel re-lays it out
     const float* rowscale;       // a[o]
     const float* gscale;         // device scalar multiplied into the result, or NULL
 };
@@ -908,7 +921,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
             const int m = mj / nb, j = mj - m * nb;
             const int o = o0 + m * 128 + lg * 32 + lane;
             const float rs = p.rowscale[o] * (p.gscale ? *p.gscale : 1.f);
-            float* dst = p.dw + ((size_t)o * p.I + bi0[j]) * p.KK + p.tap_widx[btap[j]];
+            float* dst = p.dw + ((size_t)p.tap_widx[btap[j]] * p.O + o) * p.I + bi0[j];      // 128 consecutive input channels of row o
 #pragma unroll 1
             for (int q = 0; q < 128 / 16; q++) {
                 float v[16];
@@ -920,7 +933,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const __grid_constant_
                     for (int c = 0; c < 16; c++) v[c] += v1[c] * (1.f / kLoScale);
                 }
 #pragma unroll
-                for (int c = 0; c < 16; c++) atomicAdd(dst + (size_t)(q * 16 + c) * p.KK, v[c] * rs);
+                for (int c = 0; c < 16; c += 4) red_add_v4(dst + q * 16 + c, v[c] * rs, v[c + 1] * rs, v[c + 2] * rs, v[c + 3] * rs);
             }
         }
         tc_fence_before();
@@ -1228,7 +1241,13 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     if (mnp && (f32 || pair || dgrad || a.a_s != 1 || op.ntaps != 1)) { set_error("tcgen05 conv: direct NCHW operands need an fp16 1x1 forward conv"); return VFM_ERR_INVALID; }
     if (nphases != 1 && nphases != 4) { set_error("tcgen05 conv: unsupported phase structure"); return VFM_ERR_INVALID; }
     if (pair && (dgrad || a.ep.enable || a.add)) { set_error("tcgen05 conv: the paired-phase kernel has no fused epilogue"); return VFM_ERR_INVALID; }
-    const int npix = (!f32 && !pair) ? 256 : 128;
+    // paired up=2 phases: 256-pixel tiles need all 512 TMEM columns for one item (no epilogue / MMA overlap) but a third less operand traffic per
+    // MMA -- measured faster for the 65- and 129-wide phase grids (1.78 -> 1.58, 2.13 -> 1.98 ms per layer), much slower for the 33-wide one
+    // (32-pixel-wide tiles waste half of the second tile column)
+    int pair_w = 0;
+    for (int i = 0; i < nphases; i++) pair_w = max(pair_w, a.ph[i].Wg);
+    const bool pair256 = pair && !f32 && pair_w >= 64;
+    const int npix = (!f32 && (!pair || pair256)) ? 256 : 128;
     int Hg = 0, Wg = 0;
     double taps_px = 0;
     for (int i = 0; i < nphases; i++) { Hg = max(Hg, a.ph[i].Hg); Wg = max(Wg, a.ph[i].Wg); taps_px += (double)a.ph[i].ntaps * a.ph[i].Hg * a.ph[i].Wg; }
@@ -1277,6 +1296,7 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
     if (!f32) {
         if (dgrad) return launch_tc<__half, true, false, false, 256>(maps, a, grid, flops, stream);
+        if (pair && pair256) return launch_tc<__half, false, false, true, 256>(maps, a, grid, flops, stream);
         if (pair) return launch_tc<__half, false, false, true, 128>(maps, a, grid, flops, stream);
         return launch_tc<__half, false, false, false, 256>(maps, a, grid, flops, stream);
     }
@@ -1314,6 +1334,7 @@ struct TcWorkspace {
     __half *xt, *xt_lo;                      // backward only: x*s' NHWC for the weight gradient
     __half* wt_mod; float* pb;               // forward, 1x1 direct-NCHW path: per-sample weights [N][O][I] and folded-shift bias [N][O]
     float *a_scale, *a_shift, *o_scale, *gs; // gs: [0] gk, [1] 1/gk, [2] c2g, [3] 1/(gk*c2g)
+    float* dw_scratch;                       // backward only: [KK][O][I] accumulation buffer of the weight gradient
     unsigned int* amax;
 };
 
@@ -1345,6 +1366,7 @@ void carve_tc(Carver& cv, const vfm_modconv_desc& d, const Stage1& s, int direct
     w.o_scale = cv.take<float>(nout);
     w.gs = cv.take<float>(4);
     w.amax = cv.take<unsigned int>(4);
+    w.dw_scratch = direction == 1 ? cv.take<float>(wel) : nullptr;
 }
 
 // 64-pixel K tile with the least padding waste for an H x W grid
@@ -1366,7 +1388,8 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     a.ntaps = s.taps.ntaps; a.sd = s.sd;
     for (int t = 0; t < a.ntaps; t++) { a.tap_ay[t] = -s.taps.off_y[t]; a.tap_ax[t] = -s.taps.off_x[t]; a.tap_widx[t] = s.taps.widx[t]; }
     a.O = O; a.I = I; a.KK = d.kh * d.kw;
-    a.dw = dweight; a.rowscale = rowscale; a.gscale = gscale;
+    a.dw = w.dw_scratch; a.rowscale = rowscale; a.gscale = gscale;
+    VFM_CUDA_OK(cudaMemsetAsync(w.dw_scratch, 0, sizeof(float) * (size_t)O * I * a.KK, stream));
     // sd == 1: the pixel tiles walk the dz grid (== x grid for the padded stride-1 conv) and the shift is on x
     const int gw = (s.sd == 1) ? s.zw : d.in_w, gh = (s.sd == 1) ? s.zh : d.in_h;
     pick_wtile(gh, gw, a.tw, a.th, a.tn);
@@ -1376,7 +1399,20 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     a.jobs_per_o = (s.sd == 1) ? ceil_div(a.ntaps * a.ib, 2) : a.ntaps * ceil_div(a.ib, 2);
     const int mb = (!f32 && O % 256 == 0) ? 2 : 1;          // row blocks (of 128 output channels) per CTA
     const int jobs = (O / (128 * mb)) * a.jobs_per_o;
-    a.ksplit = max(1, min(tiles, (2 * kNumSMs + jobs / 2) / jobs));
+    // split-K factor: a CTA's time is (its share of the pixel tiles) x (time of one 64-pixel K block) + its epilogue, and the epilogue -- 32 K
+    // (64 K with two row blocks) fp32 sums through L2 atomics while every other CTA of the wave does the same -- costs as much as ~35 K
+    // blocks of an fp16 kernel.  Waves of one CTA per SM run back to back, so: minimise waves x (blocks per CTA x t_block + t_epilogue).
+    {
+        const double t_block = f32 ? 3.0 : (double)mb;             // in units of one 128 x 256 x 64 MMA block (512 tensor-pipe cycles)
+        const double t_epi = 35.0 * mb;
+        double best = 1e30;
+        a.ksplit = 1;
+        for (int ks = 1; ks <= tiles && (long long)jobs * ks <= 4LL * kNumSMs; ks++) {
+            const double waves = (double)ceil_div(jobs * ks, kNumSMs);
+            const double t = waves * (ceil_div(tiles, ks) * t_block + t_epi);
+            if (t < best - 1e-9) { best = t; a.ksplit = ks; }
+        }
+    }
     CUtensorMap maps[4];
     uint64_t adims[4] = {(uint64_t)O, (uint64_t)s.zw, (uint64_t)s.zh, (uint64_t)N};
     uint32_t abox[4] = {64u, (uint32_t)(a.tw * s.sd), (uint32_t)(a.th * s.sd), (uint32_t)a.tn};
@@ -1391,6 +1427,7 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
     if (grid.y > 65535) { set_error("tcgen05 wgrad: grid too large"); return VFM_ERR_INVALID; }
     const size_t smem = (size_t)192 * 1024 + 1024 + 256;
     const double flops = 2.0 * N * d.in_h * d.in_w * (double)O * I * a.ntaps;
+    {
     KernelTimer timer(f32 ? "modconv_tc_wgrad_split" : "modconv_tc_wgrad", stream, flops, 0.0, "i%do%dh%ds%d", I, O, d.in_h, s.sd);
     if (f32) {
         VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1402,7 +1439,10 @@ int run_tc_wgrad(bool f32, const vfm_modconv_desc& d, const Stage1& s, const TcW
         VFM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         wgrad_tc_kernel<false, 1><<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     }
-    return launch_status("modconv wgrad_tc_kernel");
+    }
+    st = launch_status("modconv wgrad_tc_kernel"); if (st) return st;
+    dw_scatter_kernel<<<ceil_div(O * I, 256), 256, 0, stream>>>(w.dw_scratch, dweight, O * I, a.KK);
+    return launch_status("modconv dw_scatter_kernel");
 }
 
 }  // namespace

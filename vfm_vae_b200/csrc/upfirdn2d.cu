@@ -1006,8 +1006,8 @@ __global__ void __launch_bounds__(256) replicate_blur_edges_kernel(const T* __re
     }
     __syncthreads();
     const int border = 2 * W + 2 * (H - 2);
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= planes * border) return;
+    // grid-stride over the border elements: the table above is built once per CTA, not once per 256 elements
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < planes * border; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t plane = idx / border;
     int e = (int)(idx - plane * border), jy, jx;
     const bool e_col = e >= 2 * W;
@@ -1053,6 +1053,7 @@ __global__ void __launch_bounds__(256) replicate_blur_edges_kernel(const T* __re
         }
     }
     dx[plane * (int64_t)H * W + (int64_t)jy * W + jx] = from_acc<T, float>(acc);
+    }
 }
 
 }  // namespace
@@ -1066,8 +1067,7 @@ extern "C" int vfm_replicate_blur_edges(const vfm_replicate_blur_edges_params* p
     VFM_CHECK_ARG(p->k == 3 || p->k == 5, "replicate_blur_edges: k must be 3 or 5 (got %d)", p->k);
     VFM_CHECK_ARG(p->planes >= 1 && p->h >= p->k && p->w >= p->k, "replicate_blur_edges: planes must be at least k x k");
     const int64_t total = p->planes * (2 * (int64_t)p->w + 2 * ((int64_t)p->h - 2));
-    VFM_CHECK_ARG(ceil_div64(total, 256) <= 0x7fffffffLL, "replicate_blur_edges: grid too large");
-    const unsigned blocks = (unsigned)ceil_div64(total, 256);
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 16);
     const int es = p->dtype == VFM_F16 ? 2 : 4;
     KernelTimer timer("replicate_blur_edges", stream, 0.0, (double)total * es * 2.0, "h%dw%d", p->h, p->w);
     if (p->dtype == VFM_F16) {

@@ -193,6 +193,7 @@ struct TcArgs {
     int tw, th, tn;            // pixel tile = tw x th pixels of tn consecutive samples (tw*th*tn == NPIX), all powers of two
     int tw_sh, th_sh;          // log2(tw), log2(th)
     int tiles_w, tiles_h;      // tile grid (covers the largest phase)
+    int org_w, org_h;          // origin of the tile grid in phase-grid coordinates (edge strips of the up=2 phases start at the last column / row)
     int N, Nout;
     int out_H, out_W, out_s;   // output tensor [N, Nout, out_H, out_W]; output coordinate = g*out_s + o{y,x}
     int out_pitch;             // row pitch of the output tensor in elements (>= out_W; planes are out_H*out_pitch apart)
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         c0 = (t % c_tiles) * CH; t /= c_tiles;
         const int tile_w = t % p.tiles_w; t /= p.tiles_w;
         const int tile_h = t % p.tiles_h; t /= p.tiles_h;
-        n0 = t * p.tn; h0 = tile_h * p.th; w0 = tile_w * p.tw;
+        n0 = t * p.tn; h0 = p.org_h + tile_h * p.th; w0 = p.org_w + tile_w * p.tw;
         const TcPhase& ph = p.ph[grp * NSUB];                  // PAIR: px = 0 has the larger (or equal) grid
         return h0 < ph.Hg && w0 < ph.Wg;
     };
@@ -1236,7 +1237,10 @@ struct TcOperands {
 // One implicit-GEMM conv.  `args` must have ph[], out*, a_s, scales, add/aux already filled in; this sets the tiling.
 // nphases == 4: the phases are the sub-pixel phases of a stride-2 transposed conv in the order 2*py + px (PAIR kernel).
 // mnp: op.act is the NCHW fp16 tensor itself and op.wt the per-sample weights [N][ntaps][Nout][Cin] (1x1 convs only, see conv_tc_kernel).
-int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream, bool mnp = false) {
+// tile shape / origin of one launch when the caller fixes them (edge strips); flop_px = sum over phases of taps x pixels this launch computes
+struct TileOverride { int tw, th, tn, org_w, org_h; double flop_px; };
+
+int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream, bool mnp, const TileOverride* ov) {
     const bool pair = (nphases == 4);
     if (mnp && (f32 || pair || dgrad || a.a_s != 1 || op.ntaps != 1)) { set_error("tcgen05 conv: direct NCHW operands need an fp16 1x1 forward conv"); return VFM_ERR_INVALID; }
     if (nphases != 1 && nphases != 4) { set_error("tcgen05 conv: unsupported phase structure"); return VFM_ERR_INVALID; }
@@ -1246,7 +1250,7 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     // (32-pixel-wide tiles waste half of the second tile column)
     int pair_w = 0;
     for (int i = 0; i < nphases; i++) pair_w = max(pair_w, a.ph[i].Wg);
-    const bool pair256 = pair && !f32 && pair_w >= 64;
+    const bool pair256 = pair && !f32 && pair_w >= 64 && !ov;
     const int npix = (!f32 && (!pair || pair256)) ? 256 : 128;
     int Hg = 0, Wg = 0;
     double taps_px = 0;
@@ -1256,8 +1260,13 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
         a.tw = (op.Wa % 256 == 0) ? 256 : (op.Wa % 128 == 0 ? 128 : 64);
         a.th = npix / a.tw; a.tn = 1;
     }
+    if (ov) {
+        if (ov->tw * ov->th * ov->tn != npix) { set_error("tcgen05 conv: edge-strip tile does not match the kernel's pixel count"); return VFM_ERR_INVALID; }
+        a.tw = ov->tw; a.th = ov->th; a.tn = ov->tn; a.org_w = ov->org_w; a.org_h = ov->org_h;
+        taps_px = ov->flop_px;
+    }
     a.tw_sh = ilog2(a.tw); a.th_sh = ilog2(a.th);
-    a.tiles_w = ceil_div(Wg, a.tw); a.tiles_h = ceil_div(Hg, a.th);
+    a.tiles_w = ceil_div(Wg - a.org_w, a.tw); a.tiles_h = ceil_div(Hg - a.org_h, a.th);
     a.kchunks = op.Cin / BK;
     a.N = op.N; a.Nout = op.Nout;
     a.ngroups = pair ? 2 : 1;
@@ -1303,6 +1312,38 @@ int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphase
     if (dgrad) return launch_tc<float, true, true, false, 128>(maps, a, grid, flops, stream);
     if (pair) return launch_tc<float, false, true, true, 128>(maps, a, grid, flops, stream);
     return launch_tc<float, false, true, false, 128>(maps, a, grid, flops, stream);
+}
+
+// The four sub-pixel phase grids of the stride-2 transposed conv are (H+1) x (W+1), (H+1) x W, H x (W+1) and H x W for a power-of-two H x W
+// input: the "+1" row and column of the (2H+1) x (2W+1) intermediate.  Tiled as one grid, the extra column and row cost a whole tile column and
+// row of zero-filled MMA work -- 2.7x the useful work on the 17 x 17 grids of the 16x16 -> 32x32 layer, 1.5x at 65 x 65, 1.2x at 129 x 129.  So:
+// one launch over the exact H x W part of every phase, one for the last column (a 1-pixel-wide strip, all rows incl. the corner) and one for the
+// last row (a 1-pixel-high strip) with tiles shaped like the strips.
+int run_tc_conv(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int nphases, cudaStream_t stream, bool mnp = false) {
+    a.org_w = a.org_h = 0;
+    if (nphases != 4) return run_tc_conv_one(f32, dgrad, op, a, nphases, stream, mnp, nullptr);
+    int Hmax = 0, Wmax = 0, Hmin = 1 << 30, Wmin = 1 << 30;
+    for (int i = 0; i < 4; i++) { Hmax = max(Hmax, a.ph[i].Hg); Wmax = max(Wmax, a.ph[i].Wg); Hmin = min(Hmin, a.ph[i].Hg); Wmin = min(Wmin, a.ph[i].Wg); }
+    const bool pow2 = (Hmin & (Hmin - 1)) == 0 && (Wmin & (Wmin - 1)) == 0;
+    if (!(pow2 && Hmax == Hmin + 1 && Wmax == Wmin + 1 && Wmin >= 16 && Hmin >= 16)) return run_tc_conv_one(f32, dgrad, op, a, 4, stream, false, nullptr);
+    TcArgs m = a;                                                  // the exact H x W part of every phase
+    for (int i = 0; i < 4; i++) { m.ph[i].Hg = Hmin; m.ph[i].Wg = Wmin; }
+    int st = run_tc_conv_one(f32, dgrad, op, m, 4, stream, false, nullptr); if (st) return st;
+    {   // last column of the phases that have one (px = 0), every row
+        TileOverride c;
+        c.tw = 1; c.th = min(128, 1 << ilog2(Hmax)); c.tn = 128 / c.th; c.org_w = Wmin; c.org_h = 0; c.flop_px = 0;
+        for (int i = 0; i < 4; i++) if (a.ph[i].Wg > Wmin) c.flop_px += (double)a.ph[i].ntaps * a.ph[i].Hg;
+        st = run_tc_conv_one(f32, dgrad, op, a, 4, stream, false, &c); if (st) return st;
+    }
+    {   // last row of the phases that have one (py = 0), without the corner
+        TcArgs r = a;
+        for (int i = 0; i < 4; i++) r.ph[i].Wg = Wmin;
+        TileOverride o;
+        o.tw = min(128, Wmin); o.th = 1; o.tn = 128 / o.tw; o.org_w = 0; o.org_h = Hmin; o.flop_px = 0;
+        for (int i = 0; i < 4; i++) if (a.ph[i].Hg > Hmin) o.flop_px += (double)a.ph[i].ntaps * Wmin;
+        st = run_tc_conv_one(f32, dgrad, op, r, 4, stream, false, &o); if (st) return st;
+    }
+    return VFM_OK;
 }
 
 int run_prepass(int dtype, bool split, const void* x, const float* scale, const float* gscale, __half* xt, __half* xt_lo, int N, int C, int HW, cudaStream_t stream,

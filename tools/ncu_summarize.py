@@ -3,6 +3,8 @@
 
     python tools/ncu_summarize.py launches <launches.csv> <out.md> [title]
         per-kernel launch counts, total time and share of a `--metrics gpu__time_duration.sum --csv` launch list
+    python tools/ncu_summarize.py merge <out.json> <traffic1.json> <traffic2.json> ...
+        launch-weighted mean DRAM bytes per kernel name over several `full` jsons (the per-layer probes of one step)
     python tools/ncu_summarize.py full <report.ncu-rep> <out.md> [out.json]
         one row per captured launch of a `--set full` report: duration, DRAM bytes, tensor-pipe / DRAM / issue utilisation;
         out.json gets the per-kernel-name average DRAM traffic per launch (bench.py reads it for roofline.traffic)
@@ -46,6 +48,19 @@ def launches(path, out, title):
             f.write(f'| `{k}` | {c} | {ms:.2f} | {100 * ms / total:.1f}% |\n')
 
 
+def merge(out_json, paths):
+    acc = {}
+    for path in paths:
+        for k, v in json.load(open(path)).items():
+            k = re.sub(r'void |unnamed>::|modconv::|vfm::', '', k)
+            a = acc.setdefault(k, {'launches': 0, 'bytes': 0.0, 'probes': []})
+            a['launches'] += v['launches']
+            a['bytes'] += v['launches'] * v['dram_bytes_per_launch']
+            a['probes'].append(path.split('/')[-1].replace('r02_traffic_', '').replace('.json', ''))
+    res = {k: {'launches': v['launches'], 'dram_bytes_per_launch': v['bytes'] / v['launches'], 'probes': v['probes']} for k, v in acc.items()}
+    json.dump(res, open(out_json, 'w'), indent=1)
+
+
 def full(rep, out, out_json):
     txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
@@ -84,6 +99,9 @@ def full(rep, out, out_json):
         json.dump({k: {'launches': c, 'dram_bytes_per_launch': b / c} for k, (c, b) in traffic.items()}, open(out_json, 'w'), indent=1)
 
 
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'merge':
+    merge(sys.argv[2], sys.argv[3:])
+    sys.exit(0)
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else 'ncu launch list')

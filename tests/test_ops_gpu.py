@@ -910,7 +910,9 @@ def test_fused_convnext_mlp(cfg, dtype):
 @pytest.mark.parametrize('cfg', [dict(shape=(2, 128, 16, 16), groups=32), dict(shape=(3, 32, 7, 5), groups=8), dict(shape=(1, 512, 8, 8), groups=32),
                                  dict(shape=(2, 64, 64, 64), groups=16),
                                  # backward reduce in warp teams: more channels per group than warps (24, 20), a team count that does not divide 16 (3)
-                                 dict(shape=(1, 768, 8, 8), groups=32), dict(shape=(1, 640, 16, 16), groups=32), dict(shape=(2, 96, 12, 12), groups=32)],
+                                 dict(shape=(1, 768, 8, 8), groups=32), dict(shape=(1, 640, 16, 16), groups=32), dict(shape=(2, 96, 12, 12), groups=32),
+                                 # N*C = 66560 planes: more than gridDim.y allows (the row kernels index planes through a 1-D grid)
+                                 dict(shape=(130, 512, 4, 4), groups=32)],
                          ids=lambda c: 'x'.join(map(str, c['shape'])))
 def test_group_norm32_forward_backward(cfg, dtype):
     """GroupNorm32 (fp32 statistics, output in x.dtype) forward and gradients against torch.nn.functional.group_norm in fp64."""
@@ -934,7 +936,7 @@ def test_group_norm32_forward_backward(cfg, dtype):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float16], ids=['fp32', 'fp16'])
-@pytest.mark.parametrize('shape', [(2, 128, 16, 16), (3, 6, 7, 5), (1, 32, 64, 64)], ids=lambda s: 'x'.join(map(str, s)))
+@pytest.mark.parametrize('shape', [(2, 128, 16, 16), (3, 6, 7, 5), (1, 32, 64, 64), (130, 512, 4, 4)], ids=lambda s: 'x'.join(map(str, s)))
 def test_layer_scale_residual(shape, dtype):
     """(gamma*y + x)*sqrt2 of the residual layers (networks/generator.py:272-274), forward and gradients."""
     from vfm_vae_b200.torch_utils.ops.layer_scale import layer_scale_residual

@@ -96,7 +96,7 @@ def timed(step):
 
 def decode():
     with torch.no_grad():
-        r = net(z, ws)
+        r = net(z, ws, None, None)
     return r
 
 
@@ -105,7 +105,7 @@ opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.0, 0.99))
 
 def train():
     opt.zero_grad(set_to_none=True)
-    r = net(z, ws)
+    r = net(z, ws, None, None)
     img = r[0] if isinstance(r, (tuple, list)) else r
     multi = r[1] if isinstance(r, (tuple, list)) and len(r) > 1 and isinstance(r[1], (tuple, list)) else []
     loss = img.float().square().mean() + sum(m.float().square().mean() for m in multi)

@@ -327,14 +327,39 @@ def test_pixel_shuffle2_autograd():
 
 @pytest.mark.parametrize('k', [3, 5])
 @pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
-def test_blur2d_replicate_autograd(k, dtype):
+@pytest.mark.parametrize('shape', [(2, 3, 7, 10), (1, 2, 5, 5), (3, 1, 9, 16), (1, 4, 12, 6)], ids=lambda s: 'x'.join(map(str, s)))
+def test_replicate_blur_edges_entry_point(k, dtype, shape):
+    """``vfm_replicate_blur_edges`` on its own (the autograd wrapper only reaches it with widths that are a multiple of 8): border elements against
+    the oracle's model -- widths that are not a multiple of 4 take the scalar column loads, the others the vector ones -- and every interior
+    element of dx left untouched."""
+    from vfm_vae_b200.plugins import upfirdn2d_plugin as P
+    g = torch.Generator().manual_seed(23)
+    f = torch.randn(k, k, generator=g)
+    dyq = torch.randn(shape, generator=g).to(dtype)
+    marker = torch.full(shape, 7.0, dtype=dtype)
+    dx = P.replicate_blur_edges(dyq.to(DEV), marker.to(DEV).clone(), f.to(DEV))
+    want = O.replicate_blur_edges(dyq.double(), f.double(), torch.full(shape, 7.0, dtype=torch.float64))
+    tol = 2e-3 if dtype == torch.float16 else 1e-5
+    assert rel_err(dx, want) <= tol
+    assert torch.equal(dx[:, :, 1:-1, 1:-1].cpu(), marker[:, :, 1:-1, 1:-1])
+
+
+@pytest.mark.parametrize('taps', ['random', 'binomial'])
+@pytest.mark.parametrize('k', [3, 5])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32], ids=['f16', 'f32'])
+def test_blur2d_replicate_autograd(k, dtype, taps):
     """Backward of replicate-pad + fixed blur (SeparableUpsampleWithFixedBlur, convnext_utils.py:250-255): one zero-padded stencil pass
-    over dy + the pad rows / columns folded onto the edges, against stock autograd in fp64 (random, non-symmetric taps)."""
+    over dy + the border row / column rewritten by vfm_replicate_blur_edges, against stock autograd in fp64.  Random (non-symmetric, full-rank)
+    taps take the dense stencil body, the decoder's binomial taps (rank 1) the separable one."""
     V = _ops()
     g = torch.Generator().manual_seed(19)
     p = k // 2
     for shape in ((2, 3, 16, 24), (1, 2, 40, 64), (2, 2, 8, 8)):
-        f = torch.randn(k, k, generator=g) * 0.3
+        if taps == 'random':
+            f = torch.randn(k, k, generator=g) * 0.3
+        else:
+            t = torch.tensor({3: [1., 2., 1.], 5: [1., 4., 6., 4., 1.]}[k])
+            f = torch.outer(t, t) / t.sum() ** 2
         x0 = torch.randn(shape, generator=g).to(dtype)
         dy0 = torch.randn(shape, generator=g).to(dtype)
         xr = x0.double().requires_grad_(True)

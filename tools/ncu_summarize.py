@@ -49,14 +49,17 @@ def launches(path, out, title):
 
 
 def merge(out_json, paths):
+    """paths: `file.json` or `file.json:weight` -- weight = how many layers of the benchmarked step the probe stands for"""
     acc = {}
-    for path in paths:
+    for spec in paths:
+        path, _, wt = spec.partition(':')
+        wt = float(wt) if wt else 1.0
         for k, v in json.load(open(path)).items():
             k = re.sub(r'void |unnamed>::|modconv::|vfm::', '', k)
-            a = acc.setdefault(k, {'launches': 0, 'bytes': 0.0, 'probes': []})
-            a['launches'] += v['launches']
-            a['bytes'] += v['launches'] * v['dram_bytes_per_launch']
-            a['probes'].append(path.split('/')[-1].replace('r02_traffic_', '').replace('.json', ''))
+            a = acc.setdefault(k, {'launches': 0.0, 'bytes': 0.0, 'probes': []})
+            a['launches'] += wt * v['launches']
+            a['bytes'] += wt * v['launches'] * v['dram_bytes_per_launch']
+            a['probes'].append(path.split('/')[-1].replace('r02_traffic_', '').replace('.json', '') + (f' x{wt:g}' if wt != 1 else ''))
     res = {k: {'launches': v['launches'], 'dram_bytes_per_launch': v['bytes'] / v['launches'], 'probes': v['probes']} for k, v in acc.items()}
     json.dump(res, open(out_json, 'w'), indent=1)
 

@@ -24,7 +24,8 @@ probe bwd_256_128 --cin 256 --cout 256 --res 128 --mode bwd
 probe bwd_512_64 --cin 512 --cout 512 --res 64 --mode bwd
 probe up2_256_128 --cin 256 --cout 128 --res 128 --up 2 --mode fused
 probe up2_640_32 --cin 640 --cout 512 --res 32 --up 2 --mode fused
-python tools/ncu_summarize.py merge $O/r02_traffic_train.json $O/r02_traffic_bwd_128_256.json $O/r02_traffic_bwd_256_128.json $O/r02_traffic_bwd_512_64.json $O/r02_traffic_up2_256_128.json $O/r02_traffic_up2_640_32.json
+# weights = layers of the benchmarked step a probe stands for (4 stride-1 layers per shape; 3 up=2 layers, two of them probed)
+python tools/ncu_summarize.py merge $O/r02_traffic_train.json $O/r02_traffic_bwd_128_256.json:4 $O/r02_traffic_bwd_256_128.json:4 $O/r02_traffic_bwd_512_64.json:4 $O/r02_traffic_up2_256_128.json:1.5 $O/r02_traffic_up2_640_32.json:1.5
 rm -f $O/*.ncu-rep
 stamp "reference, stock GPU path (context)"; timeout 420 python tools/ref_gpu_bench.py --steps 3 --warmup 2 --json $O/r02_reference_stock_gpu.json > $O/ref_gpu.log 2>&1; echo "rc=$?"; tail -3 $O/ref_gpu.log | cut -c1-400
 B="python bench.py --steps 1 --warmup 3 --no-secondary --no-cpu-baseline --no-parity"

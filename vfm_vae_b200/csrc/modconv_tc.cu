@@ -47,6 +47,7 @@
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <type_traits>
 
 namespace vfm {
@@ -209,6 +210,8 @@ struct TcArgs {
     Epilogue ep;               // forward: optional fused bias/activation/residual
     int vec_out, vec_side, vec_add;   // 16-byte vector access allowed on out / (aux | residual) / noise
     const float* bias_nc;             // forward: optional per-(sample, channel) bias added before the activation (folded input shift)
+    // ROW3 kernels (3x3, stride 1): column group g has pixel offset r3_dx[g]; its three taps, rows r3_dy0 .. r3_dy0 + 2, are weight slices r3_tb[g][0..2]
+    int r3_dx[3], r3_dy0, r3_tb[3][3];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -295,7 +298,12 @@ template <> __device__ __forceinline__ void store16<float>(float* p, const float
 // row, 64 channels] per image row of the tile) and the weight operand is a per-sample weight [n][Cout][Cin] that carries the
 // modulation (and a folded input affine map) -- no pre-pass over the activations at all.  Only possible without tap shifts: TMA
 // needs the innermost box start 16-byte aligned, which a +-1 pixel shift of an NCHW row is not.
-template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP>
+// ROW3 (fp16 3x3 stride-1 convs, 16 x 16-pixel tiles): the three taps of one kernel COLUMN read the same pixels shifted by whole image rows, and a
+// row of a 16-pixel-wide tile is 16 x 128 B = two 1024-byte swizzle atoms -- so ONE TMA box of (16 + 2) rows x 16 pixels serves all three taps as
+// UMMA descriptors 2 KB apart, and the pixel operand is fetched 3 times per K chunk instead of 9 (36 KB boxes: 108 KB instead of 288 KB; with the nine
+// 16 KB weight tiles 252 KB instead of 432 KB per 64-channel chunk).  The kernel is bound by operand delivery from L2, which this cuts by
+// 42 %.  Two rings instead of one: 3 pixel boxes (Bfull / Bempty) and 5 weight tiles (Afull / Aempty); a box is released after its third tap.
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP, bool ROW3 = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmP,
                                                                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPlo, TcArgs p) {
     constexpr int P_BYTES = NPIX * BK * 2;
@@ -314,6 +322,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     uint64_t* tempty_bar = tfull_bar + 2;                       // [NBUF] accumulators drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     float* s_noise = (float*)(tmem_slot + 4);                   // [2][NPIX] noise of the current / next item's pixels
+    static_assert(!ROW3 || (!SPLIT && !PAIR && !MNP && NPIX == 256), "ROW3 is the fp16 stride-1 3x3 configuration");
+    constexpr int R3_TW = 16, R3_TH = 16, R3_NB = 3, R3_NA = 5;
+    constexpr int R3_PBOX = (R3_TH + 2) * R3_TW * BK * 2;       // 36 KB: 18 rows x 16 pixels x 64 channels
+    static_assert(R3_NB * R3_PBOX + R3_NA * W_BYTES <= NSTAGE * STAGE_BYTES, "ROW3 rings do not fit");
+    uint8_t* r3_b = smem;                                       // pixel-box ring
+    uint8_t* r3_a = smem + R3_NB * R3_PBOX;                     // weight-tile ring
+    uint64_t* r3_bfull = (uint64_t*)(s_noise + 2 * NPIX);       // [3], then bempty [3], afull [5], aempty [5]
+    uint64_t* r3_bempty = r3_bfull + R3_NB;
+    uint64_t* r3_afull = r3_bempty + R3_NB;
+    uint64_t* r3_aempty = r3_afull + R3_NA;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -323,6 +341,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         if (SPLIT) { tma_prefetch_desc(&tmWlo); tma_prefetch_desc(&tmPlo); }
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+        if (ROW3) {
+            for (int i = 0; i < R3_NB; i++) { mbar_init(&r3_bfull[i], 1); mbar_init(&r3_bempty[i], 1); }
+            for (int i = 0; i < R3_NA; i++) { mbar_init(&r3_afull[i], 1); mbar_init(&r3_aempty[i], 1); }
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -351,7 +373,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (ROW3 && lane == 0) {
+            uint32_t ib = 0, ia = 0;
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                int grp, n0, h0, w0, c0;
+                if (!decode(t, grp, n0, h0, w0, c0)) continue;
+                for (int g = 0; g < 3; g++)
+                    for (int kc = 0; kc < p.kchunks; kc++, ib++) {
+                        const int bs = ib % R3_NB;
+                        mbar_wait(&r3_bempty[bs], ((ib / R3_NB) & 1) ^ 1);
+                        mbar_expect_tx(&r3_bfull[bs], R3_PBOX);
+                        tma_load_4d(r3_b + bs * R3_PBOX, &tmP, &r3_bfull[bs], kc * BK, w0 + p.r3_dx[g], h0 + p.r3_dy0, n0);
+                        for (int r = 0; r < 3; r++, ia++) {
+                            const int as = ia % R3_NA;
+                            mbar_wait(&r3_aempty[as], ((ia / R3_NA) & 1) ^ 1);
+                            mbar_expect_tx(&r3_afull[as], W_BYTES);
+                            tma_load_3d(r3_a + as * W_BYTES, &tmW, &r3_afull[as], kc * BK, c0, p.r3_tb[g][r]);
+                        }
+                    }
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 int grp, n0, h0, w0, c0;
@@ -387,7 +428,41 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        if (ROW3 && lane == 0) {
+            constexpr uint32_t idesc3 = make_idesc_f16(CH, NPIX);
+            uint32_t ib = 0, ia = 0, icount = 0;
+            for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
+                int grp, n0, h0, w0, c0;
+                if (!decode(t, grp, n0, h0, w0, c0)) continue;
+                const uint32_t buf = icount % NBUF;
+                mbar_wait(&tempty_bar[buf], ((icount / NBUF) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + buf * ITEM_COLS;
+                uint32_t accum = 0u;
+                for (int g = 0; g < 3; g++)
+                    for (int kc = 0; kc < p.kchunks; kc++, ib++) {
+                        const int bs = ib % R3_NB;
+                        mbar_wait(&r3_bfull[bs], (ib / R3_NB) & 1);
+                        const uint32_t pbase = smem_u32(r3_b + bs * R3_PBOX);
+                        for (int r = 0; r < 3; r++, ia++) {
+                            const int as = ia % R3_NA;
+                            mbar_wait(&r3_afull[as], (ia / R3_NA) & 1);
+                            tc_fence_after();
+                            const uint64_t wdesc = make_kmajor_sw128_desc(smem_u32(r3_a + as * W_BYTES));
+                            const uint64_t pdesc = make_kmajor_sw128_desc(pbase + r * (R3_TW * BK * 2));      // tap row r: the box shifted by one image row = 2 KB
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; kk++) {
+                                umma_f16(acc, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc3, accum);
+                                accum = 1u;
+                            }
+                            umma_commit(&r3_aempty[as]);
+                        }
+                        umma_commit(&r3_bempty[bs]);      // all three taps of this box have been issued: free it once they have read it
+                    }
+                umma_commit(&tfull_bar[buf]);
+                icount++;
+            }
+        } else if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(CH, NPIX) | (MNP ? (1u << 16) : 0u);      // bit 16: B operand MN-major
             uint32_t it = 0, icount = 0;
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
@@ -1214,15 +1289,15 @@ void pick_tile(int Hg, int Wg, int npix, int a_s, int& tw, int& th, int& tn) {
 }
 int ilog2(int v) { int r = 0; while ((1 << r) < v) r++; return r; }
 
-size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 256 + 2 * 256 * sizeof(float); }
+size_t smem_bytes() { return (size_t)192 * 1024 + 1024 + 512 + 2 * 256 * sizeof(float); }      // operand rings + alignment slack + barriers + noise tile
 
-template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP = false>
+template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP = false, bool ROW3 = false>
 int launch_tc(const CUtensorMap* maps, const TcArgs& a, dim3 grid, double flops, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PAIR, NPIX, MNP>;
+    auto kern = conv_tc_kernel<TOut, DGRAD, SPLIT, PAIR, NPIX, MNP, ROW3>;
     size_t smem = smem_bytes();
     VFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KernelTimer timer(DGRAD ? (SPLIT ? "modconv_tc_dgrad_split" : "modconv_tc_dgrad") : (SPLIT ? "modconv_tc_fwd_split" : "modconv_tc_fwd"), stream, flops, 0.0,
-                      "i%do%dh%d%s%s%s%s", a.kchunks * BK, a.Nout, a.out_H, MNP ? "m" : "", PAIR ? "p" : "", (!DGRAD && a.ep.enable) ? "e" : "",
+                      "i%do%dh%d%s%s%s%s", a.kchunks * BK, a.Nout, a.out_H, MNP ? "m" : (ROW3 ? "3" : ""), PAIR ? "p" : "", (!DGRAD && a.ep.enable) ? "e" : "",
                       (DGRAD ? a.aux_sum != nullptr : (a.ep.enable && a.ep.residual)) ? "r" : "");
     kern<<<grid, kConvThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
     return launch_status("modconv conv_tc_kernel");
@@ -1260,6 +1335,23 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
         a.tw = (op.Wa % 256 == 0) ? 256 : (op.Wa % 128 == 0 ? 128 : 64);
         a.th = npix / a.tw; a.tn = 1;
     }
+    // ROW3: fp16 3x3 stride-1 conv whose nine taps form the full {-1,0,1}^2 grid, image a multiple of the 16 x 16 tile
+    bool row3 = false;
+    static const bool row3_enabled = getenv("VFM_ROW3") != nullptr;     // A/B switch while the kernel is being validated
+    if (row3_enabled && !f32 && !pair && !mnp && !ov && a.a_s == 1 && nphases == 1 && a.ph[0].ntaps == 9 && Hg % 16 == 0 && Wg % 16 == 0) {
+        const TcPhase& ph = a.ph[0];
+        int found = 0;
+        for (int g = 0; g < 3; g++) {
+            a.r3_dx[g] = g - 1;
+            for (int r = 0; r < 3; r++) {
+                a.r3_tb[g][r] = -1;
+                for (int t = 0; t < 9; t++) if (ph.dx[t] == g - 1 && ph.dy[t] == r - 1) { a.r3_tb[g][r] = ph.tb[t]; found++; }
+            }
+        }
+        a.r3_dy0 = -1;
+        row3 = (found == 9);
+        if (row3) { a.tw = 16; a.th = 16; a.tn = 1; }
+    }
     if (ov) {
         if (ov->tw * ov->th * ov->tn != npix) { set_error("tcgen05 conv: edge-strip tile does not match the kernel's pixel count"); return VFM_ERR_INVALID; }
         a.tw = ov->tw; a.th = ov->th; a.tn = ov->tn; a.org_w = ov->org_w; a.org_h = ov->org_h;
@@ -1279,7 +1371,7 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
     a.vec_add = 0;
     CUtensorMap maps[4];
     uint64_t pdims[4] = {(uint64_t)op.Cin, (uint64_t)op.Wa, (uint64_t)op.Ha, (uint64_t)op.N};
-    uint32_t pbox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)(a.th * a.a_s), (uint32_t)a.tn};
+    uint32_t pbox[4] = {(uint32_t)BK, (uint32_t)(a.tw * a.a_s), (uint32_t)((a.th + (row3 ? 2 : 0)) * a.a_s), (uint32_t)a.tn};
     uint32_t pstr[4] = {1u, (uint32_t)a.a_s, (uint32_t)a.a_s, 1u};
     uint64_t wdims[3] = {(uint64_t)op.Cin, (uint64_t)op.Nout, (uint64_t)op.ntaps};
     uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)CH, 1u};
@@ -1303,6 +1395,10 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
     const long long total_items = (long long)a.tiles_w * a.tiles_h * ceil_div(op.N, a.tn) * a.ngroups * (op.Nout / CH);
     dim3 grid((unsigned)(total_items < kNumSMs ? total_items : kNumSMs), 1, 1);      // persistent: one CTA per SM
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
+    if (row3) {
+        if (dgrad) return launch_tc<__half, true, false, false, 256, false, true>(maps, a, grid, flops, stream);
+        return launch_tc<__half, false, false, false, 256, false, true>(maps, a, grid, flops, stream);
+    }
     if (!f32) {
         if (dgrad) return launch_tc<__half, true, false, false, 256>(maps, a, grid, flops, stream);
         if (pair && pair256) return launch_tc<__half, false, false, true, 256>(maps, a, grid, flops, stream);

@@ -23,6 +23,9 @@
 // * epilogue: tcgen05.ld 32 lanes x 16 columns (next step's load in flight), demodulation d[n,o], noise (staged per
 //   tile in shared memory), optional fused bias / lrelu|GELU / gain / clamp / layer-scaled residual (inference),
 //   256-bit NCHW stores; side inputs (residual, or x for the dstyles reduction) prefetched in a rolling window.
+// * fp16 3x3 stride-1 convs on images that are a multiple of 16 x 16 (ROW3): the three taps of one kernel column share ONE TMA box of (16 + 2)
+//   rows x 16 pixels -- a tile row is two 1024-byte swizzle atoms, so the taps are UMMA descriptors 2 KB apart -- and the pixel operand is
+//   fetched 3 instead of 9 times per K chunk (two rings: 3 pixel boxes of 36 KB, 5 weight tiles of 16 KB).
 // * up=2 (transposed conv, stride 2; PAIR): 4 sub-pixel phases, each a stride-1 conv over the input grid with the taps
 //   of matching parity.  An item computes the two horizontal phases of one row parity into two accumulators and the
 //   epilogue interleaves them, so stores to the (2H+1) x (2W+1) intermediate are contiguous vectors.
@@ -47,7 +50,6 @@
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
-#include <cstdlib>
 #include <type_traits>
 
 namespace vfm {
@@ -1337,8 +1339,7 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
     }
     // ROW3: fp16 3x3 stride-1 conv whose nine taps form the full {-1,0,1}^2 grid, image a multiple of the 16 x 16 tile
     bool row3 = false;
-    static const bool row3_enabled = getenv("VFM_ROW3") != nullptr;     // A/B switch while the kernel is being validated
-    if (row3_enabled && !f32 && !pair && !mnp && !ov && a.a_s == 1 && nphases == 1 && a.ph[0].ntaps == 9 && Hg % 16 == 0 && Wg % 16 == 0) {
+    if (!f32 && !pair && !mnp && !ov && a.a_s == 1 && nphases == 1 && a.ph[0].ntaps == 9 && Hg % 16 == 0 && Wg % 16 == 0) {
         const TcPhase& ph = a.ph[0];
         int found = 0;
         for (int g = 0; g < 3; g++) {

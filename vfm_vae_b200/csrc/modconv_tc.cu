@@ -50,6 +50,7 @@
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <type_traits>
 
 namespace vfm {
@@ -212,8 +213,12 @@ struct TcArgs {
     Epilogue ep;               // forward: optional fused bias/activation/residual
     int vec_out, vec_side, vec_add;   // 16-byte vector access allowed on out / (aux | residual) / noise
     const float* bias_nc;             // forward: optional per-(sample, channel) bias added before the activation (folded input shift)
-    // ROW3 kernels (3x3, stride 1): column group g has pixel offset r3_dx[g]; its three taps, rows r3_dy0 .. r3_dy0 + 2, are weight slices r3_tb[g][0..2]
-    int r3_dx[3], r3_dy0, r3_tb[3][3];
+    // ROW3 kernels: per phase group (PAIR: py; otherwise only [0]) the taps sorted into COLUMN groups -- taps of one pixel offset dx share ONE
+    // pixel box that starts at row h0 + dy0 and is 2 rows taller than the tile; tap m of a group accumulates into phase sub[m], reads the box
+    // from image row row[m] (0..2) on, and multiplies weight slice tb[m]
+    struct ColGroup { int dx, nm; int sub[4], row[4], tb[4]; };
+    int cg_n[2], cg_dy0[2];
+    ColGroup cg[2][3];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
     uint64_t* tempty_bar = tfull_bar + 2;                       // [NBUF] accumulators drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     float* s_noise = (float*)(tmem_slot + 4);                   // [2][NPIX] noise of the current / next item's pixels
-    static_assert(!ROW3 || (!SPLIT && !PAIR && !MNP && NPIX == 256), "ROW3 is the fp16 stride-1 3x3 configuration");
+    static_assert(!ROW3 || (!SPLIT && !MNP && NPIX == 256), "ROW3 is an fp16, 256-pixel-tile configuration");
     constexpr int R3_TW = 16, R3_TH = 16, R3_NB = 3, R3_NA = 5;
     constexpr int R3_PBOX = (R3_TH + 2) * R3_TW * BK * 2;       // 36 KB: 18 rows x 16 pixels x 64 channels
     static_assert(R3_NB * R3_PBOX + R3_NA * W_BYTES <= NSTAGE * STAGE_BYTES, "ROW3 rings do not fit");
@@ -380,19 +385,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
             for (int t = blockIdx.x; t < total_items; t += gridDim.x) {
                 int grp, n0, h0, w0, c0;
                 if (!decode(t, grp, n0, h0, w0, c0)) continue;
-                for (int g = 0; g < 3; g++)
+                for (int g = 0; g < p.cg_n[grp]; g++) {
+                    const TcArgs::ColGroup& cg = p.cg[grp][g];
                     for (int kc = 0; kc < p.kchunks; kc++, ib++) {
                         const int bs = ib % R3_NB;
                         mbar_wait(&r3_bempty[bs], ((ib / R3_NB) & 1) ^ 1);
                         mbar_expect_tx(&r3_bfull[bs], R3_PBOX);
-                        tma_load_4d(r3_b + bs * R3_PBOX, &tmP, &r3_bfull[bs], kc * BK, w0 + p.r3_dx[g], h0 + p.r3_dy0, n0);
-                        for (int r = 0; r < 3; r++, ia++) {
+                        tma_load_4d(r3_b + bs * R3_PBOX, &tmP, &r3_bfull[bs], kc * BK, w0 + cg.dx, h0 + p.cg_dy0[grp], n0);
+                        for (int m = 0; m < cg.nm; m++, ia++) {
                             const int as = ia % R3_NA;
                             mbar_wait(&r3_aempty[as], ((ia / R3_NA) & 1) ^ 1);
                             mbar_expect_tx(&r3_afull[as], W_BYTES);
-                            tma_load_3d(r3_a + as * W_BYTES, &tmW, &r3_afull[as], kc * BK, c0, p.r3_tb[g][r]);
+                            tma_load_3d(r3_a + as * W_BYTES, &tmW, &r3_afull[as], kc * BK, c0, cg.tb[m]);
                         }
                     }
+                }
             }
         } else if (lane == 0) {
             uint32_t it = 0;
@@ -440,27 +447,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
                 mbar_wait(&tempty_bar[buf], ((icount / NBUF) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + buf * ITEM_COLS;
-                uint32_t accum = 0u;
-                for (int g = 0; g < 3; g++)
+                uint32_t accum[2] = {0u, 0u};             // per phase accumulator: the first MMA into it overwrites
+                for (int g = 0; g < p.cg_n[grp]; g++) {
+                    const TcArgs::ColGroup& cg = p.cg[grp][g];
                     for (int kc = 0; kc < p.kchunks; kc++, ib++) {
                         const int bs = ib % R3_NB;
                         mbar_wait(&r3_bfull[bs], (ib / R3_NB) & 1);
                         const uint32_t pbase = smem_u32(r3_b + bs * R3_PBOX);
-                        for (int r = 0; r < 3; r++, ia++) {
+                        for (int m = 0; m < cg.nm; m++, ia++) {
                             const int as = ia % R3_NA;
                             mbar_wait(&r3_afull[as], (ia / R3_NA) & 1);
                             tc_fence_after();
+                            const int sub = cg.sub[m];
                             const uint64_t wdesc = make_kmajor_sw128_desc(smem_u32(r3_a + as * W_BYTES));
-                            const uint64_t pdesc = make_kmajor_sw128_desc(pbase + r * (R3_TW * BK * 2));      // tap row r: the box shifted by one image row = 2 KB
+                            const uint64_t pdesc = make_kmajor_sw128_desc(pbase + cg.row[m] * (R3_TW * BK * 2));   // the box from image row row[m] on: 2 KB per row
 #pragma unroll
                             for (int kk = 0; kk < BK / 16; kk++) {
-                                umma_f16(acc, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc3, accum);
-                                accum = 1u;
+                                umma_f16(acc + sub * SUB_COLS, wdesc + (uint64_t)(2 * kk), pdesc + (uint64_t)(2 * kk), idesc3, accum[sub]);
+                                accum[sub] = 1u;
                             }
                             umma_commit(&r3_aempty[as]);
                         }
-                        umma_commit(&r3_bempty[bs]);      // all three taps of this box have been issued: free it once they have read it
+                        umma_commit(&r3_bempty[bs]);      // every tap of this box has been issued: free it once they have read it
                     }
+                }
                 umma_commit(&tfull_bar[buf]);
                 icount++;
             }
@@ -1337,20 +1347,35 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
         a.tw = (op.Wa % 256 == 0) ? 256 : (op.Wa % 128 == 0 ? 128 : 64);
         a.th = npix / a.tw; a.tn = 1;
     }
-    // ROW3: fp16 3x3 stride-1 conv whose nine taps form the full {-1,0,1}^2 grid, image a multiple of the 16 x 16 tile
+    // ROW3 (column groups): fp16, stride-1 pixel operand, image a multiple of the 16 x 16 tile; the taps of every phase group must sort into <= 3
+    // pixel offsets dx with <= 4 taps each whose rows span <= 3 image rows.  Covers the 3x3 stride-1 conv / data gradient (3 groups x 3 taps) and
+    // the paired up=2 phases (py = 0: the box of dx = 0 serves both row taps of BOTH horizontal phases, 2 boxes instead of 6 pixel tiles).
     bool row3 = false;
-    if (!f32 && !pair && !mnp && !ov && a.a_s == 1 && nphases == 1 && a.ph[0].ntaps == 9 && Hg % 16 == 0 && Wg % 16 == 0) {
-        const TcPhase& ph = a.ph[0];
-        int found = 0;
-        for (int g = 0; g < 3; g++) {
-            a.r3_dx[g] = g - 1;
-            for (int r = 0; r < 3; r++) {
-                a.r3_tb[g][r] = -1;
-                for (int t = 0; t < 9; t++) if (ph.dx[t] == g - 1 && ph.dy[t] == r - 1) { a.r3_tb[g][r] = ph.tb[t]; found++; }
+    static const bool pair_colgroups = getenv("VFM_PAIR_COLGROUPS") != nullptr;      // A/B switch while the paired variant is validated
+    if (!f32 && !mnp && !ov && a.a_s == 1 && Hg % 16 == 0 && Wg % 16 == 0 && (pair ? (pair256 && pair_colgroups) : (nphases == 1 && a.ph[0].ntaps == 9))) {
+        row3 = true;
+        const int ngrp = pair ? 2 : 1, nsub = pair ? 2 : 1;
+        for (int grp = 0; grp < ngrp && row3; grp++) {
+            int dy0 = 1 << 30, ntap = 0;
+            for (int sub = 0; sub < nsub; sub++) for (int t = 0; t < a.ph[grp * nsub + sub].ntaps; t++) { dy0 = min(dy0, a.ph[grp * nsub + sub].dy[t]); ntap++; }
+            a.cg_dy0[grp] = dy0;
+            a.cg_n[grp] = 0;
+            int placed = 0;
+            for (int sub = 0; sub < nsub && row3; sub++) {
+                const TcPhase& ph = a.ph[grp * nsub + sub];
+                for (int t = 0; t < ph.ntaps && row3; t++) {
+                    int g = 0;
+                    while (g < a.cg_n[grp] && a.cg[grp][g].dx != ph.dx[t]) g++;
+                    if (g == a.cg_n[grp]) { if (g == 3) { row3 = false; break; } a.cg[grp][g].dx = ph.dx[t]; a.cg[grp][g].nm = 0; a.cg_n[grp]++; }
+                    TcArgs::ColGroup& cg = a.cg[grp][g];
+                    const int row = ph.dy[t] - dy0;
+                    if (cg.nm == 4 || row > 2) { row3 = false; break; }
+                    cg.sub[cg.nm] = sub; cg.row[cg.nm] = row; cg.tb[cg.nm] = ph.tb[t]; cg.nm++;
+                    placed++;
+                }
             }
+            if (placed != ntap) row3 = false;
         }
-        a.r3_dy0 = -1;
-        row3 = (found == 9);
         if (row3) { a.tw = 16; a.th = 16; a.tn = 1; }
     }
     if (ov) {
@@ -1397,6 +1422,7 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
     dim3 grid((unsigned)(total_items < kNumSMs ? total_items : kNumSMs), 1, 1);      // persistent: one CTA per SM
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
     if (row3) {
+        if (pair) return launch_tc<__half, false, false, true, 256, false, true>(maps, a, grid, flops, stream);
         if (dgrad) return launch_tc<__half, true, false, false, 256, false, true>(maps, a, grid, flops, stream);
         return launch_tc<__half, false, false, false, 256, false, true>(maps, a, grid, flops, stream);
     }

@@ -50,7 +50,6 @@
 // output channel), epilogue scale = d[n,o].
 #include "modconv_common.cuh"
 #include <cuda.h>
-#include <cstdlib>
 #include <type_traits>
 
 namespace vfm {
@@ -1348,11 +1347,12 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
         a.th = npix / a.tw; a.tn = 1;
     }
     // ROW3 (column groups): fp16, stride-1 pixel operand, image a multiple of the 16 x 16 tile; the taps of every phase group must sort into <= 3
-    // pixel offsets dx with <= 4 taps each whose rows span <= 3 image rows.  Covers the 3x3 stride-1 conv / data gradient (3 groups x 3 taps) and
-    // the paired up=2 phases (py = 0: the box of dx = 0 serves both row taps of BOTH horizontal phases, 2 boxes instead of 6 pixel tiles).
+    // pixel offsets dx with <= 4 taps each whose rows span <= 3 image rows: the 3x3 stride-1 conv / data gradient (3 groups x 3 taps).
+    // The tables (and the kernel) also describe the paired up=2 phases -- py = 0: the box of dx = 0 serves both row taps of BOTH horizontal
+    // phases, 2 boxes instead of 6 pixel tiles -- and that variant passes the whole GPU suite, but it measured SLOWER than the plain paired
+    // kernel (512->256: 1.19 -> 1.26 ms, 256->128: 1.69 -> 1.74 ms per layer incl. pre-pass and blur), so up=2 is not routed here.
     bool row3 = false;
-    static const bool pair_colgroups = getenv("VFM_PAIR_COLGROUPS") != nullptr;      // A/B switch while the paired variant is validated
-    if (!f32 && !mnp && !ov && a.a_s == 1 && Hg % 16 == 0 && Wg % 16 == 0 && (pair ? (pair256 && pair_colgroups) : (nphases == 1 && a.ph[0].ntaps == 9))) {
+    if (!f32 && !mnp && !ov && !pair && a.a_s == 1 && Hg % 16 == 0 && Wg % 16 == 0 && nphases == 1 && a.ph[0].ntaps == 9) {
         row3 = true;
         const int ngrp = pair ? 2 : 1, nsub = pair ? 2 : 1;
         for (int grp = 0; grp < ngrp && row3; grp++) {
@@ -1422,7 +1422,6 @@ int run_tc_conv_one(bool f32, bool dgrad, const TcOperands& op, TcArgs a, int np
     dim3 grid((unsigned)(total_items < kNumSMs ? total_items : kNumSMs), 1, 1);      // persistent: one CTA per SM
     const double flops = 2.0 * op.N * taps_px * (double)op.Nout * op.Cin;
     if (row3) {
-        if (pair) return launch_tc<__half, false, false, true, 256, false, true>(maps, a, grid, flops, stream);
         if (dgrad) return launch_tc<__half, true, false, false, 256, false, true>(maps, a, grid, flops, stream);
         return launch_tc<__half, false, false, false, 256, false, true>(maps, a, grid, flops, stream);
     }

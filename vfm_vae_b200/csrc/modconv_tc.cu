@@ -308,7 +308,9 @@ template <> __device__ __forceinline__ void store16<float>(float* p, const float
 // row of a 16-pixel-wide tile is 16 x 128 B = two 1024-byte swizzle atoms -- so ONE TMA box of (16 + 2) rows x 16 pixels serves all three taps as
 // UMMA descriptors 2 KB apart, and the pixel operand is fetched 3 times per K chunk instead of 9 (36 KB boxes: 108 KB instead of 288 KB; with the nine
 // 16 KB weight tiles 252 KB instead of 432 KB per 64-channel chunk).  The kernel is bound by operand delivery from L2, which this cuts by
-// 42 %.  Two rings instead of one: 3 pixel boxes (Bfull / Bempty) and 5 weight tiles (Afull / Aempty); a box is released after its third tap.
+// 42 %.  Two rings instead of one: 3 pixel boxes (Bfull / Bempty) and 5 weight tiles (Afull / Aempty); a box is released after its last tap.
+// The taps come as COLUMN-GROUP tables (TcArgs::cg: per pixel offset dx the taps with their box row, weight slice and target accumulator), built and
+// checked on the host (run_tc_conv_one).
 template <class TOut, bool DGRAD, bool SPLIT, bool PAIR, int NPIX, bool MNP, bool ROW3 = false>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmP,
                                                                   const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmPlo, TcArgs p) {
